@@ -1,0 +1,210 @@
+/*
+ * msi_b200.h -- C ABI of the Blackwell-native multi-sphere-image (MSI) inference path.
+ *
+ * The reference (brownvc/matryodshka @ 831c407) is pure Python/TensorFlow and has
+ * NO native boundary of its own: the path sits behind the
+ * Python call surface matryodshka.msi.MSI / geometry.projector.  This header is
+ * the boundary a binding for that surface needs: each entry point replaces the
+ * graph of stock TF ops behind one reference function, cited as file:line of
+ * /root/reference.  INTEGRATION.md shows the ctypes stub the Python side uses.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (cudaMalloc'd / torch CUDA storage) unless
+ *     the parameter name ends in _host; tensors are dense NHWC float32 as in the
+ *     reference (images [B,H,W,3], PSV [B,H,W,6P], RGBA layers [B,H,W,L,4]);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ *     only enqueue work, they never synchronise; reentrant per stream;
+ *   - return value: 0 = MSI_OK, <0 = error (msi_last_error() gives the text);
+ *     asynchronous CUDA faults surface at the caller's next synchronisation;
+ *   - no entry point falls back to the CPU: without a CUDA device every compute
+ *     call returns MSI_ERR_CUDA.
+ */
+#ifndef MSI_B200_H_
+#define MSI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSI_B200_ABI_VERSION 1
+
+#define MSI_OK 0
+#define MSI_ERR_INVALID_ARG (-1)
+#define MSI_ERR_CUDA (-2)
+#define MSI_ERR_UNSUPPORTED (-3)
+#define MSI_ERR_STATE (-4)
+
+/* image element types accepted by msi_psv_build */
+#define MSI_IMG_F32 0 /* float32 in [0,1] (or already in [-1,1] when preprocess=0) */
+#define MSI_IMG_U8 1  /* uint8 in [0,255]: x/255 as tf.image.convert_image_dtype  */
+
+/* convolution back ends of the net (both are hand-written kernels of this library) */
+#define MSI_CONV_TCGEN05 0 /* tcgen05.mma + TMA implicit GEMM, accumulators in TMEM   */
+#define MSI_CONV_SIMT 1    /* fp32 CUDA-core implicit GEMM: bring-up / cross-check    */
+
+/* operand precision of the tcgen05 back end */
+#define MSI_PREC_FP16X3 0 /* fp16 hi/lo split, 3 MMAs per product: ~fp32 accuracy (default; meets 1e-3) */
+#define MSI_PREC_FP16 1   /* single fp16 MMA: 3x fewer MMAs, ~7e-3 max-abs on the net output  */
+
+int msi_b200_abi_version(void);
+const char* msi_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (all entry
+ * points, all threads).  bench.py reports the delta over its timed region. */
+uint64_t msi_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 1 -- spherical plane-sweep volume
+ * replaces: MSI.format_network_input (matryodshka/msi.py:1094-1130) ->
+ *   projector.ods_sphere_sweep / sweep_one (geometry/projector.py:129-170,209-211) ->
+ *   spherical.lat_long_grid (:42-44), backproject_spherical (:116-129),
+ *   projector.apply_pose (:275-291), spherical.project_ods (:170-233),
+ *   sampling.bilinear_wrapper2 / resample (geometry/sampling.py:59-67,135-197),
+ *   and MSI.preprocess_image (msi.py:1163-1171) when preprocess=1.
+ *
+ * ref, src      [B,H,W,3] images (eye 0 = ref, order +1; eye 1 = src, order -1)
+ * poses         [B,2,16]  row-major 4x4 `pose_eye . ref_pose_inv` per frame and eye
+ * baselines     [B]       ODS baseline radius = intrinsics[b,0,0] (data_loader.py:160)
+ * depths        [P]       sphere radii, far -> near (MSI.inv_depths, msi.py:1196)
+ * cos_s,sin_s   [W], cos_t,sin_t [H]: cos/sin of the pixel-centre longitudes /
+ *               latitudes of lat_long_grid (the "ERP-coord tables")
+ * out_f32       [B,H,W,6P] float32 PSV, channel = eye*3P + p*3 + rgb   (may be NULL)
+ * out_hi,out_lo [B,H,W,c_stride] fp16 hi/lo split of the PSV scaled by
+ *               MSI_ACT_SCALE, the operand format of the conv net (may be NULL);
+ *               c_stride >= 6P, channels [6P, c_stride) are zero-filled.
+ * ------------------------------------------------------------------------- */
+#define MSI_ACT_SCALE 16.0f
+#define MSI_WEIGHT_SCALE 1024.0f
+
+int msi_psv_build(const void* ref, const void* src, int img_dtype, int preprocess,
+                  const float* poses, const float* baselines, const float* depths,
+                  const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                  int B, int H, int W, int P,
+                  float* out_f32, void* out_hi, void* out_lo, int c_stride, void* stream);
+
+/* Sample coordinates only (spherical.project_ods, spherical.py:170-233, after
+ * backproject + apply_pose): uv [B,2,P,H,W,2] (x=u, y=v) and valid [B,2,P,H,W]
+ * (uint8, 0 where disc < 0 and the sample snaps to pixel (1,1), :226-229). */
+int msi_sweep_coords(const float* poses, const float* baselines, const float* depths,
+                     const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                     int B, int H, int W, int P, float* uv, uint8_t* valid, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 2 1/2 -- RGBA layer assembly, `blend_psv`
+ * replaces: MSI.infer_msi layer_prediction block (msi.py:130-147).
+ * pred [B,H,W,2L] net output in (-1,1); PSV either float32 (psv_f32) or the
+ * fp16 hi/lo pair (psv_f32 == NULL), channel stride c_stride.
+ * rgba [B,H,W,L,4]; blend_weights / alphas [B,H,W,L] optional (NULL to skip).
+ * ------------------------------------------------------------------------- */
+int msi_rgba_assemble(const float* pred, const float* psv_f32, const void* psv_hi, const void* psv_lo,
+                      int c_stride, int B, int H, int W, int L,
+                      float* rgba, float* blend_weights, float* alphas, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 3 -- reproject the L spheres to the target position and over-composite
+ * replaces: MSI.msi_render_equirect_view (msi.py:407-429) and
+ *   msi_render_equirect_depth (:384-405) in ONE pass ->
+ *   projector.projective_forward_sphere (projector.py:34-62),
+ *   spherical.intersect_sphere (spherical.py:268-326), project_spherical
+ *   (:235-246), theta_phi_to_pixels (:54-68), sampling.resample,
+ *   projector.over_composite (:246-265), over_composite_depth (:225-244),
+ *   MSI.deprocess_image / deprocess_depth_image (msi.py:1173-1194).
+ *
+ * rgba        [B,H,W,L,4]
+ * tgt_pose_rt [B,16] row-major [R|t]; tgt_pos [B,3] target offset (x,y,z)
+ * depths      [L]
+ * out_rgb     [B,H,W,3] float32 in [-1,1]       (NULL to skip)
+ * out_depth   [B,H,W,3] float32 in [0,1)        (NULL to skip)
+ * out_rgb_u8 / out_depth_u8 [B,H,W,3] uint8, convert_image_dtype semantics
+ * ------------------------------------------------------------------------- */
+int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                         const float* depths,
+                         const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                         int B, int H, int W, int L,
+                         float* out_rgb, float* out_depth, uint8_t* out_rgb_u8, uint8_t* out_depth_u8,
+                         void* stream);
+
+/* Sample coordinates only (spherical.intersect_sphere): uv [B,L,H,W,2]. */
+int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
+                                const float* cos_s, const float* sin_s, const float* cos_t,
+                                const float* sin_t, int B, int H, int W, int L, float* uv, void* stream);
+
+/* Reprojected layers without compositing (MSI.msi_render_equirect_view_single,
+ * msi.py:431-452): out [L,B,H,W,4]. */
+int msi_project_layers(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                       const float* depths,
+                       const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                       int B, int H, int W, int L, float* out, void* stream);
+
+/* sampling.resample (sampling.py:135-197): image [N,H,W,C], coords [N,h,w,2] -> out [N,h,w,C];
+ * bilinear, floor-mod wrap-around in x and y. */
+int msi_resample(const float* image, const float* coords, int N, int H, int W, int C, int h, int w,
+                 float* out, void* stream);
+
+/* projector.over_composite (:246-265) / over_composite_depth (:225-244):
+ * layers [L,B,H,W,4] back to front -> out [B,H,W,3]. */
+int msi_over_composite(const float* layers, int L, int B, int H, int W, int depth_mode, float* out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 2 -- the conv net
+ * replaces: nets.msi_coord_train_net (matryodshka/nets.py:471-515): 14 coord
+ * convs 3x3 + LayerNorm + ReLU, 3 transposed convs 4x4 s2 + LayerNorm + ReLU,
+ * 1x1 head + bias + tanh (slim.conv2d / conv2d_transpose / layer_norm).
+ *
+ * A net object owns nothing but small host-side bookkeeping and TMA descriptors;
+ * device memory comes from the caller (workspace for activations, arena for
+ * packed weights) so that the host framework's allocator stays in charge.
+ * ------------------------------------------------------------------------- */
+typedef struct msi_net msi_net;
+
+int msi_net_create(msi_net** net, int H, int W, int c_in, int c_out, int ngf, int max_batch,
+                   int conv_impl, int precision);
+void msi_net_destroy(msi_net* net);
+size_t msi_net_workspace_bytes(const msi_net* net);
+size_t msi_net_arena_bytes(const msi_net* net);
+int msi_net_input_c_stride(const msi_net* net);
+int msi_net_bind(msi_net* net, void* workspace, size_t workspace_bytes, void* arena, size_t arena_bytes);
+
+/* Pack one layer's parameters from the TF checkpoint layout into
+ * the arena: conv weights HWIO [k,k,Cin(+1 coord),Cout], deconv [k,k,Cout,Cin],
+ * LayerNorm gamma/beta [Cout], head bias [Cout] (NULL where absent). */
+int msi_net_load_layer(msi_net* net, const char* scope, const float* weights, const float* gamma,
+                       const float* beta, const float* bias, void* stream);
+
+/* Forward B <= max_batch frames.  Input is the PSV either as float32
+ * [B,H,W,c_in] (in_f32) or as the fp16 hi/lo pair written by msi_psv_build
+ * (in_f32 == NULL; channel stride msi_net_input_c_stride()).  pred [B,H,W,c_out]. */
+int msi_net_forward(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                    float* pred, void* stream);
+
+/* The workspace copy of the network input (fp16 hi/lo, channel stride
+ * msi_net_input_c_stride()): let msi_psv_build write the PSV there and pass the
+ * same pointers to msi_net_forward to skip the copy. */
+int msi_net_input_buffers(msi_net* net, void** hi, void** lo);
+
+/* Test hook: copy the post-LayerNorm+ReLU activation of a layer (fp16 hi+lo
+ * recombined, un-scaled) into out [B,h,w,C] float32, after a forward. */
+int msi_net_read_activation(msi_net* net, const char* scope, int B, float* out, void* stream);
+/* Test hook: raw (pre-LayerNorm) conv output of a layer, [B,h,w,C] float32. */
+int msi_net_read_raw(msi_net* net, const char* scope, int B, float* out, void* stream);
+int msi_net_num_launches_per_forward(const msi_net* net);
+
+/* Measurement hooks (bench.py): the same forward with CUDA events recorded on
+ * `stream` around every conv launch and every LayerNorm group.  Synchronises the
+ * stream; conv_ms_host / ln_ms_host are HOST arrays of msi_net_num_layers()
+ * floats.  msi_net_layer_flops = algorithmic FLOPs of layer i for one frame
+ * (2 x MACs, coord channels counted: SURVEY.md 8a a10 table). */
+int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
+                             int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host);
+int msi_net_num_layers(const msi_net* net);
+const char* msi_net_layer_scope(const msi_net* net, int i);
+double msi_net_layer_flops(const msi_net* net, int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSI_B200_H_ */

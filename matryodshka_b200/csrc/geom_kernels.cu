@@ -1,0 +1,566 @@
+// Stage 1 (plane-sweep volume), stage 2 1/2 (RGBA assembly) and stage 3 (reprojection +
+// over-composite) of the MSI inference path.  HBM-bound gather / blend kernels.
+// Compiled with -fmad=false (see geom_device.cuh).
+#include "geom_device.cuh"
+
+namespace msi {
+
+// ------------------------------------------------------------------------------------------
+// K1  psv_build: one thread per (pixel, eye, plane); coordinates live in registers, the four
+// bilinear taps come from the (L1/L2-resident, 2.5 MB) source image, and the 3 output floats
+// of 256 consecutive threads are staged in shared memory so that the block writes 3 KB of
+// contiguous PSV with 128-bit stores (float32) / 64-bit-per-8-channels stores (fp16 hi/lo).
+// ------------------------------------------------------------------------------------------
+struct PsvParams {
+    const void* img[2];
+    const float* poses;      // [B,2,16]
+    const float* baselines;  // [B]
+    const float* depths;     // [P]
+    const float *cos_s, *sin_s, *cos_t, *sin_t;
+    int B, H, W, P;
+    int preprocess;
+    float* out_f32;
+    __half* out_hi;
+    __half* out_lo;
+    int c_stride;
+    ErpConsts k;
+};
+
+template <typename T>
+__device__ __forceinline__ float load_img(const T* img, size_t off, int preprocess);
+template <>
+__device__ __forceinline__ float load_img<float>(const float* img, size_t off, int preprocess) {
+    float v = __ldg(img + off);
+    return preprocess ? (v * 2.0f - 1.0f) : v;
+}
+template <>
+__device__ __forceinline__ float load_img<uint8_t>(const uint8_t* img, size_t off, int preprocess) {
+    // tf.image.convert_image_dtype(uint8 -> float32): cast * (1.0 / 255)
+    float v = (float)__ldg(img + off) * (float)(1.0 / 255);
+    return preprocess ? (v * 2.0f - 1.0f) : v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) psv_build_kernel(PsvParams p) {
+    __shared__ __align__(16) float stage[768];
+    const long long total = (long long)p.B * p.H * p.W * 2 * p.P;
+    const long long base = (long long)blockIdx.x * 256;
+    const long long idx = base + threadIdx.x;
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    long long pix = 0;
+    int e = 0, pl = 0;
+    if (idx < total) {
+        pl = (int)(idx % p.P);
+        e = (int)((idx / p.P) & 1);
+        pix = idx / (2 * p.P);
+        const int j = (int)(pix % p.W);
+        const int i = (int)((pix / p.W) % p.H);
+        const int b = (int)(pix / ((long long)p.W * p.H));
+        float u, v;
+        sweep_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                 __ldg(p.depths + pl), p.poses + (b * 2 + e) * 16, e == 0 ? 1.0f : -1.0f,
+                 __ldg(p.baselines + b), p.k, u, v);
+        const Bilinear s = bilinear_setup(u, v, p.W, p.H);
+        const T* img = reinterpret_cast<const T*>(p.img[e]);
+        const size_t ib = (size_t)b * p.H * p.W;
+        const size_t oa = (ib + (size_t)s.y0 * p.W + s.x0) * 3;
+        const size_t ob = (ib + (size_t)s.y0 * p.W + s.x1) * 3;
+        const size_t oc = (ib + (size_t)s.y1 * p.W + s.x0) * 3;
+        const size_t od = (ib + (size_t)s.y1 * p.W + s.x1) * 3;
+        r0 = blend4(s, load_img<T>(img, oa + 0, p.preprocess), load_img<T>(img, ob + 0, p.preprocess),
+                    load_img<T>(img, oc + 0, p.preprocess), load_img<T>(img, od + 0, p.preprocess));
+        r1 = blend4(s, load_img<T>(img, oa + 1, p.preprocess), load_img<T>(img, ob + 1, p.preprocess),
+                    load_img<T>(img, oc + 1, p.preprocess), load_img<T>(img, od + 1, p.preprocess));
+        r2 = blend4(s, load_img<T>(img, oa + 2, p.preprocess), load_img<T>(img, ob + 2, p.preprocess),
+                    load_img<T>(img, oc + 2, p.preprocess), load_img<T>(img, od + 2, p.preprocess));
+    }
+    const bool dense = (base + 256 <= total) && (p.c_stride == 6 * p.P);
+    if (dense) {
+        // thread idx owns floats [3*idx, 3*idx+3) of the dense [B,H,W,6P] tensor
+        stage[3 * threadIdx.x + 0] = r0;
+        stage[3 * threadIdx.x + 1] = r1;
+        stage[3 * threadIdx.x + 2] = r2;
+        __syncthreads();
+        const size_t fbase = (size_t)base * 3;  // multiple of 768
+        if (p.out_f32 != nullptr && threadIdx.x < 192) {
+            const float4 q = reinterpret_cast<const float4*>(stage)[threadIdx.x];
+            reinterpret_cast<float4*>(p.out_f32 + fbase)[threadIdx.x] = q;
+        }
+        if (p.out_hi != nullptr && threadIdx.x < 96) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_half(stage[8 * threadIdx.x + q] * MSI_ACT_SCALE, hi[q], lo[q]);
+            reinterpret_cast<uint4*>(p.out_hi + fbase)[threadIdx.x] = *reinterpret_cast<const uint4*>(hi);
+            if (p.out_lo != nullptr)
+                reinterpret_cast<uint4*>(p.out_lo + fbase)[threadIdx.x] = *reinterpret_cast<const uint4*>(lo);
+        }
+    } else if (idx < total) {
+        const int ch = e * 3 * p.P + pl * 3;
+        if (p.out_f32 != nullptr) {
+            float* o = p.out_f32 + (size_t)pix * 6 * p.P + ch;
+            o[0] = r0;
+            o[1] = r1;
+            o[2] = r2;
+        }
+        if (p.out_hi != nullptr) {
+            const size_t o = (size_t)pix * p.c_stride + ch;
+            const float r[3] = {r0, r1, r2};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                __half hi, lo;
+                split_half(r[q] * MSI_ACT_SCALE, hi, lo);
+                p.out_hi[o + q] = hi;
+                if (p.out_lo != nullptr) p.out_lo[o + q] = lo;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sweep_coords_kernel(PsvParams p, float* uv, uint8_t* valid) {
+    // output order [B,2,P,H,W]: thread per element, W fastest
+    const long long total = (long long)p.B * 2 * p.P * p.H * p.W;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % p.W);
+    const int i = (int)((idx / p.W) % p.H);
+    const int pl = (int)((idx / ((long long)p.W * p.H)) % p.P);
+    const int e = (int)((idx / ((long long)p.W * p.H * p.P)) & 1);
+    const int b = (int)(idx / ((long long)p.W * p.H * p.P * 2));
+    float u, v;
+    const bool ok = sweep_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                             __ldg(p.depths + pl), p.poses + (b * 2 + e) * 16, e == 0 ? 1.0f : -1.0f,
+                             __ldg(p.baselines + b), p.k, u, v);
+    uv[2 * idx + 0] = u;
+    uv[2 * idx + 1] = v;
+    if (valid != nullptr) valid[idx] = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  rgba_assemble: thread per (pixel, layer); lanes = layers, so pred / PSV reads and the
+// float4 RGBA store of a warp are contiguous.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rgba_assemble_kernel(const float* __restrict__ pred, const float* __restrict__ psv_f32,
+                     const __half* __restrict__ psv_hi, const __half* __restrict__ psv_lo, int c_stride,
+                     long long npix, int L, float4* __restrict__ rgba, float* __restrict__ bw_out,
+                     float* __restrict__ al_out) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= npix * L) return;
+    const long long pix = idx / L;
+    const int l = (int)(idx % L);
+    const float w = (__ldg(pred + pix * 2 * L + l) + 1.0f) / 2.0f;
+    const float al = (__ldg(pred + pix * 2 * L + L + l) + 1.0f) / 2.0f;
+    float fg[3], bg[3];
+    if (psv_f32 != nullptr) {
+        const float* f = psv_f32 + pix * 6 * L + 3 * l;
+        const float* g = psv_f32 + pix * 6 * L + 3 * (L + l);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            fg[c] = __ldg(f + c);
+            bg[c] = __ldg(g + c);
+        }
+    } else {
+        const size_t f = (size_t)pix * c_stride + 3 * l;
+        const size_t g = (size_t)pix * c_stride + 3 * (L + l);
+        const float inv = 1.0f / MSI_ACT_SCALE;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            fg[c] = (__half2float(psv_hi[f + c]) + __half2float(psv_lo[f + c])) * inv;
+            bg[c] = (__half2float(psv_hi[g + c]) + __half2float(psv_lo[g + c])) * inv;
+        }
+    }
+    const float omw = 1.0f - w;
+    float4 o;
+    o.x = w * fg[0] + omw * bg[0];
+    o.y = w * fg[1] + omw * bg[1];
+    o.z = w * fg[2] + omw * bg[2];
+    o.w = al;
+    rgba[idx] = o;
+    if (bw_out != nullptr) bw_out[idx] = w;
+    if (al_out != nullptr) al_out[idx] = al;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5  render_composite: a block owns 32 consecutive output pixels.
+//   phase 1 (all 8 warps): lanes = layers.  Each thread computes the ray/sphere hit of its
+//     (pixel, layer), gathers the 4 bilinear RGBA taps as float4 (a warp's taps of one source
+//     texel are one contiguous 512-byte run of [.., L, 4]) and parks the sample in shared memory;
+//   phase 2 (4 warps): lane = pixel, warp = channel (r, g, b, depth).  Each thread runs the
+//     back-to-front recurrence of over_composite / over_composite_depth in the reference's
+//     exact order, so colour AND depth come out of ONE reprojection (the reference does two).
+// ------------------------------------------------------------------------------------------
+struct RenderParams {
+    const float4* rgba;      // [B,H,W,L] float4
+    const float* pose_rt;    // [B,16]
+    const float* tgt_pos;    // [B,3]
+    const float* depths;     // [L]
+    const float *cos_s, *sin_s, *cos_t, *sin_t;
+    int B, H, W, L;
+    float* out_rgb;
+    float* out_depth;
+    uint8_t* out_rgb_u8;
+    uint8_t* out_depth_u8;
+    ErpConsts k;
+};
+
+__device__ __forceinline__ float4 sample_layer(const RenderParams& p, int b, int i, int j, int l) {
+    float u, v;
+    sphere_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+              p.pose_rt + b * 16, p.tgt_pos + b * 3, __ldg(p.depths + l), p.k, u, v);
+    const Bilinear s = bilinear_setup(u, v, p.W, p.H);
+    const size_t ib = (size_t)b * p.H * p.W;
+    const float4 pa = __ldg(p.rgba + (ib + (size_t)s.y0 * p.W + s.x0) * p.L + l);
+    const float4 pb = __ldg(p.rgba + (ib + (size_t)s.y0 * p.W + s.x1) * p.L + l);
+    const float4 pc = __ldg(p.rgba + (ib + (size_t)s.y1 * p.W + s.x0) * p.L + l);
+    const float4 pd = __ldg(p.rgba + (ib + (size_t)s.y1 * p.W + s.x1) * p.L + l);
+    float4 o;
+    o.x = blend4(s, pa.x, pb.x, pc.x, pd.x);
+    o.y = blend4(s, pa.y, pb.y, pc.y, pd.y);
+    o.z = blend4(s, pa.z, pb.z, pc.z, pd.z);
+    o.w = blend4(s, pa.w, pb.w, pc.w, pd.w);
+    return o;
+}
+
+__device__ __forceinline__ uint8_t to_u8(float x) {
+    // tf.image.convert_image_dtype(float -> uint8, saturate=False): truncating cast of x * 255.5
+    return (uint8_t)(__float2int_rz(x * 255.5f) & 0xff);
+}
+
+__global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
+    extern __shared__ float sm[];  // [4][32][L+1] samples, then [L] depth fractions
+    const int L = p.L;
+    const int ld = L + 1;
+    float* frac = sm + 4 * 32 * ld;
+    const long long npix = (long long)p.B * p.H * p.W;
+    const long long pix0 = (long long)blockIdx.x * 32;
+
+    for (int l = threadIdx.x; l < L; l += 256) frac[l] = (float)((double)l / (double)L);
+
+    for (int s = threadIdx.x; s < 32 * L; s += 256) {
+        const int q = s / L;
+        const int l = s - q * L;
+        const long long pix = pix0 + q;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pix < npix) {
+            const int j = (int)(pix % p.W);
+            const int i = (int)((pix / p.W) % p.H);
+            const int b = (int)(pix / ((long long)p.W * p.H));
+            o = sample_layer(p, b, i, j, l);
+        }
+        sm[(0 * 32 + q) * ld + l] = o.x;
+        sm[(1 * 32 + q) * ld + l] = o.y;
+        sm[(2 * 32 + q) * ld + l] = o.z;
+        sm[(3 * 32 + q) * ld + l] = o.w;
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 128) {
+        const int ch = threadIdx.x >> 5;
+        const int q = threadIdx.x & 31;
+        const long long pix = pix0 + q;
+        const float* col = sm + (ch * 32 + q) * ld;
+        const float* alp = sm + (3 * 32 + q) * ld;
+        float out;
+        if (ch < 3) {
+            out = col[0];  // alpha of the farthest layer is ignored (projector.py:257-259)
+            for (int l = 1; l < L; ++l) {
+                const float a = alp[l];
+                out = col[l] * a + out * (1.0f - a);
+            }
+        } else {
+            out = 0.0f;
+            for (int l = 1; l < L; ++l) {
+                const float a = alp[l];
+                out = frac[l] * a + out * (1.0f - a);
+            }
+        }
+        if (pix < npix) {
+            if (ch < 3) {
+                if (p.out_rgb != nullptr) p.out_rgb[pix * 3 + ch] = out;
+                if (p.out_rgb_u8 != nullptr) p.out_rgb_u8[pix * 3 + ch] = to_u8((out + 1.0f) / 2.0f);
+            } else {
+                if (p.out_depth != nullptr) {
+                    p.out_depth[pix * 3 + 0] = out;
+                    p.out_depth[pix * 3 + 1] = out;
+                    p.out_depth[pix * 3 + 2] = out;
+                }
+                if (p.out_depth_u8 != nullptr) {
+                    const uint8_t d = to_u8(out);
+                    p.out_depth_u8[pix * 3 + 0] = d;
+                    p.out_depth_u8[pix * 3 + 1] = d;
+                    p.out_depth_u8[pix * 3 + 2] = d;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sphere_coords_kernel(RenderParams p, float* uv) {
+    // [B,L,H,W]
+    const long long total = (long long)p.B * p.L * p.H * p.W;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % p.W);
+    const int i = (int)((idx / p.W) % p.H);
+    const int l = (int)((idx / ((long long)p.W * p.H)) % p.L);
+    const int b = (int)(idx / ((long long)p.W * p.H * p.L));
+    float u, v;
+    sphere_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+              p.pose_rt + b * 16, p.tgt_pos + b * 3, __ldg(p.depths + l), p.k, u, v);
+    uv[2 * idx + 0] = u;
+    uv[2 * idx + 1] = v;
+}
+
+__global__ void __launch_bounds__(256) project_layers_kernel(RenderParams p, float4* out) {
+    // thread per (b, i, j, l), l fastest (coalesced gathers); out [L,B,H,W] float4
+    const long long total = (long long)p.B * p.H * p.W * p.L;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int l = (int)(idx % p.L);
+    const long long pix = idx / p.L;
+    const int j = (int)(pix % p.W);
+    const int i = (int)((pix / p.W) % p.H);
+    const int b = (int)(pix / ((long long)p.W * p.H));
+    out[(size_t)l * p.B * p.H * p.W + pix] = sample_layer(p, b, i, j, l);
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone sampling.resample and projector.over_composite[_depth]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ image, const float* __restrict__ coords, int N, int H, int W, int C,
+                int h, int w, float* __restrict__ out) {
+    const long long total = (long long)N * h * w;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int n = (int)(idx / ((long long)h * w));
+    const Bilinear s = bilinear_setup(__ldg(coords + 2 * idx), __ldg(coords + 2 * idx + 1), W, H);
+    const float* base = image + (size_t)n * H * W * C;
+    const float* pa = base + ((size_t)s.y0 * W + s.x0) * C;
+    const float* pb = base + ((size_t)s.y0 * W + s.x1) * C;
+    const float* pc = base + ((size_t)s.y1 * W + s.x0) * C;
+    const float* pd = base + ((size_t)s.y1 * W + s.x1) * C;
+    float* o = out + (size_t)idx * C;
+    for (int c = 0; c < C; ++c) o[c] = blend4(s, __ldg(pa + c), __ldg(pb + c), __ldg(pc + c), __ldg(pd + c));
+}
+
+__global__ void __launch_bounds__(256)
+over_composite_kernel(const float4* __restrict__ layers, int L, long long npix, int depth_mode,
+                      float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= npix) return;
+    float4 first = __ldg(layers + idx);
+    float r = depth_mode ? 0.f : first.x, g = depth_mode ? 0.f : first.y, b = depth_mode ? 0.f : first.z;
+    for (int l = 1; l < L; ++l) {
+        const float4 c = __ldg(layers + (size_t)l * npix + idx);
+        const float a = c.w;
+        const float oma = 1.0f - a;
+        if (depth_mode) {
+            const float f = (float)((double)l / (double)L);
+            r = f * a + r * oma;
+            g = r;
+            b = r;
+        } else {
+            r = c.x * a + r * oma;
+            g = c.y * a + g * oma;
+            b = c.z * a + b * oma;
+        }
+    }
+    out[idx * 3 + 0] = r;
+    out[idx * 3 + 1] = g;
+    out[idx * 3 + 2] = b;
+}
+
+}  // namespace msi
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace msi;
+
+static int fill_psv_params(PsvParams& p, const void* ref, const void* src, int preprocess, const float* poses,
+                           const float* baselines, const float* depths, const float* cos_s, const float* sin_s,
+                           const float* cos_t, const float* sin_t, int B, int H, int W, int P) {
+    MSI_CHECK_ARG(B > 0 && H > 1 && W > 1 && P > 0, "psv: bad shape B=%d H=%d W=%d P=%d", B, H, W, P);
+    MSI_CHECK_ARG(poses && baselines && depths && cos_s && sin_s && cos_t && sin_t, "psv: null table/pose pointer");
+    p.img[0] = ref;
+    p.img[1] = src;
+    p.poses = poses;
+    p.baselines = baselines;
+    p.depths = depths;
+    p.cos_s = cos_s;
+    p.sin_s = sin_s;
+    p.cos_t = cos_t;
+    p.sin_t = sin_t;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.P = P;
+    p.preprocess = preprocess;
+    p.out_f32 = nullptr;
+    p.out_hi = nullptr;
+    p.out_lo = nullptr;
+    p.c_stride = 6 * P;
+    p.k = make_erp_consts(H, W);
+    return MSI_OK;
+}
+
+extern "C" int msi_psv_build(const void* ref, const void* src, int img_dtype, int preprocess, const float* poses,
+                             const float* baselines, const float* depths, const float* cos_s, const float* sin_s,
+                             const float* cos_t, const float* sin_t, int B, int H, int W, int P, float* out_f32,
+                             void* out_hi, void* out_lo, int c_stride, void* stream) {
+    PsvParams p;
+    int rc = fill_psv_params(p, ref, src, preprocess, poses, baselines, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, P);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(ref && src, "psv: null image pointer");
+    MSI_CHECK_ARG(out_f32 || out_hi, "psv: no output requested");
+    MSI_CHECK_ARG(img_dtype == MSI_IMG_F32 || img_dtype == MSI_IMG_U8, "psv: bad img_dtype %d", img_dtype);
+    if (out_hi) MSI_CHECK_ARG(c_stride >= 6 * P && c_stride % 8 == 0, "psv: c_stride %d must be >= 6P and a multiple of 8", c_stride);
+    p.out_f32 = out_f32;
+    p.out_hi = reinterpret_cast<__half*>(out_hi);
+    p.out_lo = reinterpret_cast<__half*>(out_lo);
+    p.c_stride = out_hi ? c_stride : 6 * P;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (out_hi && c_stride != 6 * P) {
+        const size_t bytes = (size_t)B * H * W * c_stride * sizeof(__half);
+        MSI_CUDA(cudaMemsetAsync(out_hi, 0, bytes, st));
+        if (out_lo) MSI_CUDA(cudaMemsetAsync(out_lo, 0, bytes, st));
+    }
+    const long long total = (long long)B * H * W * 2 * P;
+    const int grid = ceil_div(total, 256);
+    if (img_dtype == MSI_IMG_F32)
+        psv_build_kernel<float><<<grid, 256, 0, st>>>(p);
+    else
+        psv_build_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_sweep_coords(const float* poses, const float* baselines, const float* depths, const float* cos_s,
+                                const float* sin_s, const float* cos_t, const float* sin_t, int B, int H, int W, int P,
+                                float* uv, uint8_t* valid, void* stream) {
+    PsvParams p;
+    int rc = fill_psv_params(p, nullptr, nullptr, 0, poses, baselines, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, P);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(uv != nullptr, "sweep_coords: null uv");
+    const long long total = (long long)B * 2 * P * H * W;
+    sweep_coords_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, uv, valid);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_rgba_assemble(const float* pred, const float* psv_f32, const void* psv_hi, const void* psv_lo,
+                                 int c_stride, int B, int H, int W, int L, float* rgba, float* blend_weights,
+                                 float* alphas, void* stream) {
+    MSI_CHECK_ARG(B > 0 && H > 0 && W > 0 && L > 0, "rgba_assemble: bad shape");
+    MSI_CHECK_ARG(pred && rgba, "rgba_assemble: null pred/rgba");
+    MSI_CHECK_ARG(psv_f32 || (psv_hi && psv_lo), "rgba_assemble: need psv_f32 or the hi/lo pair");
+    if (!psv_f32) MSI_CHECK_ARG(c_stride >= 6 * L, "rgba_assemble: c_stride %d < 6L", c_stride);
+    const long long npix = (long long)B * H * W;
+    rgba_assemble_kernel<<<ceil_div(npix * L, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        pred, psv_f32, reinterpret_cast<const __half*>(psv_hi), reinterpret_cast<const __half*>(psv_lo), c_stride,
+        npix, L, reinterpret_cast<float4*>(rgba), blend_weights, alphas);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+static int fill_render_params(RenderParams& p, const float* rgba, const float* pose_rt, const float* tgt_pos,
+                              const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
+                              const float* sin_t, int B, int H, int W, int L) {
+    MSI_CHECK_ARG(B > 0 && H > 1 && W > 1 && L > 0, "render: bad shape B=%d H=%d W=%d L=%d", B, H, W, L);
+    MSI_CHECK_ARG(pose_rt && tgt_pos && depths && cos_s && sin_s && cos_t && sin_t, "render: null pointer");
+    p.rgba = reinterpret_cast<const float4*>(rgba);
+    p.pose_rt = pose_rt;
+    p.tgt_pos = tgt_pos;
+    p.depths = depths;
+    p.cos_s = cos_s;
+    p.sin_s = sin_s;
+    p.cos_t = cos_t;
+    p.sin_t = sin_t;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.L = L;
+    p.out_rgb = nullptr;
+    p.out_depth = nullptr;
+    p.out_rgb_u8 = nullptr;
+    p.out_depth_u8 = nullptr;
+    p.k = make_erp_consts(H, W);
+    return MSI_OK;
+}
+
+extern "C" int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                                    const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
+                                    const float* sin_t, int B, int H, int W, int L, float* out_rgb, float* out_depth,
+                                    uint8_t* out_rgb_u8, uint8_t* out_depth_u8, void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, rgba, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(rgba != nullptr, "render: null rgba");
+    MSI_CHECK_ARG(out_rgb || out_depth || out_rgb_u8 || out_depth_u8, "render: no output requested");
+    p.out_rgb = out_rgb;
+    p.out_depth = out_depth;
+    p.out_rgb_u8 = out_rgb_u8;
+    p.out_depth_u8 = out_depth_u8;
+    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
+    MSI_CHECK_ARG(smem <= 200 * 1024, "render: L=%d needs %zu B of shared memory", L, smem);
+    static std::atomic<size_t> smem_opted{48 * 1024};
+    if (smem > smem_opted.load()) {
+        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_opted.store(smem);
+    }
+    const long long npix = (long long)B * H * W;
+    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
+                                           const float* cos_s, const float* sin_s, const float* cos_t,
+                                           const float* sin_t, int B, int H, int W, int L, float* uv, void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, nullptr, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(uv != nullptr, "intersect_sphere_coords: null uv");
+    const long long total = (long long)B * L * H * W;
+    sphere_coords_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, uv);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_project_layers(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                                  const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
+                                  const float* sin_t, int B, int H, int W, int L, float* out, void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, rgba, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(rgba && out, "project_layers: null pointer");
+    const long long total = (long long)B * H * W * L;
+    project_layers_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p, reinterpret_cast<float4*>(out));
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_resample(const float* image, const float* coords, int N, int H, int W, int C, int h, int w,
+                            float* out, void* stream) {
+    MSI_CHECK_ARG(image && coords && out, "resample: null pointer");
+    MSI_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && h > 0 && w > 0, "resample: bad shape");
+    const long long total = (long long)N * h * w;
+    resample_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(image, coords, N, H, W,
+                                                                                             C, h, w, out);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_over_composite(const float* layers, int L, int B, int H, int W, int depth_mode, float* out,
+                                  void* stream) {
+    MSI_CHECK_ARG(layers && out, "over_composite: null pointer");
+    MSI_CHECK_ARG(L > 0 && B > 0 && H > 0 && W > 0, "over_composite: bad shape");
+    const long long npix = (long long)B * H * W;
+    over_composite_kernel<<<ceil_div(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(layers), L, npix, depth_mode, out);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}

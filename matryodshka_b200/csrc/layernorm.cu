@@ -1,0 +1,200 @@
+// LayerNorm over (H, W, C) per frame + ReLU (slim.layer_norm, nets.py:484-485 arg_scope),
+// input splitting into the fp16 hi/lo operand format, and the coord-channel bias table.
+//
+// slim.layer_norm [TF-1.14]: mean/variance over axes 1..3, then tf.nn.batch_normalization with
+// eps = 1e-12:  inv = rsqrt(var + eps) * gamma;  y = x * inv + (beta - mean * inv).
+// 13.1 M elements per frame after conv1_1, so the reduction is grid-wide: per-block (sum, sumsq)
+// partials in float64, a one-block finalize, and a fused normalise + ReLU + fp16 hi/lo split pass.
+#include "net_internal.cuh"
+
+namespace msi {
+
+static constexpr int kLnChunk = 256 * 4 * 8;  // elements per partial block: 256 threads x 8 float4
+
+int ln_partials_count(long long n_per_sample) { return ceil_div(n_per_sample, kLnChunk); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+ln_partial_kernel(const float* __restrict__ raw, long long n_per_sample, double2* __restrict__ partials,
+                  int n_partials) {
+    const int b = blockIdx.y;
+    const float* x = raw + (size_t)b * n_per_sample;
+    const long long start = (long long)blockIdx.x * kLnChunk;
+    const long long end = min(start + (long long)kLnChunk, n_per_sample);
+    float s = 0.f, q = 0.f;
+    // n_per_sample is a multiple of 8 (C % 8 == 0) so float4 access is aligned
+    for (long long i = start + threadIdx.x * 4; i < end; i += 256 * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
+        s += (v.x + v.y) + (v.z + v.w);
+        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    __shared__ double sh[2][8];
+    double ds = warp_sum((double)s), dq = warp_sum((double)q);
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = ds;
+        sh[1][threadIdx.x >> 5] = dq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < 8; ++w) {
+            a += sh[0][w];
+            c += sh[1][w];
+        }
+        partials[(size_t)b * n_partials + blockIdx.x] = make_double2(a, c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ln_finalize_kernel(const double2* __restrict__ partials, int n_partials, long long n_per_sample,
+                   float2* __restrict__ stats) {
+    const int b = blockIdx.x;
+    double s = 0, q = 0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) {
+        const double2 p = partials[(size_t)b * n_partials + i];
+        s += p.x;
+        q += p.y;
+    }
+    __shared__ double sh[2][8];
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = s;
+        sh[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < 8; ++w) {
+            a += sh[0][w];
+            c += sh[1][w];
+        }
+        const double mean = a / (double)n_per_sample;
+        double var = c / (double)n_per_sample - mean * mean;
+        if (var < 0) var = 0;
+        stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-12)));
+    }
+}
+
+// thread = 8 consecutive channels of one pixel
+__global__ void __launch_bounds__(256)
+ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
+                __half* __restrict__ out_lo) {
+    const int b = blockIdx.y;
+    const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (i >= n_per_sample) return;
+    const float2 st = stats[b];
+    const int c0 = (int)(i % C);
+    const size_t off = (size_t)b * n_per_sample + i;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(raw + off));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(raw + off + 4));
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float inv = st.y * __ldg(gamma + c0 + q);
+        const float sh = __ldg(beta + c0 + q) - st.x * inv;
+        float y = x[q] * inv + sh;
+        y = fmaxf(y, 0.f);
+        split_half(y * MSI_ACT_SCALE, hi[q], lo[q]);
+    }
+    *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
+               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
+               bool partials_ready, cudaStream_t st) {
+    MSI_CHECK_ARG(C % 8 == 0, "layer_norm: C=%d must be a multiple of 8", C);
+    if (!partials_ready) {
+        ln_partial_kernel<<<dim3(n_partials, B), 256, 0, st>>>(raw, n_per_sample, partials, n_partials);
+        MSI_LAUNCH_CHECK();
+    }
+    ln_finalize_kernel<<<B, 256, 0, st>>>(partials, n_partials, n_per_sample, stats);
+    MSI_LAUNCH_CHECK();
+    ln_apply_kernel<<<dim3(ceil_div(n_per_sample, 256 * 8), B), 256, 0, st>>>(raw, n_per_sample, C, stats, gamma,
+                                                                            beta, out_hi, out_lo);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+// float32 NHWC [npix, C] -> fp16 hi/lo [npix, c_stride] scaled by MSI_ACT_SCALE (pad channels = 0)
+__global__ void __launch_bounds__(256)
+split_input_kernel(const float* __restrict__ in, long long npix, int C, int c_stride, __half* __restrict__ hi,
+                   __half* __restrict__ lo) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= npix * c_stride) return;
+    const long long pix = idx / c_stride;
+    const int c = (int)(idx % c_stride);
+    __half h = __float2half_rn(0.f), l = h;
+    if (c < C) split_half(__ldg(in + pix * C + c) * MSI_ACT_SCALE, h, l);
+    hi[idx] = h;
+    lo[idx] = l;
+}
+
+int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st) {
+    split_input_kernel<<<ceil_div(npix * c_stride, 256), 256, 0, st>>>(in, npix, C, c_stride, hi, lo);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+__global__ void __launch_bounds__(256)
+merge_activation_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long npix, int C,
+                        int c_stride, float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= npix * C) return;
+    const long long pix = idx / C;
+    const int c = (int)(idx % C);
+    const size_t o = (size_t)pix * c_stride + c;
+    out[idx] = (__half2float(hi[o]) + __half2float(lo[o])) * (1.0f / MSI_ACT_SCALE);
+}
+
+int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
+                     cudaStream_t st) {
+    merge_activation_kernel<<<ceil_div(npix * C, 256), 256, 0, st>>>(hi, lo, npix, C, c_stride, out);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+// Coord-channel fold (nets.py:260-270).  The appended channel |sin(lat_row)| depends only on the
+// input row, and SAME zero padding zeroes it outside the image, so its contribution to an output
+// (ho, wo, n) is a function of ho and of WHICH kw taps are inside the image at wo:
+//   cbias[ho][mask][n] = sum_{kh in-bounds} coord[h(ho,kh)] * sum_{kw in mask} Wc[kh][kw][n]
+// with mask = 3 bits (kw in-bounds).  The tensor-core GEMM then runs on K = 9*Cin (a multiple of
+// 64) and the epilogue adds cbias[ho][mask(wo)][n].
+__global__ void __launch_bounds__(256)
+coord_bias_kernel(const float* __restrict__ w /*[k,k,cin+1,cout]*/, const float* __restrict__ coord_rows, int k,
+                  int cin, int cout, int Hin, int Hout, int stride, int rate, int pad_t, float* __restrict__ cbias) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Hout * 8 * cout) return;
+    const int n = idx % cout;
+    const int mask = (idx / cout) & 7;
+    const int ho = idx / (cout * 8);
+    float acc = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+        const int h = ho * stride + kh * rate - pad_t;
+        if (h < 0 || h >= Hin) continue;
+        float ws = 0.f;
+        for (int kw = 0; kw < k; ++kw)
+            if (mask & (1 << kw)) ws += w[((size_t)(kh * k + kw) * (cin + 1) + cin) * cout + n];
+        acc += coord_rows[h] * ws;
+    }
+    cbias[idx] = acc;
+}
+
+int coord_bias_build(const LayerPlan& L, const float* coord_rows_dev, cudaStream_t st) {
+    const int total = L.Hout * 8 * L.cout;
+    coord_bias_kernel<<<ceil_div(total, 256), 256, 0, st>>>(L.w_f32, coord_rows_dev, L.k, L.cin_total, L.cout, L.Hin,
+                                                           L.Hout, L.stride, L.rate, L.pad_t, L.cbias);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+}  // namespace msi

@@ -1,0 +1,464 @@
+// Host orchestration of the conv net (nets.msi_coord_train_net, nets.py:471-515) behind the
+// msi_net_* C ABI: layer table, workspace / arena carving, parameter packing, and the launch
+// sequence  conv -> LayerNorm(stats, finalize, normalise+ReLU+split)  x17  -> 1x1 head + tanh.
+// All work is enqueued on the caller's stream without host synchronisation, so one forward can be
+// captured into a CUDA graph.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "net_internal.cuh"
+
+using namespace msi;
+
+struct msi_net {
+    int H, W, c_in, c_out, ngf, max_batch, conv_impl, precision;
+    int in_c_stride;
+    std::vector<LayerPlan> layers;
+    std::vector<ActBuf> acts;  // acts[0] = network input; acts[i + 1] = output of layer i
+    std::vector<std::vector<float>> coord_rows_host;
+    size_t ws_bytes = 0, arena_bytes = 0;
+    // carve-out offsets (filled at create, turned into pointers at bind)
+    struct Off {
+        size_t w_f32, gamma, beta, bias, cbias, w_hi, w_lo;  // arena
+        size_t raw, partials, stats, act_hi, act_lo;         // workspace
+    };
+    std::vector<Off> off;
+    size_t in_hi_off = 0, in_lo_off = 0;
+    char* ws = nullptr;
+    char* arena = nullptr;
+    bool bound = false;
+    const void* bound_in_hi = nullptr;
+};
+
+namespace {
+
+struct ArchRow {
+    const char* scope;
+    int kind, mult, k, stride, rate, nsrc;
+    const char* src[2];
+};
+
+// nets.py:486-515
+const ArchRow kArch[] = {
+    {"conv1_1", kConv, 1, 3, 1, 1, 1, {"input", nullptr}},
+    {"conv1_2", kConv, 2, 3, 2, 1, 1, {"conv1_1", nullptr}},
+    {"conv2_1", kConv, 2, 3, 1, 1, 1, {"conv1_2", nullptr}},
+    {"conv2_2", kConv, 4, 3, 2, 1, 1, {"conv2_1", nullptr}},
+    {"conv3_1", kConv, 4, 3, 1, 1, 1, {"conv2_2", nullptr}},
+    {"conv3_2", kConv, 4, 3, 1, 1, 1, {"conv3_1", nullptr}},
+    {"conv3_3", kConv, 8, 3, 2, 1, 1, {"conv3_2", nullptr}},
+    {"conv4_1", kConv, 8, 3, 1, 2, 1, {"conv3_3", nullptr}},
+    {"conv4_2", kConv, 8, 3, 1, 2, 1, {"conv4_1", nullptr}},
+    {"conv4_3", kConv, 8, 3, 1, 2, 1, {"conv4_2", nullptr}},
+    {"conv6_1", kDeconv, 4, 4, 2, 1, 2, {"conv4_3", "conv3_3"}},
+    {"conv6_2", kConv, 4, 3, 1, 1, 1, {"conv6_1", nullptr}},
+    {"conv6_3", kConv, 4, 3, 1, 1, 1, {"conv6_2", nullptr}},
+    {"conv7_1", kDeconv, 2, 4, 2, 1, 2, {"conv6_3", "conv2_2"}},
+    {"conv7_2", kConv, 2, 3, 1, 1, 1, {"conv7_1", nullptr}},
+    {"conv8_1", kDeconv, 1, 4, 2, 1, 2, {"conv7_2", "conv1_2"}},
+    {"conv8_2", kConv, 1, 3, 1, 1, 1, {"conv8_1", nullptr}},
+    {"color_pred", kHead, 0, 1, 1, 1, 1, {"conv8_2", nullptr}},
+};
+const int kNumLayers = sizeof(kArch) / sizeof(kArch[0]);
+
+size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+// [TF-1.14] SAME padding before
+int same_pad_before(int n, int k, int s, int rate) {
+    const int k_eff = (k - 1) * rate + 1;
+    const int out = (n + s - 1) / s;
+    int total = (out - 1) * s + k_eff - n;
+    if (total < 0) total = 0;
+    return total / 2;
+}
+
+int find_act(const msi_net* net, const char* scope) {
+    if (strcmp(scope, "input") == 0) return 0;
+    for (int i = 0; i < (int)net->layers.size(); ++i)
+        if (strcmp(net->layers[i].scope, scope) == 0) return i + 1;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, int ngf, int max_batch,
+                              int conv_impl, int precision) {
+    MSI_CHECK_ARG(out != nullptr, "net_create: null out");
+    MSI_CHECK_ARG(H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "net_create: H=%d W=%d must be multiples of 8", H, W);
+    MSI_CHECK_ARG(c_in > 0 && c_out > 0 && c_out % 4 == 0, "net_create: bad channels c_in=%d c_out=%d", c_in, c_out);
+    MSI_CHECK_ARG(ngf >= 8 && ngf % 8 == 0, "net_create: ngf=%d must be a multiple of 8", ngf);
+    MSI_CHECK_ARG(max_batch >= 1, "net_create: max_batch=%d", max_batch);
+    MSI_CHECK_ARG(conv_impl == MSI_CONV_TCGEN05 || conv_impl == MSI_CONV_SIMT, "net_create: conv_impl=%d", conv_impl);
+    MSI_CHECK_ARG(precision == MSI_PREC_FP16X3 || precision == MSI_PREC_FP16, "net_create: precision=%d", precision);
+    if (conv_impl == MSI_CONV_TCGEN05) {
+        if (ngf % 64 != 0 || c_out % 16 != 0 || c_out > 256) {
+            set_error("net_create: the tcgen05 back end needs ngf %% 64 == 0 and c_out %% 16 == 0, c_out <= 256 (got ngf=%d c_out=%d)", ngf, c_out);
+            return MSI_ERR_UNSUPPORTED;
+        }
+    }
+    msi_net* net = new msi_net();
+    net->H = H;
+    net->W = W;
+    net->c_in = c_in;
+    net->c_out = c_out;
+    net->ngf = ngf;
+    net->max_batch = max_batch;
+    net->conv_impl = conv_impl;
+    net->precision = precision;
+    net->in_c_stride = (int)align_up((size_t)c_in, 64);
+
+    net->acts.resize(kNumLayers + 1);
+    net->acts[0].H = H;
+    net->acts[0].W = W;
+    net->acts[0].C = c_in;
+    net->acts[0].c_stride = net->in_c_stride;
+    net->layers.resize(kNumLayers);
+    net->off.resize(kNumLayers);
+    net->coord_rows_host.resize(kNumLayers);
+
+    size_t a = 0, w = 0;
+    const size_t B = (size_t)max_batch;
+    net->in_hi_off = w;
+    w += align_up(B * H * W * net->in_c_stride * sizeof(__half));
+    net->in_lo_off = w;
+    w += align_up(B * H * W * net->in_c_stride * sizeof(__half));
+
+    for (int i = 0; i < kNumLayers; ++i) {
+        const ArchRow& r = kArch[i];
+        LayerPlan& L = net->layers[i];
+        memset(L.scope, 0, sizeof(L.scope));
+        strncpy(L.scope, r.scope, sizeof(L.scope) - 1);
+        L.kind = r.kind;
+        L.k = r.k;
+        L.stride = r.stride;
+        L.rate = r.rate;
+        L.nsrc = r.nsrc;
+        L.cin_total = 0;
+        for (int s = 0; s < r.nsrc; ++s) {
+            L.src[s] = find_act(net, r.src[s]);
+            L.cin[s] = net->acts[L.src[s]].C;
+            L.cin_total += L.cin[s];
+        }
+        if (r.nsrc == 1) {
+            L.src[1] = -1;
+            L.cin[1] = 0;
+        }
+        const ActBuf& in0 = net->acts[L.src[0]];
+        L.Hin = in0.H;
+        L.Win = in0.W;
+        L.cout = (r.kind == kHead) ? c_out : ngf * r.mult;
+        if (r.kind == kDeconv) {
+            L.Hout = L.Hin * 2;
+            L.Wout = L.Win * 2;
+            L.pad_t = L.pad_l = 0;
+            L.ncls = 4;
+        } else {
+            L.Hout = (L.Hin + r.stride - 1) / r.stride;
+            L.Wout = (L.Win + r.stride - 1) / r.stride;
+            L.pad_t = same_pad_before(L.Hin, r.k, r.stride, r.rate);
+            L.pad_l = same_pad_before(L.Win, r.k, r.stride, r.rate);
+            L.ncls = 1;
+        }
+        L.out_act = i + 1;
+        ActBuf& o = net->acts[i + 1];
+        o.H = L.Hout;
+        o.W = L.Wout;
+        o.C = L.cout;
+        o.c_stride = L.cout;
+
+        // packed reduction length: taps x (sum of source channel strides)
+        int cs_total = 0;
+        for (int s = 0; s < L.nsrc; ++s) cs_total += net->acts[L.src[s]].c_stride;
+        const int ntaps = (r.kind == kDeconv) ? 4 : r.k * r.k;
+        L.K = ntaps * cs_total;
+
+        msi_net::Off& f = net->off[i];
+        size_t wcount;
+        if (r.kind == kConv)
+            wcount = (size_t)r.k * r.k * (L.cin_total + 1) * L.cout;
+        else if (r.kind == kDeconv)
+            wcount = (size_t)r.k * r.k * L.cout * L.cin_total;
+        else
+            wcount = (size_t)L.cin_total * L.cout;
+        f.w_f32 = a;
+        a += align_up(wcount * sizeof(float));
+        f.gamma = a;
+        a += align_up(L.cout * sizeof(float));
+        f.beta = a;
+        a += align_up(L.cout * sizeof(float));
+        f.bias = a;
+        a += align_up(L.cout * sizeof(float));
+        f.cbias = a;
+        if (r.kind == kConv) a += align_up(((size_t)L.Hout * 8 * L.cout + L.Hin) * sizeof(float));
+        f.w_hi = a;
+        a += align_up((size_t)L.ncls * L.cout * L.K * sizeof(__half));
+        f.w_lo = a;
+        a += align_up((size_t)L.ncls * L.cout * L.K * sizeof(__half));
+
+        const size_t n_per = (size_t)L.Hout * L.Wout * L.cout;
+        L.n_partials = ln_partials_count((long long)n_per);
+        f.raw = w;
+        if (r.kind != kHead) w += align_up(B * n_per * sizeof(float));
+        f.partials = w;
+        w += align_up(B * L.n_partials * sizeof(double2));
+        f.stats = w;
+        w += align_up(B * sizeof(float2));
+        f.act_hi = w;
+        if (r.kind != kHead) w += align_up(B * n_per * sizeof(__half));
+        f.act_lo = w;
+        if (r.kind != kHead) w += align_up(B * n_per * sizeof(__half));
+
+        if (r.kind == kConv) {
+            // nets.py:262-263: |sin(linspace(-pi/2, pi/2, H))| in float64, cast to float32
+            std::vector<float>& rows = net->coord_rows_host[i];
+            rows.resize(L.Hin);
+            const double pi = 3.141592653589793;
+            const double start = -pi / 2.0, stop = pi / 2.0;
+            const double step = (L.Hin > 1) ? (stop - start) / (double)(L.Hin - 1) : 0.0;
+            for (int h = 0; h < L.Hin; ++h) {
+                const double lat = (h == L.Hin - 1 && L.Hin > 1) ? stop : start + step * (double)h;
+                rows[h] = (float)fabs(sin(lat));
+            }
+        }
+    }
+    net->ws_bytes = w;
+    net->arena_bytes = a;
+    *out = net;
+    return MSI_OK;
+}
+
+extern "C" void msi_net_destroy(msi_net* net) {
+    if (!net) return;
+    for (auto& L : net->layers) conv_tc_plan_destroy(L);
+    delete net;
+}
+
+extern "C" size_t msi_net_workspace_bytes(const msi_net* net) { return net ? net->ws_bytes : 0; }
+extern "C" size_t msi_net_arena_bytes(const msi_net* net) { return net ? net->arena_bytes : 0; }
+extern "C" int msi_net_input_c_stride(const msi_net* net) { return net ? net->in_c_stride : 0; }
+
+extern "C" int msi_net_num_launches_per_forward(const msi_net* net) {
+    if (!net) return 0;
+    // conv + (stats, finalize, apply) per normalised layer, + head
+    return (kNumLayers - 1) * 4 + 1;
+}
+
+extern "C" int msi_net_bind(msi_net* net, void* workspace, size_t workspace_bytes, void* arena, size_t arena_bytes) {
+    MSI_CHECK_ARG(net && workspace && arena, "net_bind: null pointer");
+    MSI_CHECK_ARG(workspace_bytes >= net->ws_bytes, "net_bind: workspace %zu < %zu", workspace_bytes, net->ws_bytes);
+    MSI_CHECK_ARG(arena_bytes >= net->arena_bytes, "net_bind: arena %zu < %zu", arena_bytes, net->arena_bytes);
+    MSI_CHECK_ARG(((uintptr_t)workspace % 1024) == 0 && ((uintptr_t)arena % 1024) == 0,
+                  "net_bind: workspace and arena must be 1024-byte aligned");
+    net->ws = (char*)workspace;
+    net->arena = (char*)arena;
+    net->acts[0].hi = (__half*)(net->ws + net->in_hi_off);
+    net->acts[0].lo = (__half*)(net->ws + net->in_lo_off);
+    for (int i = 0; i < kNumLayers; ++i) {
+        LayerPlan& L = net->layers[i];
+        const msi_net::Off& f = net->off[i];
+        L.w_f32 = (float*)(net->arena + f.w_f32);
+        L.gamma = (float*)(net->arena + f.gamma);
+        L.beta = (float*)(net->arena + f.beta);
+        L.bias = (float*)(net->arena + f.bias);
+        L.cbias = (L.kind == kConv) ? (float*)(net->arena + f.cbias) : nullptr;
+        L.w_hi = (__half*)(net->arena + f.w_hi);
+        L.w_lo = (__half*)(net->arena + f.w_lo);
+        L.raw = (L.kind != kHead) ? (float*)(net->ws + f.raw) : nullptr;
+        L.partials = (double2*)(net->ws + f.partials);
+        L.stats = (float2*)(net->ws + f.stats);
+        if (L.kind != kHead) {
+            net->acts[i + 1].hi = (__half*)(net->ws + f.act_hi);
+            net->acts[i + 1].lo = (__half*)(net->ws + f.act_lo);
+        }
+        L.loaded = false;
+    }
+    net->bound_in_hi = nullptr;
+    if (net->conv_impl == MSI_CONV_TCGEN05) {
+        for (int i = 0; i < kNumLayers; ++i) {
+            LayerPlan& L = net->layers[i];
+            ActBuf srcs[2];
+            for (int s = 0; s < L.nsrc; ++s) srcs[s] = net->acts[L.src[s]];
+            conv_tc_plan_destroy(L);
+            int rc = conv_tc_plan_create(L, srcs, net->max_batch, net->precision);
+            if (rc != MSI_OK) return rc;
+        }
+    }
+    net->bound = true;
+    return MSI_OK;
+}
+
+extern "C" int msi_net_load_layer(msi_net* net, const char* scope, const float* weights, const float* gamma,
+                                  const float* beta, const float* bias, void* stream) {
+    MSI_CHECK_ARG(net && scope && weights, "net_load_layer: null pointer");
+    if (!net->bound) {
+        set_error("net_load_layer: call msi_net_bind first");
+        return MSI_ERR_STATE;
+    }
+    const int ai = find_act(net, scope);
+    MSI_CHECK_ARG(ai >= 1, "net_load_layer: unknown scope '%s'", scope);
+    const int i = ai - 1;
+    LayerPlan& L = net->layers[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t wcount;
+    if (L.kind == kConv)
+        wcount = (size_t)L.k * L.k * (L.cin_total + 1) * L.cout;
+    else if (L.kind == kDeconv)
+        wcount = (size_t)L.k * L.k * L.cout * L.cin_total;
+    else
+        wcount = (size_t)L.cin_total * L.cout;
+    MSI_CUDA(cudaMemcpyAsync(L.w_f32, weights, wcount * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (L.kind == kHead) {
+        MSI_CHECK_ARG(bias != nullptr, "net_load_layer: '%s' needs a bias", scope);
+        MSI_CUDA(cudaMemcpyAsync(L.bias, bias, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        MSI_CHECK_ARG(gamma && beta, "net_load_layer: '%s' needs LayerNorm gamma and beta", scope);
+        MSI_CUDA(cudaMemcpyAsync(L.gamma, gamma, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        MSI_CUDA(cudaMemcpyAsync(L.beta, beta, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (L.kind == kConv) {
+        float* rows_dev = L.cbias + (size_t)L.Hout * 8 * L.cout;
+        MSI_CUDA(cudaMemcpyAsync(rows_dev, net->coord_rows_host[i].data(), L.Hin * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+        int rc = coord_bias_build(L, rows_dev, st);
+        if (rc != MSI_OK) return rc;
+    }
+    if (net->conv_impl == MSI_CONV_TCGEN05) {
+        ActBuf srcs[2];
+        for (int s = 0; s < L.nsrc; ++s) srcs[s] = net->acts[L.src[s]];
+        int rc = conv_tc_pack_weights(L, srcs, st);
+        if (rc != MSI_OK) return rc;
+    }
+    L.loaded = true;
+    return MSI_OK;
+}
+
+static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                            float* pred, void* stream, cudaEvent_t* ev);
+
+extern "C" int msi_net_forward(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                               float* pred, void* stream) {
+    return net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, nullptr);
+}
+
+// Same forward with CUDA events recorded on `stream` around every conv launch and every LayerNorm
+// group; synchronises the stream and returns per-layer milliseconds (host arrays of
+// msi_net_num_layers() floats; ln_ms of the head is 0).  Not capturable into a graph.
+extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
+                                        int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host) {
+    MSI_CHECK_ARG(conv_ms_host && ln_ms_host, "net_forward_profiled: null output");
+    std::vector<cudaEvent_t> ev(3 * kNumLayers);
+    for (auto& e : ev) MSI_CUDA(cudaEventCreate(&e));
+    int rc = net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, ev.data());
+    if (rc == MSI_OK) {
+        cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) {
+            set_error("net_forward_profiled: %s", cudaGetErrorString(e));
+            rc = MSI_ERR_CUDA;
+        }
+    }
+    if (rc == MSI_OK) {
+        for (int i = 0; i < kNumLayers; ++i) {
+            cudaEventElapsedTime(&conv_ms_host[i], ev[3 * i], ev[3 * i + 1]);
+            ln_ms_host[i] = 0.f;
+            if (net->layers[i].kind != kHead) cudaEventElapsedTime(&ln_ms_host[i], ev[3 * i + 1], ev[3 * i + 2]);
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" int msi_net_num_layers(const msi_net* net) { return net ? kNumLayers : 0; }
+extern "C" const char* msi_net_layer_scope(const msi_net* net, int i) {
+    return (net && i >= 0 && i < kNumLayers) ? net->layers[i].scope : nullptr;
+}
+// Algorithmic FLOPs (2 x MACs, coord channels counted) of layer i for one frame.
+extern "C" double msi_net_layer_flops(const msi_net* net, int i) {
+    if (!net || i < 0 || i >= kNumLayers) return 0.0;
+    const LayerPlan& L = net->layers[i];
+    if (L.kind == kConv) return 2.0 * L.Hout * L.Wout * L.cout * (double)(L.cin_total + 1) * L.k * L.k;
+    if (L.kind == kDeconv) return 2.0 * L.Hin * L.Win * (double)L.cin_total * L.cout * L.k * L.k;
+    return 2.0 * L.Hout * L.Wout * (double)L.cin_total * L.cout;
+}
+
+static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                            float* pred, void* stream, cudaEvent_t* ev) {
+    MSI_CHECK_ARG(net && pred, "net_forward: null pointer");
+    MSI_CHECK_ARG(B >= 1 && B <= net->max_batch, "net_forward: B=%d outside [1, %d]", B, net->max_batch);
+    MSI_CHECK_ARG(in_f32 || (in_hi && in_lo), "net_forward: need in_f32 or the hi/lo pair");
+    if (!net->bound) {
+        set_error("net_forward: call msi_net_bind first");
+        return MSI_ERR_STATE;
+    }
+    for (auto& L : net->layers)
+        if (!L.loaded) {
+            set_error("net_forward: layer '%s' has no parameters loaded", L.scope);
+            return MSI_ERR_STATE;
+        }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+    const size_t in_elems = (size_t)B * net->H * net->W * net->in_c_stride;
+    if (in_f32) {
+        rc = split_input(in_f32, (long long)B * net->H * net->W, net->c_in, net->in_c_stride, net->acts[0].hi,
+                         net->acts[0].lo, st);
+        if (rc != MSI_OK) return rc;
+    } else if (in_hi != net->acts[0].hi) {
+        // keep the TMA descriptors pointing at the workspace copy of the input
+        MSI_CUDA(cudaMemcpyAsync(net->acts[0].hi, in_hi, in_elems * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+        MSI_CUDA(cudaMemcpyAsync(net->acts[0].lo, in_lo, in_elems * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    }
+    for (int i = 0; i < kNumLayers; ++i) {
+        LayerPlan& L = net->layers[i];
+        ActBuf srcs[2];
+        for (int s = 0; s < L.nsrc; ++s) srcs[s] = net->acts[L.src[s]];
+        float* out = (L.kind == kHead) ? pred : L.raw;
+        if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i], st));
+        if (net->conv_impl == MSI_CONV_SIMT)
+            rc = conv_simt_forward(L, srcs, B, out, st);
+        else
+            rc = conv_tc_forward(L, B, out, st);
+        if (rc != MSI_OK) return rc;
+        if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i + 1], st));
+        if (L.kind != kHead) {
+            const long long n_per = (long long)L.Hout * L.Wout * L.cout;
+            rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
+                            net->acts[i + 1].hi, net->acts[i + 1].lo, /*partials_ready=*/false, st);
+            if (rc != MSI_OK) return rc;
+            if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i + 2], st));
+        }
+    }
+    return MSI_OK;
+}
+
+// Pointers of the workspace copy of the network input, so that msi_psv_build can write the PSV
+// operand in place (no copy in msi_net_forward).
+extern "C" int msi_net_input_buffers(msi_net* net, void** hi, void** lo) {
+    MSI_CHECK_ARG(net && hi && lo, "net_input_buffers: null pointer");
+    if (!net->bound) {
+        set_error("net_input_buffers: call msi_net_bind first");
+        return MSI_ERR_STATE;
+    }
+    *hi = net->acts[0].hi;
+    *lo = net->acts[0].lo;
+    return MSI_OK;
+}
+
+extern "C" int msi_net_read_activation(msi_net* net, const char* scope, int B, float* out, void* stream) {
+    MSI_CHECK_ARG(net && scope && out, "net_read_activation: null pointer");
+    const int ai = find_act(net, scope);
+    MSI_CHECK_ARG(ai >= 0 && ai < kNumLayers, "net_read_activation: unknown or un-normalised scope '%s'", scope);
+    const ActBuf& a = net->acts[ai];
+    return merge_activation(a.hi, a.lo, (long long)B * a.H * a.W, a.C, a.c_stride, out,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msi_net_read_raw(msi_net* net, const char* scope, int B, float* out, void* stream) {
+    MSI_CHECK_ARG(net && scope && out, "net_read_raw: null pointer");
+    const int ai = find_act(net, scope);
+    MSI_CHECK_ARG(ai >= 1 && ai < kNumLayers, "net_read_raw: unknown or un-normalised scope '%s'", scope);
+    const LayerPlan& L = net->layers[ai - 1];
+    MSI_CUDA(cudaMemcpyAsync(out, L.raw, (size_t)B * L.Hout * L.Wout * L.cout * sizeof(float),
+                             cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    return MSI_OK;
+}

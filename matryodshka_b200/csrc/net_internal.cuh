@@ -1,0 +1,118 @@
+// Internal description of the conv net (nets.py:471-515) shared by the host orchestration
+// (net.cu) and the conv back ends (conv_simt.cu, conv_tcgen05.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace msi {
+
+enum LayerKind { kConv = 0, kDeconv = 1, kHead = 2 };
+
+// One activation tensor in the workspace: post-LayerNorm+ReLU values scaled by MSI_ACT_SCALE and
+// split into fp16 hi + lo, NHWC with channel stride c_stride (>= C, multiple of 64 for tcgen05).
+struct ActBuf {
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    int H = 0, W = 0, C = 0, c_stride = 0;
+};
+
+struct LayerPlan {
+    char scope[16];
+    int kind;
+    int k, stride, rate;
+    int nsrc;
+    int src[2];  // activation indices; -1 = network input
+    int cin[2];
+    int cin_total;
+    int cout;
+    int Hin, Win, Hout, Wout;
+    int pad_t, pad_l;  // SAME padding before (conv)
+    // arena (parameters)
+    float* w_f32 = nullptr;   // TF layout as loaded
+    float* gamma = nullptr;
+    float* beta = nullptr;
+    float* bias = nullptr;    // head only
+    float* cbias = nullptr;   // coord-channel bias table [Hout][8][cout] (conv only)
+    __half* w_hi = nullptr;   // packed K-major [ncls][cout][K], scaled by MSI_WEIGHT_SCALE
+    __half* w_lo = nullptr;
+    int K = 0;                // packed reduction length = ntaps * sum(c_stride of sources)
+    int ncls = 1;             // 4 output-parity classes for deconv
+    bool loaded = false;
+    // workspace
+    float* raw = nullptr;     // [B,Hout,Wout,cout] pre-LayerNorm conv output (head: pred, caller's buffer)
+    double2* partials = nullptr;  // [B][n_partials] (sum, sumsq)
+    float2* stats = nullptr;      // [B] (mean, rstd)
+    int n_partials = 0;
+    int out_act = -1;         // index of the activation this layer produces
+    void* tc_plan = nullptr;  // back-end private (TMA descriptors, tile shape)
+};
+
+// Geometry of one gather tap of the implicit GEMM.
+struct TapList {
+    int n;
+    int dy[9], dx[9];  // input offset added to (o * in_stride)
+    int wtap[9];       // index of the (kh,kw) weight slice
+};
+
+// conv: input = o*stride + k*rate - pad.  deconv class (py,px): input = o + d, output = 2*o + parity.
+inline TapList conv_taps(const LayerPlan& L) {
+    TapList t;
+    t.n = L.k * L.k;
+    for (int kh = 0; kh < L.k; ++kh)
+        for (int kw = 0; kw < L.k; ++kw) {
+            const int i = kh * L.k + kw;
+            t.dy[i] = kh * L.rate - L.pad_t;
+            t.dx[i] = kw * L.rate - L.pad_l;
+            t.wtap[i] = i;
+        }
+    return t;
+}
+
+// 4x4 stride-2 SAME transposed conv, oy = 2*iy - 1 + kh:
+//   oy even (py=0): kh=1 -> iy=o, kh=3 -> iy=o-1;   oy odd (py=1): kh=0 -> iy=o+1, kh=2 -> iy=o
+inline void deconv_axis(int parity, int t, int& k, int& d) {
+    if (parity == 0) {
+        k = (t == 0) ? 1 : 3;
+        d = (t == 0) ? 0 : -1;
+    } else {
+        k = (t == 0) ? 0 : 2;
+        d = (t == 0) ? 1 : 0;
+    }
+}
+
+inline TapList deconv_taps(int py, int px) {
+    TapList t;
+    t.n = 4;
+    for (int th = 0; th < 2; ++th)
+        for (int tw = 0; tw < 2; ++tw) {
+            int kh, dy, kw, dx;
+            deconv_axis(py, th, kh, dy);
+            deconv_axis(px, tw, kw, dx);
+            const int i = th * 2 + tw;
+            t.dy[i] = dy;
+            t.dx[i] = dx;
+            t.wtap[i] = kh * 4 + kw;
+        }
+    return t;
+}
+
+// back ends -------------------------------------------------------------------------------
+int conv_simt_forward(const LayerPlan& L, const ActBuf* srcs, int B, float* out, cudaStream_t st);
+
+int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int precision);
+void conv_tc_plan_destroy(LayerPlan& L);
+int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st);
+int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
+
+// LayerNorm ---------------------------------------------------------------------------------
+int ln_partials_count(long long n_per_sample);
+int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
+               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
+               bool partials_ready, cudaStream_t st);
+int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st);
+int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
+                     cudaStream_t st);
+int coord_bias_build(const LayerPlan& L, const float* coord_rows_dev, cudaStream_t st);
+
+}  // namespace msi

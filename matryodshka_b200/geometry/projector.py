@@ -1,0 +1,45 @@
+"""Mirror of geometry/projector.py for the functions on the MSI inference path."""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def _baselines(intrinsics):
+    k = intrinsics.detach().cpu().numpy() if torch.is_tensor(intrinsics) else np.asarray(intrinsics)
+    return k.astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
+
+
+def ods_sphere_sweep(image, order, depths, pose, intrinsics):
+    """projector.py:209-211 (sweep_one :129-170 with the ODS functions).  image [B,H,W,3]
+    (already preprocessed), order +1 / -1, pose [B,4,4] -> [B,H,W,3P], channel = p*3 + rgb."""
+    B = image.shape[0]
+    P = len(depths)
+    pose = torch.as_tensor(pose, dtype=torch.float32).reshape(B, 1, 16).repeat(1, 2, 1)
+    psv = ops.psv_build(image, image, pose, _baselines(intrinsics), list(depths), preprocess=False)
+    e = 0 if order > 0 else 1
+    return psv[..., e * 3 * P:(e + 1) * 3 * P].contiguous()
+
+
+def sweep_one(image, order, depths, pose, intrinsics, st_fun=None, backproj_fun=None, proj_fun=None):
+    """projector.py:129-170; only the ODS function triple is built (the callbacks are accepted
+    for signature compatibility and must be the spherical ones or None)."""
+    return ods_sphere_sweep(image, order, depths, pose, intrinsics)
+
+
+def projective_forward_sphere(src_images, intrinsics, tgt_pose_rt, tgt_pos, depths):
+    """projector.py:34-62.  src_images [L,B,H,W,4], depths [L,B] (columns identical) ->
+    reprojected layers [L,B,H,W,4]."""
+    rgba = src_images.permute(1, 2, 3, 0, 4).contiguous()
+    d = depths[:, 0] if torch.is_tensor(depths) else np.asarray(depths)[:, 0]
+    return ops.project_layers(rgba, tgt_pose_rt, torch.as_tensor(tgt_pos).reshape(-1, 3), d)
+
+
+def over_composite(rgbas):
+    """projector.py:246-265.  list (back to front) of [B,H,W,4] -> [B,H,W,3]."""
+    return ops.over_composite(torch.stack(list(rgbas), 0))
+
+
+def over_composite_depth(rgbas):
+    """projector.py:225-244."""
+    return ops.over_composite(torch.stack(list(rgbas), 0), depth_mode=True)

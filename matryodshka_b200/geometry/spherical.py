@@ -1,0 +1,37 @@
+"""Mirror of geometry/spherical.py for the functions on the MSI inference path.
+
+``lat_long_grid`` is host table logic (float32 NumPy, TF-1.14 LinSpace semantics) uploaded
+to the GPU; the per-pixel projections run in csrc/geom_kernels.cu.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def lat_long_grid(shape, epsilon=1.0e-12, device="cuda"):
+    """spherical.py:42-44 -> S, T [H, W] float32 (pixel-centre longitudes / latitudes)."""
+    H, W = shape
+    s, t = ops.lat_long_axes(H, W)
+    S, T = np.meshgrid(s, t)
+    return torch.from_numpy(S.copy()).to(device), torch.from_numpy(T.copy()).to(device)
+
+
+def intersect_sphere(pos, center, radius, num_planes, num_batch, width, height, epsilon=1e-12):
+    """spherical.py:268-326 -> uv [L, H, W, 2]: where the target-view ray of every ERP pixel
+    hits each sphere, in source pixel coordinates.  pos [4,4], center [3], radius [L]."""
+    dev = radius.device if torch.is_tensor(radius) else (pos.device if torch.is_tensor(pos) else "cuda")
+    pos = torch.as_tensor(pos, dtype=torch.float32).reshape(1, 4, 4)
+    center = torch.as_tensor(center, dtype=torch.float32).reshape(1, 3)
+    uv = ops.intersect_sphere_coords(pos, center, radius, 1, height, width, dev)
+    return uv[0]
+
+
+def project_ods_sweep(depths, pose, intrinsics, order, width, height, device="cuda"):
+    """backproject_spherical (:116-129) + apply_pose + project_ods (:170-233) for the whole ERP
+    grid: uv [P, H, W, 2] and the `disc >= 0` mask [P, H, W] for one eye (order = +1 / -1)."""
+    pose = torch.as_tensor(pose, dtype=torch.float32).reshape(1, 1, 16).repeat(1, 2, 1)
+    base = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(-1, 3, 3)[:1, 0, 0]
+    uv, valid = ops.sweep_coords(pose, base, depths, 1, height, width, device)
+    e = 0 if order > 0 else 1
+    return uv[0, e], valid[0, e].bool()

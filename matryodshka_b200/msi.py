@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's ``matryodshka/msi.py`` -- class ``MSI``, inference half.
+
+Same method names, argument order and dict keys as the reference (msi.py:40-52, :276-289,
+:384-452, :1094-1217) so that a driver written against ``matryodshka.msi.MSI`` reads the same.
+What the reference takes from TF graph-global state is explicit here:
+
+* the FLAGS it reads deep inside (``input_type``, ``operation``, ``coord_net``, ``ngf`` ...;
+  msi.py:70,81,95-105,120-127) are a frozen ``MSIConfig``;
+* the hidden graph tensors ``ref_pose_inv:0`` / ``jitter_pose_inv:0`` (msi.py:1113-1119) are the
+  keyword arguments ``ref_pose_inv`` / ``jitter_pose_inv``;
+* the TF variables under scope ``net/`` are a ``weights`` dict keyed by the checkpoint names.
+
+Tensors are torch CUDA tensors, NHWC float32 (images in [0,1] at the API).  All arithmetic runs
+in the sm_100a kernels behind include/msi_b200.h; there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .runtime import NetEngine
+
+
+@dataclass(frozen=True)
+class MSIConfig:
+    """The reference's flags for this path, same names and defaults (test.py:39-83, loader.py:30-42)."""
+    height: int = 320
+    width: int = 640
+    num_psv_planes: int = 32
+    num_msi_planes: int = 32
+    min_depth: float = 1.0
+    max_depth: float = 100.0
+    ngf: int = 64
+    which_color_pred: str = "blend_psv"
+    coord_net: bool = True
+    input_type: str = "ODS"
+    operation: str = "train"
+    transform_inverse_reg: bool = False
+    jitter: bool = False
+    net_only: bool = False
+    supervision: str = "tgt"
+    batch_size: int = 1
+    # back-end selection (ours)
+    conv_impl: str = "tcgen05"
+    precision: str = "fp16x3"
+
+
+def _matmul44_f32(a, b):
+    """[N,4,4] x [N,4,4] in float32 with the k-sum evaluated left to right."""
+    a = np.asarray(a, np.float32).reshape(-1, 4, 4)
+    b = np.asarray(b, np.float32).reshape(-1, 4, 4)
+    out = np.zeros_like(a)
+    for i in range(4):
+        for j in range(4):
+            acc = a[:, i, 0] * b[:, 0, j]
+            for k in range(1, 4):
+                acc = acc + a[:, i, k] * b[:, k, j]
+            out[:, i, j] = acc
+    return out
+
+
+def _host(x):
+    return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+
+
+class MSI(object):
+    """Multi-sphere-image inference (reference class ``MSI``, msi.py:33)."""
+
+    def __init__(self, weights=None, config: Optional[MSIConfig] = None, device="cuda"):
+        self.config = config or MSIConfig()
+        self.weights = weights
+        self.device = torch.device(device)
+        self._engines = {}
+
+    # ---- msi.py:1196-1217 ------------------------------------------------------------------
+    def inv_depths(self, start_depth, end_depth, num_depths):
+        """Depths uniform in inverse depth, sorted far -> near (python floats)."""
+        inv_start_depth = 1.0 / start_depth
+        inv_end_depth = 1.0 / end_depth
+        depths = [start_depth, end_depth]
+        for i in range(1, num_depths - 1):
+            fraction = float(i) / float(num_depths - 1)
+            inv_depth = inv_start_depth + (inv_end_depth - inv_start_depth) * fraction
+            depths.append(1.0 / inv_depth)
+        depths = sorted(depths)
+        return depths[::-1]
+
+    # ---- msi.py:1163-1194 --------------------------------------------------------------------
+    def preprocess_image(self, image):
+        """float [0,1] or uint8 [0,255] -> float32 [-1,1].  (On the fused path this happens inside
+        msi_psv_build; this stand-alone form is API glue on a [B,H,W,3] tensor.)"""
+        if image.dtype == torch.uint8:
+            image = image.to(torch.float32) * np.float32(1.0 / 255)
+        return image.to(torch.float32) * 2 - 1
+
+    def deprocess_image(self, image):
+        """float32 [-1,1] -> uint8, tf.image.convert_image_dtype semantics (x*255.5 truncated)."""
+        image = (image + 1.0) / 2.0
+        return (image * 255.5).to(torch.int32).to(torch.uint8)
+
+    def deprocess_depth_image(self, image):
+        return (image * 255.5).to(torch.int32).to(torch.uint8)
+
+    # ---- msi.py:1094-1130 ----------------------------------------------------------------------
+    def _sweep_poses(self, ref_pose, src_pose, ref_pose_inv=None, jitter_pose_inv=None):
+        ref_pose = _host(ref_pose).astype(np.float32).reshape(-1, 4, 4)
+        src_pose = _host(src_pose).astype(np.float32).reshape(-1, 4, 4)
+        if ref_pose_inv is None:
+            ref_pose_inv = np.linalg.inv(ref_pose.astype(np.float64)).astype(np.float32)
+        ref_pose_inv = _host(ref_pose_inv).astype(np.float32).reshape(-1, 4, 4)
+        if jitter_pose_inv is not None:
+            ref_pose_inv = _matmul44_f32(ref_pose_inv, _host(jitter_pose_inv))
+        eye0 = _matmul44_f32(ref_pose, ref_pose_inv)
+        eye1 = _matmul44_f32(src_pose, ref_pose_inv)
+        return np.stack([eye0, eye1], axis=1)  # [B,2,4,4]
+
+    def format_network_input(self, ref_image, src_image, ref_pose, src_pose, planes, intrinsics,
+                             ref_pose_inv=None, jitter_pose_inv=None):
+        """Double plane-sweep volume [B,H,W,6P] from preprocessed ([-1,1]) images; channel =
+        eye*3P + p*3 + rgb, eye 0 = ref (order +1), eye 1 = src (order -1)."""
+        poses = self._sweep_poses(ref_pose, src_pose, ref_pose_inv, jitter_pose_inv)
+        baselines = _host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
+        return ops.psv_build(ref_image, src_image, poses, baselines, list(planes), preprocess=False)
+
+    def sweep_src(self, image, order, depths, pose, intrinsics):
+        from .geometry import projector as pj
+        return pj.ods_sphere_sweep(image, order, depths, pose, intrinsics)
+
+    # ---- msi.py:40-289 ---------------------------------------------------------------------------
+    def _engine(self, H, W, c_in, c_out, ngf, max_batch):
+        key = (H, W, c_in, c_out, ngf, max_batch)
+        eng = self._engines.get(key)
+        if eng is None:
+            if self.weights is None:
+                raise _lib.MsiError("MSI.infer_msi needs weights (MSI(weights=...))")
+            eng = NetEngine(self.weights, H, W, c_in, c_out, ngf, self.device, max_batch=max_batch,
+                            conv_impl=self.config.conv_impl, precision=self.config.precision)
+            self._engines[key] = eng
+        return eng
+
+    def infer_msi(self, raw_src_image, raw_ref_image, raw_hres_src_image, raw_hres_ref_image,
+                  ref_pose, src_pose, intrinsics, which_color_pred, num_msi_planes, psv_planes,
+                  extra_outputs='', ngf=64, ref_pose_inv=None, jitter_pose_inv=None):
+        """Same signature as the reference (argument order src, ref).  Returns (pred dict, net_input)
+        with pred['rgba_layers'] [B,H,W,L,4] always and 'blend_weights' / 'alphas' / 'psv' when the
+        substring is in ``extra_outputs`` (msi.py:276-288)."""
+        cfg = self.config
+        if which_color_pred != 'blend_psv':
+            raise NotImplementedError("only which_color_pred='blend_psv' is built (SURVEY.md 8f-4)")
+        if cfg.input_type != 'ODS' or cfg.operation != 'train' or not cfg.coord_net:
+            raise NotImplementedError("only input_type=ODS, operation=train, coord_net=True is built")
+        B, H, W, _ = raw_src_image.shape
+        P = len(psv_planes)
+        if P != num_msi_planes:
+            raise ValueError("blend_psv needs len(psv_planes) == num_msi_planes")
+        poses = self._sweep_poses(ref_pose, src_pose, ref_pose_inv, jitter_pose_inv)
+        baselines = _host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
+        eng = self._engine(H, W, 6 * P, 2 * num_msi_planes, ngf, B)
+        hi, lo = eng.input_buffers(B)
+        # preprocessing (msi.py:73-75) is fused into the sweep kernel
+        net_input = ops.psv_build(raw_ref_image, raw_src_image, poses, baselines, list(psv_planes),
+                                  preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride)
+        if cfg.net_only:
+            eng.forward(hi_lo=(hi, lo))
+            return None
+        msi_pred = eng.forward(hi_lo=(hi, lo))
+        want_w = ('blend_weights' in extra_outputs) or ('alpha' in extra_outputs)
+        rgba, bw, al = ops.rgba_assemble(msi_pred, net_input, want_weights=want_w)
+        pred = {'rgba_layers': rgba}
+        if 'blend_weights' in extra_outputs and 'blend' in which_color_pred:
+            pred['blend_weights'] = bw
+        if 'alpha' in extra_outputs:
+            pred['alphas'] = al
+        if 'psv' in extra_outputs:
+            pred['psv'] = net_input
+        return pred, net_input
+
+    # ---- msi.py:384-452 ------------------------------------------------------------------------
+    def msi_render_equirect_view(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
+        """Rendered view [B,H,W,3] in [-1,1]."""
+        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes), want_rgb=True,
+                                    want_depth=False, want_u8=False)["rgb"]
+
+    def msi_render_equirect_depth(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
+        """Composited normalised layer index [B,H,W,3] in [0,1)."""
+        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes), want_rgb=False,
+                                    want_depth=True, want_u8=False)["depth"]
+
+    def msi_render_equirect(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
+        """Ours: colour and depth (float32 + deprocessed uint8) from ONE reprojection."""
+        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes))
+
+    def msi_render_equirect_view_single(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
+        """Reprojected layers without compositing [L,B,H,W,4] (msi.py:431-452)."""
+        planes = planes.tolist() if torch.is_tensor(planes) else list(planes)
+        return ops.project_layers(rgba_layers, tgt_pose_rt, tgt_pos, planes)
+
+    msi_render_equirect_depth_single = msi_render_equirect_view_single

@@ -1,0 +1,228 @@
+"""Tensor-level entry points over the C ABI: one Python function per kernel family.
+
+Inputs and outputs are torch CUDA tensors (torch is the allocator and the stream owner,
+nothing else); the arithmetic happens in libmsi_b200.so.  Work is enqueued on torch's current
+stream.  The ERP-coord tables (cos/sin of the pixel-centre longitudes/latitudes) are computed
+once per (H, W, device) on the host in float32 -- the same way a CPU evaluation of the
+reference would -- and uploaded, which is what makes the project_ods `disc < 0` mask
+bit-reproducible on the GPU (csrc/geom_device.cuh).
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _linspace_tf(start, stop, num):
+    """[TF-1.14 LinSpace]: float32 ``start + step * i`` with ``step = (stop - start) / (num - 1)``."""
+    start = np.float32(start)
+    stop = np.float32(stop)
+    if num == 1:
+        return np.array([start], np.float32)
+    step = np.float32((stop - start) / np.float32(num - 1))
+    return (start + step * np.arange(num).astype(np.float32)).astype(np.float32)
+
+
+def lat_long_axes(H, W):
+    """Pixel-centre longitudes s[W] and latitudes t[H] (spherical.py:42-44), float32 NumPy."""
+    s = _linspace_tf(-np.pi + np.pi / W, np.pi - np.pi / W, W)
+    t = _linspace_tf(-np.pi / 2.0 + np.pi / (2 * H), np.pi / 2.0 - np.pi / (2 * H), H)
+    return s, t
+
+
+class ErpTables:
+    """cos/sin of the ERP pixel-centre angles on a device."""
+
+    def __init__(self, H, W, device):
+        s, t = lat_long_axes(H, W)
+        self.H, self.W = H, W
+        self.s, self.t = s, t
+        self.cos_s = torch.from_numpy(np.cos(s)).to(device)
+        self.sin_s = torch.from_numpy(np.sin(s)).to(device)
+        self.cos_t = torch.from_numpy(np.cos(t)).to(device)
+        self.sin_t = torch.from_numpy(np.sin(t)).to(device)
+
+    def ptrs(self):
+        return ptr(self.cos_s), ptr(self.sin_s), ptr(self.cos_t), ptr(self.sin_t)
+
+
+@functools.lru_cache(maxsize=32)
+def _tables_cached(H, W, dev_str):
+    return ErpTables(H, W, torch.device(dev_str))
+
+
+def erp_tables(H, W, device) -> ErpTables:
+    return _tables_cached(int(H), int(W), str(torch.device(device)))
+
+
+def _dev_f32(x, device, shape=None):
+    """Small host array / tensor -> contiguous float32 CUDA tensor."""
+    if torch.is_tensor(x):
+        t = x.to(device=device, dtype=torch.float32)
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.float32), device=device)
+    if shape is not None:
+        t = t.reshape(shape)
+    return t.contiguous()
+
+
+def psv_build(ref, src, poses, baselines, depths, *, preprocess=True, want_f32=True, hi_lo=None, c_stride=None):
+    """msi_psv_build.  ref/src: [B,H,W,3] float32 or uint8 CUDA tensors; poses [B,2,4,4];
+    baselines [B]; depths [P].  Returns the float32 PSV [B,H,W,6P] (or None); ``hi_lo`` is an
+    optional (hi, lo) pair of fp16 [B,H,W,c_stride] tensors filled with the conv-operand copy."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    assert ref.shape == src.shape and ref.dim() == 4 and ref.shape[3] == 3
+    B, H, W, _ = ref.shape
+    dev = ref.device
+    depths = _dev_f32(depths, dev, (-1,))
+    P = depths.numel()
+    poses = _dev_f32(poses, dev, (B, 2, 16))
+    baselines = _dev_f32(baselines, dev, (B,))
+    tb = erp_tables(H, W, dev)
+    if ref.dtype == torch.uint8:
+        dt = _lib.IMG_U8
+    elif ref.dtype == torch.float32:
+        dt = _lib.IMG_F32
+    else:
+        raise _lib.MsiError(f"psv_build: unsupported image dtype {ref.dtype}")
+    out = torch.empty((B, H, W, 6 * P), dtype=torch.float32, device=dev) if want_f32 else None
+    hi = lo = None
+    cs = 6 * P
+    if hi_lo is not None:
+        hi, lo = hi_lo
+        cs = int(c_stride if c_stride is not None else hi.shape[-1])
+    check(lib.msi_psv_build(ptr(ref.contiguous()), ptr(src.contiguous()), dt, 1 if preprocess else 0,
+                            ptr(poses), ptr(baselines), ptr(depths), *tb.ptrs(), B, H, W, P,
+                            ptr(out), ptr(hi), ptr(lo), cs, stream_ptr()), "msi_psv_build")
+    return out
+
+
+def sweep_coords(poses, baselines, depths, B, H, W, device):
+    """msi_sweep_coords -> (uv [B,2,P,H,W,2] float32, valid [B,2,P,H,W] uint8)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    depths = _dev_f32(depths, device, (-1,))
+    P = depths.numel()
+    poses = _dev_f32(poses, device, (B, 2, 16))
+    baselines = _dev_f32(baselines, device, (B,))
+    tb = erp_tables(H, W, device)
+    uv = torch.empty((B, 2, P, H, W, 2), dtype=torch.float32, device=device)
+    valid = torch.empty((B, 2, P, H, W), dtype=torch.uint8, device=device)
+    check(lib.msi_sweep_coords(ptr(poses), ptr(baselines), ptr(depths), *tb.ptrs(), B, H, W, P, ptr(uv), ptr(valid),
+                               stream_ptr()), "msi_sweep_coords")
+    return uv, valid
+
+
+def rgba_assemble(pred, psv=None, *, hi_lo=None, c_stride=None, want_weights=False):
+    """msi_rgba_assemble.  pred [B,H,W,2L]; psv float32 [B,H,W,6L] or the fp16 (hi, lo) pair.
+    Returns (rgba [B,H,W,L,4], blend_weights | None, alphas | None)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, C2 = pred.shape
+    L = C2 // 2
+    dev = pred.device
+    rgba = torch.empty((B, H, W, L, 4), dtype=torch.float32, device=dev)
+    bw = torch.empty((B, H, W, L), dtype=torch.float32, device=dev) if want_weights else None
+    al = torch.empty((B, H, W, L), dtype=torch.float32, device=dev) if want_weights else None
+    hi = lo = None
+    cs = 6 * L
+    if psv is None:
+        hi, lo = hi_lo
+        cs = int(c_stride if c_stride is not None else hi.shape[-1])
+    else:
+        assert psv.shape[-1] == 6 * L, "blend_psv needs num_psv_planes == num_msi_planes"
+    check(lib.msi_rgba_assemble(ptr(pred.contiguous()), ptr(psv.contiguous() if psv is not None else None),
+                                ptr(hi), ptr(lo), cs, B, H, W, L, ptr(rgba), ptr(bw), ptr(al), stream_ptr()),
+          "msi_rgba_assemble")
+    return rgba, bw, al
+
+
+def render_composite(rgba, tgt_pose_rt, tgt_pos, depths, *, want_rgb=True, want_depth=True, want_u8=True,
+                     out=None):
+    """msi_render_composite.  rgba [B,H,W,L,4]; tgt_pose_rt [B,4,4]; tgt_pos [B,3]; depths [L].
+    Returns dict with 'rgb', 'depth' (float32 [B,H,W,3]) and 'rgb_u8', 'depth_u8'."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, L, four = rgba.shape
+    assert four == 4
+    dev = rgba.device
+    depths = _dev_f32(depths, dev, (-1,))
+    assert depths.numel() == L
+    pose = _dev_f32(tgt_pose_rt, dev, (B, 16))
+    pos = _dev_f32(tgt_pos, dev, (B, 3))
+    tb = erp_tables(H, W, dev)
+    res = out if out is not None else {}
+    if want_rgb and "rgb" not in res:
+        res["rgb"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    if want_depth and "depth" not in res:
+        res["depth"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    if want_u8 and want_rgb and "rgb_u8" not in res:
+        res["rgb_u8"] = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    if want_u8 and want_depth and "depth_u8" not in res:
+        res["depth_u8"] = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    check(lib.msi_render_composite(ptr(rgba.contiguous()), ptr(pose), ptr(pos), ptr(depths), *tb.ptrs(), B, H, W, L,
+                                   ptr(res.get("rgb")), ptr(res.get("depth")), ptr(res.get("rgb_u8")),
+                                   ptr(res.get("depth_u8")), stream_ptr()), "msi_render_composite")
+    return res
+
+
+def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device):
+    """msi_intersect_sphere_coords -> uv [B,L,H,W,2]."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    depths = _dev_f32(depths, device, (-1,))
+    L = depths.numel()
+    pose = _dev_f32(tgt_pose_rt, device, (B, 16))
+    pos = _dev_f32(tgt_pos, device, (B, 3))
+    tb = erp_tables(H, W, device)
+    uv = torch.empty((B, L, H, W, 2), dtype=torch.float32, device=device)
+    check(lib.msi_intersect_sphere_coords(ptr(pose), ptr(pos), ptr(depths), *tb.ptrs(), B, H, W, L, ptr(uv),
+                                          stream_ptr()), "msi_intersect_sphere_coords")
+    return uv
+
+
+def project_layers(rgba, tgt_pose_rt, tgt_pos, depths):
+    """msi_project_layers -> [L,B,H,W,4]."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, L, _ = rgba.shape
+    dev = rgba.device
+    depths = _dev_f32(depths, dev, (-1,))
+    pose = _dev_f32(tgt_pose_rt, dev, (B, 16))
+    pos = _dev_f32(tgt_pos, dev, (B, 3))
+    tb = erp_tables(H, W, dev)
+    out = torch.empty((L, B, H, W, 4), dtype=torch.float32, device=dev)
+    check(lib.msi_project_layers(ptr(rgba.contiguous()), ptr(pose), ptr(pos), ptr(depths), *tb.ptrs(), B, H, W, L,
+                                 ptr(out), stream_ptr()), "msi_project_layers")
+    return out
+
+
+def resample(image, coords):
+    """msi_resample (sampling.py:135-197).  image [N,H,W,C], coords [N,h,w,2] -> [N,h,w,C]."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    N, H, W, C = image.shape
+    n2, h, w, two = coords.shape
+    assert n2 == N and two == 2
+    out = torch.empty((N, h, w, C), dtype=torch.float32, device=image.device)
+    check(lib.msi_resample(ptr(image.contiguous().float()), ptr(coords.contiguous().float()), N, H, W, C, h, w,
+                           ptr(out), stream_ptr()), "msi_resample")
+    return out
+
+
+def over_composite(layers, depth_mode=False):
+    """msi_over_composite.  layers [L,B,H,W,4] back to front -> [B,H,W,3]."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    L, B, H, W, four = layers.shape
+    assert four == 4
+    out = torch.empty((B, H, W, 3), dtype=torch.float32, device=layers.device)
+    check(lib.msi_over_composite(ptr(layers.contiguous()), L, B, H, W, 1 if depth_mode else 0, ptr(out),
+                                 stream_ptr()), "msi_over_composite")
+    return out

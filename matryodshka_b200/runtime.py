@@ -1,0 +1,298 @@
+"""Runtime objects of the MSI inference path: the conv-net engine and the frame pipeline.
+
+``NetEngine``   owns one ``msi_net`` (C ABI), its workspace / parameter arena (torch uint8
+                CUDA storage) and the packed weights.
+``MSIPipeline`` runs whole frames: host images -> PSV -> net -> RGBA layers -> rendered ERP
+                view (+ depth), with the per-batch launch sequence captured in a CUDA graph,
+                pinned host staging for the end-to-end path, and frame sharding across ranks
+                with one all-gather of the rendered outputs.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+from .nets import ARCH
+
+_CONV_IMPL = {"tcgen05": _lib.CONV_TCGEN05, "simt": _lib.CONV_SIMT}
+_PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16}
+
+
+def _aligned_bytes(n, device):
+    """uint8 CUDA buffer of >= n bytes whose base is 1024-byte aligned."""
+    buf = torch.empty(n + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf, off
+
+
+class NetEngine:
+    """nets.msi_coord_train_net (nets.py:471-515) on the GPU.
+
+    weights: dict keyed by the TF checkpoint variable names (``net/<scope>/weights`` ...),
+    NumPy arrays or tensors in the TF layouts."""
+
+    _cache: Dict[tuple, "NetEngine"] = {}
+
+    def __init__(self, weights, H, W, c_in, c_out, ngf=64, device="cuda", max_batch=1,
+                 conv_impl="tcgen05", precision="fp16x3", vscope="net"):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.H, self.W, self.c_in, self.c_out, self.ngf = H, W, c_in, c_out, ngf
+        self.max_batch = max_batch
+        self.conv_impl, self.precision = conv_impl, precision
+        self._h = c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.msi_net_create(ctypes.byref(self._h), H, W, c_in, c_out, ngf, max_batch,
+                                          _CONV_IMPL[conv_impl], _PRECISION[precision]), "msi_net_create")
+            self.ws_bytes = int(self.lib.msi_net_workspace_bytes(self._h))
+            self.arena_bytes = int(self.lib.msi_net_arena_bytes(self._h))
+            self._ws, wo = _aligned_bytes(self.ws_bytes, self.device)
+            self._arena, ao = _aligned_bytes(self.arena_bytes, self.device)
+            check(self.lib.msi_net_bind(self._h, c_void_p(self._ws.data_ptr() + wo), self.ws_bytes,
+                                        c_void_p(self._arena.data_ptr() + ao), self.arena_bytes), "msi_net_bind")
+            self.in_c_stride = int(self.lib.msi_net_input_c_stride(self._h))
+            self.load_weights(weights, vscope)
+        self.launches_per_forward = int(self.lib.msi_net_num_launches_per_forward(self._h))
+
+    @classmethod
+    def cached(cls, weights, H, W, c_in, c_out, ngf, device, vscope="net", **kw):
+        key = (id(weights), H, W, c_in, c_out, ngf, str(device), vscope, tuple(sorted(kw.items())))
+        eng = cls._cache.get(key)
+        if eng is None:
+            eng = cls(weights, H, W, c_in, c_out, ngf, device, vscope=vscope, **kw)
+            cls._cache[key] = eng
+        return eng
+
+    def load_weights(self, weights, vscope="net"):
+        def dev(name):
+            if name not in weights:
+                return None
+            w = weights[name]
+            if not torch.is_tensor(w):
+                w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+            return w.to(device=self.device, dtype=torch.float32).contiguous()
+
+        keep = []
+        for l in ARCH:
+            w = dev(f"{vscope}/{l.scope}/weights")
+            if w is None:
+                raise _lib.MsiError(f"missing weights for {vscope}/{l.scope}")
+            g = dev(f"{vscope}/{l.scope}/LayerNorm/gamma")
+            b = dev(f"{vscope}/{l.scope}/LayerNorm/beta")
+            bias = dev(f"{vscope}/{l.scope}/biases")
+            keep += [w, g, b, bias]
+            check(self.lib.msi_net_load_layer(self._h, l.scope.encode(), ptr(w), ptr(g), ptr(b), ptr(bias),
+                                              stream_ptr()), f"msi_net_load_layer({l.scope})")
+        torch.cuda.current_stream().synchronize()  # staging tensors in `keep` may now be freed
+
+    def input_buffers(self, B):
+        """(hi, lo) fp16 views [B,H,W,in_c_stride] of the workspace copy of the net input."""
+        hi, lo = c_void_p(), c_void_p()
+        check(self.lib.msi_net_input_buffers(self._h, ctypes.byref(hi), ctypes.byref(lo)), "msi_net_input_buffers")
+        n = B * self.H * self.W * self.in_c_stride
+
+        def view(p):
+            off = p.value - self._ws.data_ptr()
+            return self._ws[off:off + 2 * n].view(torch.float16).view(B, self.H, self.W, self.in_c_stride)
+        return view(hi), view(lo)
+
+    def forward(self, psv=None, *, hi_lo=None, out=None):
+        """psv: float32 [B,H,W,c_in] (or hi_lo = the fp16 operand pair).  Returns pred [B,H,W,c_out]."""
+        if psv is not None:
+            B = psv.shape[0]
+            assert tuple(psv.shape[1:]) == (self.H, self.W, self.c_in), psv.shape
+            psv = psv.contiguous()
+        else:
+            B = hi_lo[0].shape[0]
+        if out is None:
+            out = torch.empty((B, self.H, self.W, self.c_out), dtype=torch.float32, device=self.device)
+        hi, lo = hi_lo if hi_lo is not None else (None, None)
+        check(self.lib.msi_net_forward(self._h, ptr(psv), ptr(hi), ptr(lo), B, ptr(out), stream_ptr()),
+              "msi_net_forward")
+        return out
+
+    def read_activation(self, scope, B=1):
+        from .nets import layer_channels, layer_geometry
+        ch = layer_channels(self.c_in, self.c_out, self.ngf)[scope]
+        h, w = layer_geometry(self.H, self.W)[scope]
+        out = torch.empty((B, h, w, ch), dtype=torch.float32, device=self.device)
+        check(self.lib.msi_net_read_activation(self._h, scope.encode(), B, ptr(out), stream_ptr()), "read_activation")
+        return out
+
+    def read_raw(self, scope, B=1):
+        from .nets import layer_channels, layer_geometry
+        ch = layer_channels(self.c_in, self.c_out, self.ngf)[scope]
+        h, w = layer_geometry(self.H, self.W)[scope]
+        out = torch.empty((B, h, w, ch), dtype=torch.float32, device=self.device)
+        check(self.lib.msi_net_read_raw(self._h, scope.encode(), B, ptr(out), stream_ptr()), "read_raw")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self.lib.msi_net_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+
+class MSIPipeline:
+    """End-to-end frames on one GPU: (ref, src) ODS pair -> rendered ERP view + depth.
+
+    Stages (all kernels of libmsi_b200.so, enqueued on one stream, graph-captured per batch size):
+      K1 msi_psv_build      -> PSV as the net's fp16 hi/lo operand, written straight into the net input
+      K2 msi_net_forward    -> pred [B,H,W,2L]
+      K4 msi_rgba_assemble  -> RGBA layers [B,H,W,L,4]
+      K5 msi_render_composite -> rgb / depth (float32 + uint8)
+    """
+
+    def __init__(self, weights, H=320, W=640, num_planes=32, ngf=64, batch=1, device="cuda",
+                 min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16x3",
+                 img_dtype=torch.float32, use_graph=True):
+        _lib.require_cuda()
+        from .msi import MSI
+        self.device = torch.device(device)
+        self.H, self.W, self.P, self.B = H, W, num_planes, batch
+        self.planes = MSI().inv_depths(min_depth, max_depth, num_planes)
+        self.net = NetEngine(weights, H, W, 6 * num_planes, 2 * num_planes, ngf, self.device, max_batch=batch,
+                             conv_impl=conv_impl, precision=precision)
+        dev = self.device
+        B = batch
+        self.img_dtype = img_dtype
+        self.ref = torch.empty((B, H, W, 3), dtype=img_dtype, device=dev)
+        self.src = torch.empty((B, H, W, 3), dtype=img_dtype, device=dev)
+        self.poses = torch.eye(4, device=dev).reshape(1, 1, 16).repeat(B, 2, 1).contiguous()
+        self.baselines = torch.full((B,), 0.032, device=dev)
+        self.tgt_pose_rt = torch.eye(4, device=dev).reshape(1, 16).repeat(B, 1).contiguous()
+        self.tgt_pos = torch.zeros((B, 3), device=dev)
+        self.depths = torch.tensor(self.planes, dtype=torch.float32, device=dev)
+        self.hi, self.lo = self.net.input_buffers(B)
+        self.pred = torch.empty((B, H, W, 2 * num_planes), dtype=torch.float32, device=dev)
+        self.rgba = torch.empty((B, H, W, num_planes, 4), dtype=torch.float32, device=dev)
+        self.out = {
+            "rgb": torch.empty((B, H, W, 3), dtype=torch.float32, device=dev),
+            "depth": torch.empty((B, H, W, 3), dtype=torch.float32, device=dev),
+            "rgb_u8": torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
+            "depth_u8": torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
+        }
+        # pinned host staging for the end-to-end path
+        np_dt = torch.uint8 if img_dtype == torch.uint8 else torch.float32
+        self.h_ref = torch.empty((B, H, W, 3), dtype=np_dt).pin_memory()
+        self.h_src = torch.empty((B, H, W, 3), dtype=np_dt).pin_memory()
+        self.h_rgb_u8 = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+        self.h_depth_u8 = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+        self.use_graph = use_graph
+        self._graph = None
+        self.launches_per_step = self.net.launches_per_forward + 3
+
+    # -- device-resident step ---------------------------------------------------------------
+    def _enqueue(self):
+        lib = _lib.load()
+        B, H, W, P = self.B, self.H, self.W, self.P
+        tb = ops.erp_tables(H, W, self.device)
+        dt = _lib.IMG_U8 if self.img_dtype == torch.uint8 else _lib.IMG_F32
+        st = stream_ptr()
+        check(lib.msi_psv_build(ptr(self.ref), ptr(self.src), dt, 1, ptr(self.poses), ptr(self.baselines),
+                                ptr(self.depths), *tb.ptrs(), B, H, W, P, None, ptr(self.hi), ptr(self.lo),
+                                self.net.in_c_stride, st), "msi_psv_build")
+        self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred)
+        check(lib.msi_rgba_assemble(ptr(self.pred), None, ptr(self.hi), ptr(self.lo), self.net.in_c_stride,
+                                    B, H, W, P, ptr(self.rgba), None, None, st), "msi_rgba_assemble")
+        check(lib.msi_render_composite(ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths),
+                                       *tb.ptrs(), B, H, W, P, ptr(self.out["rgb"]), ptr(self.out["depth"]),
+                                       ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]), st),
+              "msi_render_composite")
+
+    def step(self):
+        """One pass of the hot path over the resident batch (inputs already in HBM)."""
+        if not self.use_graph:
+            self._enqueue()
+            return
+        if self._graph is None:
+            # warm-up outside capture (lazy module load, cudaFuncSetAttribute), then capture
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self._graph = g
+        self._graph.replay()
+
+    def set_inputs(self, ref, src, tgt_pos=None, baselines=None):
+        self.ref.copy_(torch.as_tensor(ref).to(self.ref.dtype), non_blocking=True)
+        self.src.copy_(torch.as_tensor(src).to(self.src.dtype), non_blocking=True)
+        if tgt_pos is not None:
+            self.tgt_pos.copy_(torch.as_tensor(tgt_pos, dtype=torch.float32))
+        if baselines is not None:
+            self.baselines.copy_(torch.as_tensor(baselines, dtype=torch.float32))
+
+    # -- end-to-end step: host buffers in, host buffers out --------------------------------
+    def step_e2e(self, ref_host=None, src_host=None):
+        """Host images -> pinned staging -> H2D -> hot path -> D2H of the rendered uint8 view and
+        depth.  Returns (rgb_u8, depth_u8) pinned host tensors (valid after the sync inside)."""
+        if ref_host is not None:
+            self.h_ref.copy_(torch.as_tensor(ref_host))
+            self.h_src.copy_(torch.as_tensor(src_host))
+        self.ref.copy_(self.h_ref, non_blocking=True)
+        self.src.copy_(self.h_src, non_blocking=True)
+        self.step()
+        self.h_rgb_u8.copy_(self.out["rgb_u8"], non_blocking=True)
+        self.h_depth_u8.copy_(self.out["depth_u8"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_rgb_u8, self.h_depth_u8
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.h_ref.numel() * self.h_ref.element_size() * 2
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.h_rgb_u8.numel() + self.h_depth_u8.numel()
+
+
+def shard_frames(num_frames: int, rank: int, world_size: int):
+    """Frame range [lo, hi) of ``rank`` (rank r takes frames [r*B/N, (r+1)*B/N))."""
+    per = -(-num_frames // world_size)
+    lo = min(rank * per, num_frames)
+    return lo, min(lo + per, num_frames)
+
+
+def all_gather_frames(local: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
+    """The path's only collective: gather the rendered frames of every rank, rank-major.
+    local: [b,H,W,3] (same b on every rank).  Works on NCCL (GPU) and gloo (CPU tests)."""
+    import torch.distributed as dist
+    if world_size == 1:
+        return local
+    out = torch.empty((world_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def profile_net_layers(net: NetEngine, hi_lo, out, reps: int = 3):
+    """Per-layer conv / LayerNorm milliseconds (CUDA events on the launching stream, average of
+    ``reps`` forwards) and algorithmic FLOPs per layer.  Used by bench.py for the roofline."""
+    lib = net.lib
+    n = int(lib.msi_net_num_layers(net._h))
+    conv = (ctypes.c_float * n)()
+    ln = (ctypes.c_float * n)()
+    B = hi_lo[0].shape[0]
+    acc_c, acc_l = np.zeros(n), np.zeros(n)
+    for _ in range(reps):
+        check(lib.msi_net_forward_profiled(net._h, None, ptr(hi_lo[0]), ptr(hi_lo[1]), B, ptr(out), stream_ptr(),
+                                           conv, ln), "msi_net_forward_profiled")
+        acc_c += np.frombuffer(conv, dtype=np.float32)
+        acc_l += np.frombuffer(ln, dtype=np.float32)
+    scopes = [lib.msi_net_layer_scope(net._h, i).decode() for i in range(n)]
+    flops = np.array([lib.msi_net_layer_flops(net._h, i) for i in range(n)]) * B
+    return scopes, acc_c / reps, acc_l / reps, flops

@@ -1,0 +1,222 @@
+"""GPU parity tests of the geometry stages (K1 psv_build, K4 rgba_assemble, K5 render_composite)
+against the CPU oracle, through the C ABI (ctypes -> libmsi_b200.so).
+
+Bars (north_star): the project_ods validity mask and the integer sample-index grid are
+bit-exact w.r.t. the float32 oracle (index mismatches allowed only at knife-edge coordinates
+within 1e-3 px of an integer, counted and bounded); float outputs within 1e-3 max-abs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_np as g
+from oracle import msi_np
+from matryodshka_b200 import ops, synth
+from matryodshka_b200.msi import MSI
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+DEV = "cuda"
+TOL = 1e-3  # north_star tolerance on float RGBA
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def _index_parity(c_dev, c_ref, size):
+    """floor() of device vs oracle coordinates; returns (#mismatch, #mismatch away from a knife edge)."""
+    f_dev = np.floor(c_dev).astype(np.int64)
+    f_ref = np.floor(c_ref).astype(np.int64)
+    bad = f_dev != f_ref
+    dist = np.abs(c_ref - np.round(c_ref))
+    return int(bad.sum()), int((bad & (dist > 1e-3)).sum())
+
+
+@pytest.mark.parametrize("H,W,P", [(32, 64, 4), (320, 640, 32)])
+def test_sweep_coords_mask_bit_exact_and_index_grid(H, W, P):
+    d = msi_np.inv_depths(1, 100, P)
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (1, 2, 1))
+    uv, valid = ops.sweep_coords(poses, [0.032], d, 1, H, W, DEV)
+    uv, valid = uv.cpu().numpy(), valid.cpu().numpy().astype(bool)
+    S, T = g.lat_long_grid((H, W))
+    pts = g.backproject_spherical(S, T, F32(d))
+    total_bad = 0
+    for e, order in enumerate((1, -1)):
+        ref, aux = g.project_ods(pts, order, None, synth.intrinsics(1), W, H, return_aux=True)
+        assert np.array_equal(valid[0, e], aux["valid"]), "disc<0 mask must be bit-exact"
+        assert np.all(uv[0, e][~aux["valid"]] == 1.0)
+        ok = aux["valid"]
+        du = np.abs(uv[0, e][ok] - ref[ok])
+        assert du.max() < 2e-3, du.max()
+        for k, size in ((0, W), (1, H)):
+            n_bad, n_far = _index_parity(uv[0, e][..., k][ok], ref[..., k][ok], size)
+            assert n_far == 0, (e, k, n_bad, n_far)
+            total_bad += n_bad
+    # knife-edge floor flips are rare
+    assert total_bad <= 2e-3 * uv.size, total_bad
+    if H == 320:
+        assert int((~valid[0, 0]).sum()) == 68409
+
+
+@pytest.mark.parametrize("H,W,P,kind", [(32, 64, 4, "band"), (320, 640, 32, "band"), (64, 128, 8, "noise")])
+def test_psv_build_matches_oracle(H, W, P, kind):
+    ref, src = synth.ods_pair(1, H, W, kind=kind)
+    d = msi_np.inv_depths(1, 100, P)
+    want = msi_np.format_network_input(msi_np.preprocess_image(ref), msi_np.preprocess_image(src),
+                                       synth.identity_poses(1), synth.identity_poses(1), d, synth.intrinsics(1))
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (1, 2, 1))
+    got = ops.psv_build(_t(ref), _t(src), poses, [0.032], d, preprocess=True).cpu().numpy()
+    err = np.abs(got - want)
+    # white noise has unit gradient per pixel: a 1e-4 px coordinate difference is visible there
+    assert err.max() < (TOL if kind == "band" else 5e-3), err.max()
+    assert err.mean() < 1e-5
+    # mirror API: MSI.format_network_input on preprocessed images
+    m = MSI()
+    got2 = m.format_network_input(_t(ref * 2 - 1), _t(src * 2 - 1), synth.identity_poses(1), synth.identity_poses(1),
+                                  d, synth.intrinsics(1)).cpu().numpy()
+    assert np.array_equal(got2, got)
+
+
+def test_psv_build_uint8_input_and_hi_lo_operand():
+    H, W, P = 32, 64, 32
+    ref, src = synth.ods_pair(2, H, W)
+    ref8, src8 = (ref * 255).astype(np.uint8), (src * 255).astype(np.uint8)
+    d = msi_np.inv_depths(1, 100, P)
+    want = np.concatenate([
+        msi_np.format_network_input(msi_np.preprocess_image(ref8[b:b + 1]), msi_np.preprocess_image(src8[b:b + 1]),
+                                    synth.identity_poses(1), synth.identity_poses(1), d, synth.intrinsics(1))
+        for b in range(2)])
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (2, 2, 1))
+    hi = torch.empty((2, H, W, 6 * P), dtype=torch.float16, device=DEV)
+    lo = torch.empty_like(hi)
+    got = ops.psv_build(_t(ref8), _t(src8), poses, [0.032, 0.032], d, preprocess=True, hi_lo=(hi, lo)).cpu().numpy()
+    assert np.abs(got - want).max() < TOL
+    rec = (hi.float() + lo.float()).cpu().numpy() / 16.0
+    assert np.abs(rec - got).max() < 2e-6  # hi/lo split keeps ~22 bits
+
+
+def test_psv_build_general_pose():
+    """Non-identity sweep pose (the --transform_inverse_reg path, msi.py:1118-1120)."""
+    H, W, P = 32, 64, 4
+    ref, src = synth.ods_pair(1, H, W)
+    d = msi_np.inv_depths(1, 100, P)
+    a = 0.02
+    pose = np.array([[np.cos(a), 0, np.sin(a), 0.004], [0, 1, 0, -0.003], [-np.sin(a), 0, np.cos(a), 0.002],
+                     [0, 0, 0, 1]], F32)[None]
+    want = g.sweep_one(ref * 2 - 1, 1, d, pose, synth.intrinsics(1))
+    from matryodshka_b200.geometry import projector as pj
+    got = pj.ods_sphere_sweep(_t(ref * 2 - 1), 1, d, pose, synth.intrinsics(1)).cpu().numpy()
+    assert np.abs(got - want).max() < TOL
+
+
+def test_rgba_assemble_bit_exact():
+    B, H, W, L = 2, 16, 32, 8
+    rng = np.random.default_rng(1)
+    pred = rng.uniform(-1, 1, (B, H, W, 2 * L)).astype(F32)
+    psv = rng.uniform(-1, 1, (B, H, W, 6 * L)).astype(F32)
+    want, bw, al = msi_np.assemble_rgba(pred, psv, L)
+    rgba, gbw, gal = ops.rgba_assemble(_t(pred), _t(psv), want_weights=True)
+    assert np.array_equal(rgba.cpu().numpy(), want)
+    assert np.array_equal(gbw.cpu().numpy(), bw) and np.array_equal(gal.cpu().numpy(), al)
+
+
+def _smooth_layers(B, H, W, L, seed=0):
+    rng = np.random.default_rng(seed)
+    base = synth.band_limited_images(B * L, H, W, seed).reshape(B, L, H, W, 3).transpose(0, 2, 3, 1, 4)
+    alpha = synth.band_limited_images(B * L, H, W, seed + 5)[..., :1].reshape(B, L, H, W, 1).transpose(0, 2, 3, 1, 4)
+    return np.ascontiguousarray(np.concatenate([base * 2 - 1, alpha], -1).astype(F32))
+
+
+@pytest.mark.parametrize("H,W,L,tp", [
+    (32, 64, 4, (0.03, -0.02, 0.04)),
+    (32, 64, 64, (0.05, 0.01, -0.03)),     # L=64: two sweeps of the lane<->layer mapping
+    (64, 128, 32, (0.3, 0.1, -0.2)),       # SURVEY 8d edge case: large offset
+    (320, 640, 32, (0.031, -0.017, 0.044)),
+])
+def test_render_composite_matches_oracle(H, W, L, tp):
+    rgba = _smooth_layers(1, H, W, L)
+    d = msi_np.inv_depths(1, 100, L)
+    eye = np.eye(4, dtype=F32)[None]
+    tp = np.array([tp], F32)
+    want = msi_np.msi_render_equirect_view(rgba, eye, tp, d)
+    wdep = msi_np.msi_render_equirect_depth(rgba, eye, tp, d)
+    res = ops.render_composite(_t(rgba), eye, tp, d)
+    got, gdep = res["rgb"].cpu().numpy(), res["depth"].cpu().numpy()
+    assert np.abs(got - want).max() < TOL, np.abs(got - want).max()
+    assert np.abs(gdep - wdep).max() < TOL
+    # uint8 epilogue: convert_image_dtype semantics; a float difference can move a truncation edge by 1
+    d8 = np.abs(res["rgb_u8"].cpu().numpy().astype(int) - msi_np.deprocess_image(want).astype(int))
+    assert d8.max() <= 1 and (d8 > 0).mean() < 1e-2
+    d8 = np.abs(res["depth_u8"].cpu().numpy().astype(int) - msi_np.deprocess_depth_image(wdep).astype(int))
+    assert d8.max() <= 1
+    # index grid of the reprojection
+    uv = ops.intersect_sphere_coords(eye, tp, d, 1, H, W, DEV).cpu().numpy()[0]
+    ref_uv = g.intersect_sphere(eye[0], tp[0], F32(d), L, 1, W, H)
+    assert np.abs(uv - ref_uv).max() < 2e-3
+    for k in range(2):
+        n_bad, n_far = _index_parity(uv[..., k], ref_uv[..., k], W if k == 0 else H)
+        assert n_far == 0 and n_bad <= 2e-3 * uv[..., k].size
+
+
+def test_render_batch_and_pose_rotation():
+    B, H, W, L = 3, 32, 64, 8
+    rgba = _smooth_layers(B, H, W, L, 3)
+    d = msi_np.inv_depths(1, 100, L)
+    a = 0.1
+    rot = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]], F32)
+    pose = np.stack([np.eye(4, dtype=F32), rot, rot.T.copy()])
+    tp = synth.target_positions(B)
+    want = msi_np.msi_render_equirect_view(rgba, pose, tp, d)
+    got = MSI().msi_render_equirect_view(_t(rgba), _t(pose), _t(tp), d).cpu().numpy()
+    assert np.abs(got - want).max() < TOL
+
+
+def test_zero_offset_render_is_mirror_at_full_size():
+    """Size-independent property: at tgt_pos = 0 the render is the horizontal mirror of
+    the un-warped over-composite; every u is an integer +- float noise, the worst case for floor()."""
+    H, W, L = 320, 640, 32
+    rgba = _smooth_layers(1, H, W, L, 7)
+    d = msi_np.inv_depths(1, 100, L)
+    res = ops.render_composite(_t(rgba), np.eye(4, dtype=F32)[None], np.zeros((1, 3), F32), d)
+    layers = _t(np.ascontiguousarray(rgba.transpose(3, 0, 1, 2, 4)))
+    flat = ops.over_composite(layers).cpu().numpy()
+    assert np.abs(res["rgb"].cpu().numpy() - flat[:, :, ::-1]).max() < TOL
+    fdep = ops.over_composite(layers, depth_mode=True).cpu().numpy()
+    assert np.abs(res["depth"].cpu().numpy() - fdep[:, :, ::-1]).max() < TOL
+
+
+def test_alpha_one_shows_nearest_layer_and_project_layers():
+    H, W, L = 32, 64, 6
+    rgba = _smooth_layers(1, H, W, L, 9)
+    rgba[..., 3] = 1.0
+    d = msi_np.inv_depths(1, 100, L)
+    eye = np.eye(4, dtype=F32)[None]
+    tp = np.array([[0.02, 0.01, -0.01]], F32)
+    m = MSI()
+    proj = m.msi_render_equirect_view_single(_t(rgba), eye, tp, d)
+    want = msi_np.msi_render_equirect_view_single(rgba, eye, tp, d)
+    assert np.abs(proj.cpu().numpy() - want).max() < TOL
+    out = m.msi_render_equirect_view(_t(rgba), eye, tp, d).cpu().numpy()
+    assert np.abs(out - proj[L - 1, ..., :3].cpu().numpy()).max() < 1e-6
+    from matryodshka_b200.geometry import projector as pj
+    comp = pj.over_composite([proj[l] for l in range(L)]).cpu().numpy()
+    assert np.array_equal(comp, out)  # same recurrence order in both kernels
+
+
+def test_resample_wraps_like_the_oracle():
+    rng = np.random.default_rng(4)
+    img = rng.uniform(-1, 1, (2, 9, 11, 5)).astype(F32)
+    coords = rng.uniform(-15, 25, (2, 7, 6, 2)).astype(F32)
+    from matryodshka_b200.geometry import sampling
+    got = sampling.bilinear_wrapper2(_t(img), _t(coords)).cpu().numpy()
+    assert np.array_equal(got, g.resample(img, coords))
+
+
+def test_invalid_arguments_raise():
+    from matryodshka_b200._lib import MsiError
+    with pytest.raises(MsiError):
+        ops.render_composite(torch.zeros((1, 8, 8, 4, 4), device=DEV), np.eye(4)[None], np.zeros((1, 3)),
+                             [1.0, 2.0, 3.0, 4.0], want_rgb=False, want_depth=False)

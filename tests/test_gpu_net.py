@@ -1,0 +1,142 @@
+"""GPU parity tests of the conv net (stage 2) and of the whole frame against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msi_np, net_torch
+from matryodshka_b200 import ops, synth
+from matryodshka_b200.msi import MSI, MSIConfig
+from matryodshka_b200.runtime import MSIPipeline, NetEngine
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+DEV = "cuda"
+TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def _oracle_net(x, c_out, wts, ngf):
+    with torch.no_grad():
+        pred, feats = net_torch.msi_coord_train_net(torch.from_numpy(x), c_out, wts, ngf=ngf, return_feats=True)
+    return pred.numpy(), {k: v.numpy() for k, v in feats.items()}
+
+
+def _check_net(eng, x, wts, c_out, ngf, B):
+    pred = eng.forward(_t(x)).cpu().numpy()
+    want, feats = _oracle_net(x, c_out, wts, ngf)
+    worst = {}
+    for scope, f in feats.items():
+        got = eng.read_activation(scope, B).cpu().numpy()
+        worst[scope] = float(np.abs(got - f).max())
+    err = np.abs(pred - want).max()
+    assert err < TOL, (err, worst)
+    return err, worst
+
+
+@pytest.mark.parametrize("H,W,P,ngf,B", [(16, 32, 4, 8, 1), (32, 64, 4, 16, 2)])
+def test_simt_net_matches_oracle(H, W, P, ngf, B):
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, conv_impl="simt")
+    err, worst = _check_net(eng, x, wts, 2 * P, ngf, B)
+    assert max(worst.values()) < TOL, worst
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16x3", TOL), ("fp16", 3e-2)])
+def test_tcgen05_net_matches_oracle(precision, tol):
+    """The tensor-core path at ngf = 64 on a small frame: every layer's activation and the head."""
+    H, W, P, ngf, B = 32, 64, 32, 64, 1
+    ref, src = synth.ods_pair(B, H, W)
+    d = msi_np.inv_depths(1, 100, P)
+    x = msi_np.format_network_input(ref * 2 - 1, src * 2 - 1, synth.identity_poses(1), synth.identity_poses(1), d,
+                                    synth.intrinsics(1))
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, conv_impl="tcgen05", precision=precision)
+    pred = eng.forward(_t(x)).cpu().numpy()
+    want, feats = _oracle_net(x, 2 * P, wts, ngf)
+    worst = {s: float(np.abs(eng.read_activation(s, B).cpu().numpy() - f).max()) for s, f in feats.items()}
+    err = np.abs(pred - want).max()
+    assert err < tol, (err, worst)
+
+
+def test_tcgen05_matches_simt_batch2_odd_tiles():
+    """tcgen05 vs the fp32 SIMT kernel of this library on a shape with partial tiles and B = 2."""
+    H, W, P, ngf, B = 48, 80, 32, 64, 2
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    a = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, conv_impl="tcgen05")
+    b = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, conv_impl="simt")
+    pa, pb = a.forward(_t(x)), b.forward(_t(x))
+    assert (pa - pb).abs().max().item() < TOL
+
+
+def test_golden_fixture_through_c_abi():
+    """The committed fixture (tests/golden/msi_small.npz) through the mirror API, SIMT net (ngf = 8)."""
+    from tests.golden.make_golden import inputs_small, P, NGF
+    z = np.load(os.path.join(GOLDEN, "msi_small.npz"))
+    i = inputs_small()
+    m = MSI(weights=i["weights"], config=MSIConfig(conv_impl="simt", ngf=NGF))
+    planes = list(i["planes"])
+    out, net_input = m.infer_msi(_t(i["src"]), _t(i["ref"]), None, None, i["ref_pose"], i["src_pose"],
+                                 i["intrinsics"], "blend_psv", P, planes, "blend_weights_alphas_psv", ngf=NGF)
+    assert np.abs(net_input.cpu().numpy() - z["psv"]).max() < TOL
+    assert np.abs(out["rgba_layers"].cpu().numpy() - z["rgba_layers"]).max() < TOL
+    pred = torch.cat([out["blend_weights"], out["alphas"]], -1).cpu().numpy() * 2 - 1
+    assert np.abs(pred - z["pred"]).max() < TOL
+    res = m.msi_render_equirect(out["rgba_layers"], np.eye(4, dtype=F32)[None], i["tgt_pos"], planes)
+    assert np.abs(res["rgb"].cpu().numpy() - z["render"]).max() < TOL
+    assert np.abs(res["depth"].cpu().numpy() - z["depth"]).max() < TOL
+    assert np.abs(res["rgb_u8"].cpu().numpy().astype(int) - z["render_u8"].astype(int)).max() <= 1
+    assert set(out.keys()) == {"rgba_layers", "blend_weights", "alphas", "psv"}
+
+
+@pytest.mark.parametrize("conv_impl", ["tcgen05"])
+def test_full_frame_pipeline_matches_oracle(conv_impl):
+    """Config C2 (640x320, 32 spheres, B=1) end to end vs the oracle: rendered view within 1e-3."""
+    H, W, P, ngf = 320, 640, 32, 64
+    ref, src = synth.ods_pair(1, H, W)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    tp = synth.target_positions(1)
+    pipe = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, conv_impl=conv_impl)
+    pipe.set_inputs(ref, src, tgt_pos=tp)
+    pipe.step()
+    pipe.step()  # second call replays the CUDA graph
+    torch.cuda.synchronize()
+    planes = msi_np.inv_depths(1, 100, P)
+    out, _ = msi_np.infer_msi(src, ref, synth.identity_poses(1), synth.identity_poses(1), synth.intrinsics(1), P,
+                              planes, wts, ngf=ngf)
+    eye = np.eye(4, dtype=F32)[None]
+    want = msi_np.msi_render_equirect_view(out["rgba_layers"], eye, tp, planes)
+    wdep = msi_np.msi_render_equirect_depth(out["rgba_layers"], eye, tp, planes)
+    rgba_err = np.abs(pipe.rgba.cpu().numpy() - out["rgba_layers"]).max()
+    err = np.abs(pipe.out["rgb"].cpu().numpy() - want).max()
+    derr = np.abs(pipe.out["depth"].cpu().numpy() - wdep).max()
+    assert rgba_err < TOL and err < TOL and derr < TOL, (rgba_err, err, derr)
+    # end-to-end host path returns the same pixels
+    rgb8, dep8 = pipe.step_e2e(torch.from_numpy(ref), torch.from_numpy(src))
+    assert torch.equal(rgb8, pipe.out["rgb_u8"].cpu())
+
+
+def test_batched_frames_equal_single_frames():
+    """Frames are independent: a batch of 3 must equal three B=1 runs bit for bit."""
+    H, W, P, ngf = 32, 64, 32, 64
+    ref, src = synth.ods_pair(3, H, W)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    tp = synth.target_positions(3)
+    big = MSIPipeline(wts, H, W, P, ngf, batch=3, device=DEV, use_graph=False)
+    big.set_inputs(ref, src, tgt_pos=tp)
+    big.step()
+    one = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, use_graph=False)
+    for b in range(3):
+        one.set_inputs(ref[b:b + 1], src[b:b + 1], tgt_pos=tp[b:b + 1])
+        one.step()
+        assert torch.equal(one.out["rgb"][0], big.out["rgb"][b])
+        assert torch.equal(one.out["depth_u8"][0], big.out["depth_u8"][b])

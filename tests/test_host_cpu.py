@@ -1,0 +1,134 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic of the
+mirror API, frame sharding, and the gloo world_size-2 all-gather path.  No GPU compute."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from matryodshka_b200 import _lib, nets, ops, synth
+from matryodshka_b200.msi import MSI, MSIConfig
+from matryodshka_b200.runtime import shard_frames
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "msi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(msi_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header drifted apart"
+    assert lib.msi_b200_abi_version() == 1
+
+
+def test_net_plan_sizes_without_gpu():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.msi_net_create(ctypes.byref(h), 320, 640, 192, 64, 64, 1, _lib.CONV_TCGEN05, _lib.PREC_FP16X3) == 0
+    assert lib.msi_net_input_c_stride(h) == 192
+    assert lib.msi_net_workspace_bytes(h) > 700e6 and lib.msi_net_arena_bytes(h) > 2 * 17.0e6 * 4
+    assert lib.msi_net_num_launches_per_forward(h) == 17 * 4 + 1
+    lib.msi_net_destroy(h)
+    # invalid arguments are reported, not crashed on
+    assert lib.msi_net_create(ctypes.byref(h), 321, 640, 192, 64, 64, 1, 0, 0) == -1
+    assert b"multiples of 8" in lib.msi_last_error()
+    assert lib.msi_net_create(ctypes.byref(h), 32, 64, 24, 8, 8, 1, _lib.CONV_TCGEN05, 0) == -3  # needs ngf % 64
+
+
+def test_compute_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MsiError):
+        ops.psv_build(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), np.eye(4).reshape(1, 1, 16).repeat(2, 1),
+                      [0.032], [2.0, 1.0])
+    with pytest.raises(_lib.MsiError):
+        MSI(weights={}).msi_render_equirect_view(torch.zeros(1, 8, 8, 2, 4), np.eye(4)[None], np.zeros((1, 3)),
+                                                 [2.0, 1.0])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "matryodshka_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_arch_table_and_flops():
+    shp = nets.layer_shapes(192, 64, 64)
+    assert shp["net/conv1_1/weights"] == (3, 3, 193, 64)
+    assert shp["net/conv6_1/weights"] == (4, 4, 256, 1024)
+    assert shp["net/color_pred/weights"] == (1, 1, 64, 64) and shp["net/color_pred/biases"] == (64,)
+    n_params = sum(int(np.prod(s)) for s in shp.values())
+    assert abs(n_params - 17.0e6) < 0.1e6
+    assert abs(nets.net_flops(320, 640, 192, 64) / 1e9 - 302.4) < 0.05
+    hw = nets.layer_geometry(320, 640)
+    assert hw["conv4_3"] == (40, 80) and hw["conv8_2"] == (320, 640)
+
+
+def test_inv_depths_and_tables_match_oracle_restatement():
+    from oracle import geometry_np as g, msi_np
+    assert MSI().inv_depths(1, 100, 32) == msi_np.inv_depths(1, 100, 32)
+    s, t = ops.lat_long_axes(320, 640)
+    so, to = g.lat_long_axes((320, 640))
+    assert np.array_equal(s, so) and np.array_equal(t, to)  # bit-identical ERP tables
+
+
+def test_sweep_pose_composition():
+    m = MSI()
+    a = 0.3
+    ref = np.array([[np.cos(a), -np.sin(a), 0, 1], [np.sin(a), np.cos(a), 0, 2], [0, 0, 1, 3], [0, 0, 0, 1]],
+                   np.float32)[None]
+    poses = m._sweep_poses(ref, ref)
+    assert np.allclose(poses[0, 0], np.eye(4), atol=1e-6) and poses.shape == (1, 2, 4, 4)
+    poses = m._sweep_poses(np.eye(4)[None], np.eye(4)[None])
+    assert np.array_equal(poses[0, 1], np.eye(4, dtype=np.float32))
+
+
+def test_infer_msi_rejects_unbuilt_modes():
+    m = MSI(weights={}, config=MSIConfig(coord_net=False))
+    with pytest.raises(NotImplementedError):
+        m.infer_msi(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), None, None, np.eye(4)[None], np.eye(4)[None],
+                    synth.intrinsics(1), "blend_psv", 2, [2.0, 1.0])
+    with pytest.raises(NotImplementedError):
+        MSI(weights={}).infer_msi(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), None, None, np.eye(4)[None],
+                                  np.eye(4)[None], synth.intrinsics(1), "alpha_only", 2, [2.0, 1.0])
+
+
+def test_shard_frames_partition():
+    for n, ws in [(64, 8), (16, 4), (1, 1), (7, 2), (3, 4)]:
+        spans = [shard_frames(n, r, ws) for r in range(ws)]
+        covered = [i for lo, hi in spans for i in range(lo, hi)]
+        assert covered == list(range(n))
+
+
+def test_synth_is_deterministic():
+    a, b = synth.ods_pair(1, 16, 32)
+    a2, b2 = synth.ods_pair(1, 16, 32)
+    assert np.array_equal(a, a2) and np.array_equal(b, b2) and a.min() >= 0 and a.max() <= 1
+    w = synth.net_weights(24, 8, 8)
+    assert set(w) == set(nets.layer_shapes(24, 8, 8))
+
+
+def test_gloo_world2_all_gather_of_frames():
+    """The path's only collective on the CPU backend: 2 ranks each own 2 frames."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_OK" in r.stdout
