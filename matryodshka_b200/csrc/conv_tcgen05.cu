@@ -1,6 +1,7 @@
 // Tensor-core back end of the conv net (MSI_CONV_TCGEN05): implicit-GEMM convolution on the 5th-gen
-// tensor cores of sm_100a.  One kernel serves the 3x3 convs (stride 1 / 2, dilation 1 / 2), the 4x4
-// stride-2 transposed convs (as four 2x2 output-parity sub-convolutions) and the 1x1 head.
+// tensor cores of sm_100a.  One persistent, warp-specialised kernel serves the 3x3 convs (stride
+// 1 / 2, dilation 1 / 2), the 4x4 stride-2 transposed convs (as four 2x2 output-parity
+// sub-convolutions) and the 1x1 head.
 //
 //   D[128 pixels, N couts] (fp32, TMEM) += A[128 pixels, 64 ch] (smem) * W[N couts, 64 ch]^T (smem)
 //
@@ -12,14 +13,23 @@
 //   128 bytes with the 128-byte swizzle = the canonical K-major UMMA layout.  No im2col buffer.
 // * W operand: weights pre-packed K-major [class][Cout][K], K = tap * Cin + c, TMA box {64, N}.
 // * fp16x3 precision (default): activations and weights are stored as fp16 hi + lo pairs
-//   (x = hi + lo to ~22 bits) and every product is hi*hi + lo*hi + hi*lo into the same fp32
-//   accumulator -- three MMAs per 16-wide K step -- because a single fp16 (or tf32) pass leaves
-//   7e-3 max-abs on the net output, above the path's 1e-3 bar.  MSI_PREC_FP16 issues one.
+//   (x = hi + lo to ~22 bits) and every product is hi*hi + hi*lo + lo*hi in fp32, because a single
+//   fp16 (or tf32) pass leaves 7e-3 max-abs on the net output, above the path's 1e-3 bar.  W_hi and
+//   W_lo sit back to back in shared memory, so  A_hi x [W_hi | W_lo]  is ONE MMA of width 2N (A_hi
+//   is read from shared memory once, not twice) into accumulator columns [0, 2N), and  A_lo x W_hi
+//   accumulates into columns [0, N); the epilogue adds the two halves.  MSI_PREC_FP16 issues one MMA.
 // * skip connections: the deconvs read their two concatenated sources through two tensor maps.
 // * the coord channel of coord_conv2d is folded out of the GEMM into a bias table (layernorm.cu).
+// * LayerNorm statistics (sum, sum of squares per frame) are accumulated in the epilogue, one partial
+//   per (frame, CTA, warp), and the last CTA to finish reduces them to (mean, rstd): the global
+//   reduction costs no extra pass over the activation and no extra launch.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 epilogue
-// (tcgen05.ld -> scale/bias/tanh -> float32 NHWC stores).  smem ring of kStages (full/empty mbarriers).
+// Persistent CTA = 6 warps, one CTA per SM, static round-robin over output tiles:
+//   warp 0   TMA producer (elected lane) -> smem ring of kStages (full / empty mbarriers)
+//   warp 1   MMA issuer (elected lane) + TMEM allocator; accumulators double-buffered in TMEM so the
+//            epilogue of tile i overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers)
+//   warps 2-5 epilogue: tcgen05.ld -> un-scale + coord bias (+ bias, tanh for the head) -> float32
+//            NHWC stores + LayerNorm partial sums
 #include <cuda.h>
 
 #include "net_internal.cuh"
@@ -29,51 +39,71 @@ namespace msi {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;            // fp16 elements = one 128-byte swizzle row
+constexpr int kBlockK = 64;                         // fp16 elements = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kThreads = 192;
-constexpr int kMaxSmem = 227 * 1024 - 2048;  // dynamic limit: 227 KB minus this kernel's static shared memory
+constexpr int kMaxDynSmem = 227 * 1024 - 4096;      // 227 KB minus this kernel's static shared memory
 
 struct TcParams {
-    int n_tile;        // UMMA N
-    int split;         // 1: fp16x3, 0: fp16
     int stages;
-    int stage_bytes;
-    int BH, BW;        // output-pixel patch of one M tile, BH * BW = 128
-    int tiles_x, tiles_y;
-    int Mh, Mw;        // output positions per class
-    int in_stride;     // conv stride (TMA traversal stride)
-    int out_stride;    // 1, or 2 for deconv classes
+    int BH, BW;          // output-pixel patch of one M tile, BH * BW = 128
+    int tiles_x, tiles_y, n_tiles;
+    int tiles_per_sample;  // tiles_x * tiles_y * n_tiles * ncls
+    int total_tiles;
+    int Mh, Mw;          // output positions per class
+    int in_stride;       // conv stride (TMA traversal stride)
+    int out_stride;      // 1, or 2 for deconv classes
     int ncls;
     int nsrc;
-    int chunks[2];     // 64-channel chunks per source
-    int cs_total;      // packed channels per tap (sum of source channel strides)
+    int chunks[2];       // 64-channel chunks per source
+    int cs_total;        // packed channels per tap (sum of source channel strides)
     TapList taps[4];
     int Hout, Wout, cout;
     int kind;
-    float unscale;     // 1 / (MSI_ACT_SCALE * MSI_WEIGHT_SCALE)
+    float unscale;       // 1 / (MSI_ACT_SCALE * MSI_WEIGHT_SCALE)
     const float* cbias;  // [Hout][8][cout] or null
     int cb_k, cb_stride, cb_rate, cb_pad_l, cb_Win;  // to derive the kw in-bounds mask of a column
     const float* bias;   // head
     float* out;
+    // LayerNorm statistics
+    int do_stats;
+    int B;
+    int n_partials;      // slots per frame (>= gridDim.x * 4)
+    double2* partials;   // [B][n_partials], zeroed before the launch
+    unsigned int* counter;  // zeroed before the launch
+    float2* stats;       // [B] (mean, rstd)
+    double n_per_sample;
 };
 
 struct TcPlan {
     TcParams p;
+    int n_tile, split;
     CUtensorMap a_map[2][2];  // [source][hi/lo]
     CUtensorMap w_map[2];     // hi/lo
-    dim3 grid;
+    int grid;
     int smem_bytes;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -92,23 +122,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {
-            printf("msi conv_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x);
+            printf("msi conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -118,14 +147,8 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // K-major, 128-byte swizzle smem matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between
 // 8-row groups, version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+constexpr uint64_t kDescBase = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) { return kDescBase | (uint64_t)((saddr >> 4) & 0x3FFF); }
 
 // kind::f16 instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major A and B, N>>3 at 17, M>>4 at 24.
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
@@ -156,64 +179,106 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct TileCoord {
+    int b, cls, n0, ox0, oy0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int n_tile) {
+    TileCoord t;
+    int r = tile;
+    const int tx = r % p.tiles_x;
+    r /= p.tiles_x;
+    const int ty = r % p.tiles_y;
+    r /= p.tiles_y;
+    const int nt = r % p.n_tiles;
+    r /= p.n_tiles;
+    t.cls = r % p.ncls;
+    t.b = r / p.ncls;
+    t.n0 = nt * n_tile;
+    t.ox0 = tx * p.BW;
+    t.oy0 = ty * p.BH;
+    return t;
+}
 
 // ---- the kernel ------------------------------------------------------------------------------
+template <int N_TILE, int SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_constant__ CUtensorMap a0_lo,
                           const __grid_constant__ CUtensorMap a1_hi, const __grid_constant__ CUtensorMap a1_lo,
                           const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
-                          const TcParams p) {
+                          const __grid_constant__ TcParams p) {
+    constexpr int kWTileBytes = N_TILE * kBlockK * 2;
+    constexpr int kStageBytes = (kATileBytes + kWTileBytes) * (SPLIT ? 2 : 1);
+    constexpr int kAccCols = SPLIT ? 2 * N_TILE : N_TILE;  // TMEM columns of one accumulator
+    constexpr int kTmemCols = 2 * kAccCols;                // double-buffered
+    constexpr uint32_t kTxBytes = (uint32_t)kStageBytes;
+    // stage layout: [A_hi][A_lo][W_hi][W_lo] (SPLIT) or [A][W]
+    constexpr int kOffALo = kATileBytes;
+    constexpr int kOffWHi = SPLIT ? 2 * kATileBytes : kATileBytes;
+    constexpr int kOffWLo = kOffWHi + kWTileBytes;
+
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ int s_is_last;
+    __shared__ double s_red[2][4];
+    __shared__ int s_dx[4][9], s_dy[4][9];
+    __shared__ int s_ntaps[4];
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    const int tile_x = blockIdx.x % p.tiles_x;
-    const int tile_y = blockIdx.x / p.tiles_x;
-    const int n0 = blockIdx.y * p.n_tile;
-    const int cls = blockIdx.z % p.ncls;
-    const int b = blockIdx.z / p.ncls;
-    const int ox0 = tile_x * p.BW;
-    const int oy0 = tile_y * p.BH;
-
-    const int w_tile_bytes = p.n_tile * kBlockK * 2;
+    const int stages = p.stages;
     const int chunks_total = p.chunks[0] + p.chunks[1];
-    const TapList& taps = p.taps[cls];
-    const int n_iters = taps.n * chunks_total;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
+    if (threadIdx.x < 36) {
+        const int c = threadIdx.x / 9, t = threadIdx.x % 9;
+        s_dx[c][t] = p.taps[c].dx[t];
+        s_dy[c][t] = p.taps[c].dy[t];
+        if (t == 0) s_ntaps[c] = p.taps[c].n;
+    }
+    if (threadIdx.x == 64) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&a0_hi);
         prefetch_tmap(&w_hi);
-        if (p.split) {
+        if (SPLIT) {
             prefetch_tmap(&a0_lo);
             prefetch_tmap(&w_lo);
         }
-        if (p.nsrc == 2) prefetch_tmap(&a1_hi);
+        if (p.nsrc == 2) {
+            prefetch_tmap(&a1_hi);
+            if (SPLIT) prefetch_tmap(&a1_lo);
+        }
     }
-    if (warp == 1) {
-        // allocate n_tile TMEM columns (power of two >= 32); the same warp frees them
-        const uint32_t dst = smem_u32(&tmem_base_smem);
-        if (p.n_tile == 64)
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(dst) : "memory");
-        else if (p.n_tile == 128)
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(dst) : "memory");
-        else
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(dst) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_smem);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -221,114 +286,211 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)((kATileBytes + w_tile_bytes) * (p.split ? 2 : 1));
-            int it = 0;
-            for (int t = 0; t < taps.n; ++t) {
-                const int cx = ox0 * p.in_stride + taps.dx[t];
-                const int cy = oy0 * p.in_stride + taps.dy[t];
-                for (int ch = 0; ch < chunks_total; ++ch, ++it) {
-                    const int stage = it % p.stages;
-                    const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile, N_TILE);
+            const int ntaps = s_ntaps[tc.cls];
+            const int bx = tc.ox0 * p.in_stride, by = tc.oy0 * p.in_stride;
+            for (int t = 0; t < ntaps; ++t) {
+                const int cx = bx + s_dx[tc.cls][t];
+                const int cy = by + s_dy[tc.cls][t];
+                int kk = t * p.cs_total;
+                for (int ch = 0; ch < chunks_total; ++ch, kk += kBlockK) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sa_hi = smem + (size_t)stage * p.stage_bytes;
-                    uint8_t* sw_hi = sa_hi + kATileBytes;
-                    uint8_t* sa_lo = sw_hi + w_tile_bytes;
-                    uint8_t* sw_lo = sa_lo + kATileBytes;
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    const bool second = ch >= p.chunks[0];
-                    const int c0 = (second ? ch - p.chunks[0] : ch) * kBlockK;
-                    const int kk = t * p.cs_total + ch * kBlockK;  // packed K offset (sources are laid back to back)
-                    tma_load_4d(sa_hi, second ? &a1_hi : &a0_hi, &full_bar[stage], c0, cx, cy, b);
-                    tma_load_3d(sw_hi, &w_hi, &full_bar[stage], kk, n0, cls);
-                    if (p.split) {
-                        tma_load_4d(sa_lo, second ? &a1_lo : &a0_lo, &full_bar[stage], c0, cx, cy, b);
-                        tma_load_3d(sw_lo, &w_lo, &full_bar[stage], kk, n0, cls);
+                    if (leader) {
+                        const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
+                        mbar_expect_tx(&full_bar[stage], kTxBytes);
+                        const bool second = ch >= p.chunks[0];
+                        const int c0 = (second ? ch - p.chunks[0] : ch) * kBlockK;
+                        tma_load_4d(sa, second ? &a1_hi : &a0_hi, &full_bar[stage], c0, cx, cy, tc.b);
+                        tma_load_3d(sa + kOffWHi, &w_hi, &full_bar[stage], kk, tc.n0, tc.cls);
+                        if (SPLIT) {
+                            tma_load_4d(sa + kOffALo, second ? &a1_lo : &a0_lo, &full_bar[stage], c0, cx, cy, tc.b);
+                            tma_load_3d(sa + kOffWLo, &w_lo, &full_bar[stage], kk, tc.n0, tc.cls);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.n_tile);
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_wide = make_idesc(SPLIT ? 2 * N_TILE : N_TILE);
+        constexpr uint32_t idesc_n = make_idesc(N_TILE);
+        int stage = 0;
+        uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int cls = (tile / (p.tiles_x * p.tiles_y * p.n_tiles)) % p.ncls;
+            const int n_iters = s_ntaps[cls] * chunks_total;
+            const int acc = local & 1;
+            const uint32_t use = (uint32_t)(local >> 1);
+            mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
             for (int it = 0; it < n_iters; ++it) {
-                const int stage = it % p.stages;
-                const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
                 mbar_wait(&full_bar[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa_hi = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                const uint32_t sw_hi = sa_hi + kATileBytes;
-                const uint32_t sa_lo = sw_hi + w_tile_bytes;
-                const uint32_t sw_lo = sa_lo + kATileBytes;
-                const uint64_t da_hi = make_desc(sa_hi), dw_hi = make_desc(sw_hi);
-                const uint64_t da_lo = make_desc(sa_lo), dw_lo = make_desc(sw_lo);
+                if (leader) {
+                    const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
+                    const uint64_t da_hi = make_desc(sa);
+                    const uint64_t dw_hi = make_desc(sa + kOffWHi);
+                    const uint64_t da_lo = make_desc(sa + kOffALo);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per K step inside the swizzle row
-                    umma_f16(tmem_base, da_hi + adv, dw_hi + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    if (p.split) {
-                        umma_f16(tmem_base, da_lo + adv, dw_hi + adv, idesc, 1u);
-                        umma_f16(tmem_base, da_hi + adv, dw_lo + adv, idesc, 1u);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes per K step inside the swizzle row (>> 4)
+                        // A_hi x [W_hi | W_lo] -> columns [0, 2N)   (fp16 mode: A x W -> [0, N))
+                        umma_f16(d_tmem, da_hi + adv, dw_hi + adv, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);
+                        // A_lo x W_hi -> accumulates into columns [0, N)
+                        if (SPLIT) umma_f16(d_tmem, da_lo + adv, dw_hi + adv, idesc_n, 1u);
                     }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (it == n_iters - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                __syncwarp();
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
-            umma_commit(&tmem_full_bar);  // accumulator complete
         }
     } else {
         // =============================== epilogue (warps 2..5) ===============================
-        mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;       // M index inside the tile
+        const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;  // M index inside the tile
         const int ly = row / p.BW;
         const int lx = row - ly * p.BW;
-        const int my = oy0 + ly, mx = ox0 + lx;    // output position inside the class grid
-        const bool valid = (my < p.Mh) && (mx < p.Mw);
-        int oy = my, ox = mx;
-        if (p.out_stride == 2) {
-            oy = my * 2 + (cls >> 1);
-            ox = mx * 2 + (cls & 1);
-        }
-        float* orow = p.out + (((size_t)b * p.Hout + oy) * p.Wout + ox) * p.cout + n0;
-        const float* cb = nullptr;
-        if (p.cbias != nullptr && valid) {
-            int mask = 0;
-            for (int kw = 0; kw < p.cb_k; ++kw) {
-                const int ix = ox * p.cb_stride + kw * p.cb_rate - p.cb_pad_l;
-                if (ix >= 0 && ix < p.cb_Win) mask |= 1 << kw;
+        float s_sum = 0.f, s_sq = 0.f;
+        int cur_b = -1;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const TileCoord tc = decode_tile(p, tile, N_TILE);
+            if (p.do_stats && tc.b != cur_b) {
+                if (cur_b >= 0) {
+                    const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
+                    if (lane == 0)
+                        p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * 4 + quarter] = make_double2(ds, dq);
+                    s_sum = 0.f;
+                    s_sq = 0.f;
+                }
+                cur_b = tc.b;
             }
-            cb = p.cbias + ((size_t)oy * 8 + mask) * p.cout + n0;
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c = 0; c < p.n_tile; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + (uint32_t)c, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (valid) {
+            const int my = tc.oy0 + ly, mx = tc.ox0 + lx;  // output position inside the class grid
+            const bool valid = (my < p.Mh) && (mx < p.Mw);
+            int oy = my, ox = mx;
+            if (p.out_stride == 2) {
+                oy = my * 2 + (tc.cls >> 1);
+                ox = mx * 2 + (tc.cls & 1);
+            }
+            float* orow = p.out + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * p.cout + tc.n0;
+            const float* cb = nullptr;
+            if (p.cbias != nullptr && valid) {
+                int mask = 0;
+                for (int kw = 0; kw < p.cb_k; ++kw) {
+                    const int ix = ox * p.cb_stride + kw * p.cb_rate - p.cb_pad_l;
+                    if (ix >= 0 && ix < p.cb_Win) mask |= 1 << kw;
+                }
+                cb = p.cbias + ((size_t)oy * 8 + mask) * p.cout + tc.n0;
+            }
+            const int acc = local & 1;
+            const uint32_t use = (uint32_t)(local >> 1);
+            mbar_wait(&tmem_full_bar[acc], use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
+#pragma unroll 1
+            for (int c = 0; c < N_TILE; c += 32) {
+                uint32_t r[32];
+                uint32_t r2[SPLIT ? 32 : 1];
+                tmem_ld32(taddr + (uint32_t)c, r);
+                if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 32 >= N_TILE) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v;
-                    v.x = __uint_as_float(r[j + 0]) * p.unscale;
-                    v.y = __uint_as_float(r[j + 1]) * p.unscale;
-                    v.z = __uint_as_float(r[j + 2]) * p.unscale;
-                    v.w = __uint_as_float(r[j + 3]) * p.unscale;
-                    if (cb != nullptr) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(cb + c + j));
-                        v.x += q.x;
-                        v.y += q.y;
-                        v.z += q.z;
-                        v.w += q.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        if (SPLIT) {
+                            v.x = (__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0])) * p.unscale;
+                            v.y = (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) * p.unscale;
+                            v.z = (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) * p.unscale;
+                            v.w = (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) * p.unscale;
+                        } else {
+                            v.x = __uint_as_float(r[j + 0]) * p.unscale;
+                            v.y = __uint_as_float(r[j + 1]) * p.unscale;
+                            v.z = __uint_as_float(r[j + 2]) * p.unscale;
+                            v.w = __uint_as_float(r[j + 3]) * p.unscale;
+                        }
+                        if (cb != nullptr) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(cb + c + j));
+                            v.x += q.x;
+                            v.y += q.y;
+                            v.z += q.z;
+                            v.w += q.w;
+                        }
+                        if (p.kind == kHead) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + tc.n0 + c + j));
+                            v.x = tanhf(v.x + q.x);
+                            v.y = tanhf(v.y + q.y);
+                            v.z = tanhf(v.z + q.z);
+                            v.w = tanhf(v.w + q.w);
+                        }
+                        s_sum += (v.x + v.y) + (v.z + v.w);
+                        s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                        *reinterpret_cast<float4*>(orow + c + j) = v;
                     }
-                    if (p.kind == kHead) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
-                        v.x = tanhf(v.x + q.x);
-                        v.y = tanhf(v.y + q.y);
-                        v.z = tanhf(v.z + q.z);
-                        v.w = tanhf(v.w + q.w);
+                }
+            }
+        }
+        if (p.do_stats) {
+            if (cur_b >= 0) {
+                const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
+                if (lane == 0)
+                    p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * 4 + quarter] = make_double2(ds, dq);
+            }
+            // last CTA to finish turns the partials into (mean, rstd) per frame
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = threadIdx.x - 64;  // 0..127 inside the epilogue group
+            if (et == 0) s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_is_last) {
+                __threadfence();
+                const int used = gridDim.x * 4;
+                for (int b = 0; b < p.B; ++b) {
+                    double s = 0, q = 0;
+                    for (int i = et; i < used; i += 128) {
+                        const double2 v = __ldcg(&p.partials[(size_t)b * p.n_partials + i]);
+                        s += v.x;
+                        q += v.y;
                     }
-                    *reinterpret_cast<float4*>(orow + c + j) = v;
+                    s = warp_sum_d(s);
+                    q = warp_sum_d(q);
+                    if (lane == 0) {
+                        s_red[0][quarter] = s;
+                        s_red[1][quarter] = q;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        const double a = s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3];
+                        const double c = s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3];
+                        const double mean = a / p.n_per_sample;
+                        double var = c / p.n_per_sample - mean * mean;
+                        if (var < 0) var = 0;
+                        p.stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-12)));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
             }
         }
@@ -338,12 +500,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (p.n_tile == 64)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
-        else if (p.n_tile == 128)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -464,17 +621,48 @@ void pick_tile(int Mh, int Mw, int& BH, int& BW) {
     }
 }
 
+int num_sms() {
+    static int n = 0;
+    if (n > 0) return n;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0) {
+        cudaGetLastError();
+        n = 0;
+        return 148;
+    }
+    return n;
+}
+
+template <int N_TILE, int SPLIT>
+int launch_tc(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_tcgen05_kernel<N_TILE, SPLIT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_igemm_tcgen05_kernel<%d,%d>, %d) failed: %s", N_TILE, SPLIT, kMaxDynSmem,
+                      cudaGetErrorString(e));
+            return MSI_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    conv_igemm_tcgen05_kernel<N_TILE, SPLIT><<<plan->grid, kThreads, plan->smem_bytes, st>>>(
+        plan->a_map[0][0], plan->a_map[0][1], plan->a_map[1][0], plan->a_map[1][1], plan->w_map[0], plan->w_map[1], p);
+    return MSI_OK;
+}
+
 }  // namespace
 
 int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int precision) {
     TcPlan* plan = new TcPlan();
     memset(plan, 0, sizeof(TcPlan));
     TcParams& p = plan->p;
-    p.split = (precision == MSI_PREC_FP16X3) ? 1 : 0;
-    p.n_tile = (L.cout % 128 == 0) ? 128 : L.cout;
-    if (!(p.n_tile == 64 || p.n_tile == 128 || p.n_tile == 256)) {
+    plan->split = (precision == MSI_PREC_FP16X3) ? 1 : 0;
+    plan->n_tile = (L.cout % 128 == 0) ? 128 : 64;
+    if (L.cout % plan->n_tile != 0) {
         delete plan;
-        set_error("conv_tc: layer %s has cout=%d; the tcgen05 back end needs 64, or a multiple of 128", L.scope, L.cout);
+        set_error("conv_tc: layer %s has cout=%d; the tcgen05 back end needs a multiple of 64", L.scope, L.cout);
         return MSI_ERR_UNSUPPORTED;
     }
     p.kind = L.kind;
@@ -510,6 +698,8 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     pick_tile(p.Mh, p.Mw, p.BH, p.BW);
     p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
     p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
+    p.n_tiles = L.cout / plan->n_tile;
+    p.tiles_per_sample = p.tiles_x * p.tiles_y * p.n_tiles * p.ncls;
     p.Hout = L.Hout;
     p.Wout = L.Wout;
     p.cout = L.cout;
@@ -521,16 +711,21 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     p.cb_pad_l = L.pad_l;
     p.cb_Win = L.Win;
     p.bias = (L.kind == kHead) ? L.bias : nullptr;
-    p.stage_bytes = (kATileBytes + p.n_tile * kBlockK * 2) * (p.split ? 2 : 1);
-    p.stages = (kMaxSmem - 1024) / p.stage_bytes;
+    const int stage_bytes = (kATileBytes + plan->n_tile * kBlockK * 2) * (plan->split ? 2 : 1);
+    p.stages = (kMaxDynSmem - 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) {
         delete plan;
         set_error("conv_tc: layer %s does not fit 2 pipeline stages", L.scope);
         return MSI_ERR_UNSUPPORTED;
     }
-    plan->smem_bytes = p.stages * p.stage_bytes + 1024;
-    plan->grid = dim3(p.tiles_x * p.tiles_y, L.cout / p.n_tile, max_batch * p.ncls);
+    plan->smem_bytes = p.stages * stage_bytes + 1024;
+    p.do_stats = (L.kind != kHead) ? 1 : 0;
+    p.n_partials = L.n_partials;
+    p.partials = L.partials;
+    p.counter = L.counter;
+    p.stats = L.stats;
+    p.n_per_sample = (double)L.Hout * L.Wout * L.cout;
 
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s) {
@@ -544,22 +739,11 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
         plan->a_map[1][0] = plan->a_map[0][0];
         plan->a_map[1][1] = plan->a_map[0][1];
     }
-    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[0], L.w_hi, L.K, L.cout, L.ncls, p.n_tile);
-    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[1], L.w_lo, L.K, L.cout, L.ncls, p.n_tile);
+    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[0], L.w_hi, L.K, L.cout, L.ncls, plan->n_tile);
+    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[1], L.w_lo, L.K, L.cout, L.ncls, plan->n_tile);
     if (rc != MSI_OK) {
         delete plan;
         return rc;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxSmem);
-        if (e != cudaSuccess) {
-            delete plan;
-            set_error("cudaFuncSetAttribute(conv_igemm_tcgen05_kernel, %d) failed: %s", kMaxSmem, cudaGetErrorString(e));
-            return MSI_ERR_CUDA;
-        }
-        attr_set = true;
     }
     L.tc_plan = plan;
     return MSI_OK;
@@ -599,6 +783,8 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
     return MSI_OK;
 }
 
+// The caller has zeroed L.partials / L.counter on `st` before this launch (net.cu does one memset
+// for all layers per forward).  On return L.stats holds (mean, rstd) per frame.
 int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
     TcPlan* plan = reinterpret_cast<TcPlan*>(L.tc_plan);
     if (!plan) {
@@ -607,11 +793,22 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
     }
     TcParams p = plan->p;
     p.out = out;
-    dim3 grid = plan->grid;
-    grid.z = B * p.ncls;
-    conv_igemm_tcgen05_kernel<<<grid, kThreads, plan->smem_bytes, st>>>(plan->a_map[0][0], plan->a_map[0][1],
-                                                                        plan->a_map[1][0], plan->a_map[1][1],
-                                                                        plan->w_map[0], plan->w_map[1], p);
+    p.B = B;
+    p.total_tiles = p.tiles_per_sample * B;
+    int grid = num_sms();
+    if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    plan->grid = grid;
+    if (p.do_stats && grid * 4 > p.n_partials) {
+        set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * 4);
+        return MSI_ERR_STATE;
+    }
+    int rc;
+    if (plan->n_tile == 64)
+        rc = plan->split ? launch_tc<64, 1>(plan, p, st) : launch_tc<64, 0>(plan, p, st);
+    else
+        rc = plan->split ? launch_tc<128, 1>(plan, p, st) : launch_tc<128, 0>(plan, p, st);
+    if (rc != MSI_OK) return rc;
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

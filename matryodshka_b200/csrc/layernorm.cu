@@ -111,14 +111,17 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
 
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool partials_ready, cudaStream_t st) {
+               bool stats_ready, cudaStream_t st) {
     MSI_CHECK_ARG(C % 8 == 0, "layer_norm: C=%d must be a multiple of 8", C);
-    if (!partials_ready) {
-        ln_partial_kernel<<<dim3(n_partials, B), 256, 0, st>>>(raw, n_per_sample, partials, n_partials);
+    if (!stats_ready) {
+        // stand-alone statistics (SIMT back end); the tcgen05 conv kernel produces `stats` itself
+        const int np = ln_partials_count(n_per_sample);
+        MSI_CHECK_ARG(np <= n_partials, "layer_norm: %d partial slots < %d", n_partials, np);
+        ln_partial_kernel<<<dim3(np, B), 256, 0, st>>>(raw, n_per_sample, partials, np);
+        MSI_LAUNCH_CHECK();
+        ln_finalize_kernel<<<B, 256, 0, st>>>(partials, np, n_per_sample, stats);
         MSI_LAUNCH_CHECK();
     }
-    ln_finalize_kernel<<<B, 256, 0, st>>>(partials, n_partials, n_per_sample, stats);
-    MSI_LAUNCH_CHECK();
     ln_apply_kernel<<<dim3(ceil_div(n_per_sample, 256 * 8), B), 256, 0, st>>>(raw, n_per_sample, C, stats, gamma,
                                                                             beta, out_hi, out_lo);
     MSI_LAUNCH_CHECK();

@@ -22,10 +22,11 @@ struct msi_net {
     // carve-out offsets (filled at create, turned into pointers at bind)
     struct Off {
         size_t w_f32, gamma, beta, bias, cbias, w_hi, w_lo;  // arena
-        size_t raw, partials, stats, act_hi, act_lo;         // workspace
+        size_t raw, partials, counter, stats, act_hi, act_lo;  // workspace
     };
     std::vector<Off> off;
     size_t in_hi_off = 0, in_lo_off = 0;
+    size_t stat_begin = 0, stat_end = 0;  // [partials | counter] of every layer: one memset per forward
     char* ws = nullptr;
     char* arena = nullptr;
     bool bound = false;
@@ -199,10 +200,9 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
 
         const size_t n_per = (size_t)L.Hout * L.Wout * L.cout;
         L.n_partials = ln_partials_count((long long)n_per);
+        if (L.n_partials < kMaxPersistentCtas * 4) L.n_partials = kMaxPersistentCtas * 4;
         f.raw = w;
         if (r.kind != kHead) w += align_up(B * n_per * sizeof(float));
-        f.partials = w;
-        w += align_up(B * L.n_partials * sizeof(double2));
         f.stats = w;
         w += align_up(B * sizeof(float2));
         f.act_hi = w;
@@ -223,6 +223,15 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
             }
         }
     }
+    net->stat_begin = w;
+    for (int i = 0; i < kNumLayers; ++i) {
+        msi_net::Off& f = net->off[i];
+        f.partials = w;
+        w += align_up(B * net->layers[i].n_partials * sizeof(double2));
+        f.counter = w;
+        w += align_up(sizeof(unsigned int));
+    }
+    net->stat_end = w;
     net->ws_bytes = w;
     net->arena_bytes = a;
     *out = net;
@@ -241,8 +250,8 @@ extern "C" int msi_net_input_c_stride(const msi_net* net) { return net ? net->in
 
 extern "C" int msi_net_num_launches_per_forward(const msi_net* net) {
     if (!net) return 0;
-    // conv + (stats, finalize, apply) per normalised layer, + head
-    return (kNumLayers - 1) * 4 + 1;
+    // tcgen05: conv (statistics fused) + normalise per layer, + head;  SIMT: conv + 3 LayerNorm kernels
+    return (kNumLayers - 1) * (net->conv_impl == MSI_CONV_TCGEN05 ? 2 : 4) + 1;
 }
 
 extern "C" int msi_net_bind(msi_net* net, void* workspace, size_t workspace_bytes, void* arena, size_t arena_bytes) {
@@ -267,6 +276,7 @@ extern "C" int msi_net_bind(msi_net* net, void* workspace, size_t workspace_byte
         L.w_lo = (__half*)(net->arena + f.w_lo);
         L.raw = (L.kind != kHead) ? (float*)(net->ws + f.raw) : nullptr;
         L.partials = (double2*)(net->ws + f.partials);
+        L.counter = (unsigned int*)(net->ws + f.counter);
         L.stats = (float2*)(net->ws + f.stats);
         if (L.kind != kHead) {
             net->acts[i + 1].hi = (__half*)(net->ws + f.act_hi);
@@ -408,6 +418,9 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
         MSI_CUDA(cudaMemcpyAsync(net->acts[0].hi, in_hi, in_elems * sizeof(__half), cudaMemcpyDeviceToDevice, st));
         MSI_CUDA(cudaMemcpyAsync(net->acts[0].lo, in_lo, in_elems * sizeof(__half), cudaMemcpyDeviceToDevice, st));
     }
+    const bool tc = net->conv_impl == MSI_CONV_TCGEN05;
+    if (tc)  // zero the LayerNorm partial sums and CTA counters of every layer
+        MSI_CUDA(cudaMemsetAsync(net->ws + net->stat_begin, 0, net->stat_end - net->stat_begin, st));
     for (int i = 0; i < kNumLayers; ++i) {
         LayerPlan& L = net->layers[i];
         ActBuf srcs[2];
@@ -423,7 +436,7 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
         if (L.kind != kHead) {
             const long long n_per = (long long)L.Hout * L.Wout * L.cout;
             rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                            net->acts[i + 1].hi, net->acts[i + 1].lo, /*partials_ready=*/false, st);
+                            net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, st);
             if (rc != MSI_OK) return rc;
             if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i + 2], st));
         }

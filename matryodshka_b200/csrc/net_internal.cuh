@@ -9,6 +9,9 @@ namespace msi {
 
 enum LayerKind { kConv = 0, kDeconv = 1, kHead = 2 };
 
+// persistent conv kernel: at most this many CTAs (B200 has 148 SMs); 4 statistic slots per CTA
+constexpr int kMaxPersistentCtas = 160;
+
 // One activation tensor in the workspace: post-LayerNorm+ReLU values scaled by MSI_ACT_SCALE and
 // split into fp16 hi + lo, NHWC with channel stride c_stride (>= C, multiple of 64 for tcgen05).
 struct ActBuf {
@@ -43,6 +46,7 @@ struct LayerPlan {
     float* raw = nullptr;     // [B,Hout,Wout,cout] pre-LayerNorm conv output (head: pred, caller's buffer)
     double2* partials = nullptr;  // [B][n_partials] (sum, sumsq)
     float2* stats = nullptr;      // [B] (mean, rstd)
+    unsigned int* counter = nullptr;  // CTA completion counter of the fused statistics (tcgen05 back end)
     int n_partials = 0;
     int out_act = -1;         // index of the activation this layer produces
     void* tc_plan = nullptr;  // back-end private (TMA descriptors, tile shape)
@@ -109,7 +113,7 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
 int ln_partials_count(long long n_per_sample);
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool partials_ready, cudaStream_t st);
+               bool stats_ready, cudaStream_t st);
 int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st);
 int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
                      cudaStream_t st);
