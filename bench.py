@@ -38,6 +38,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL's version banner, for one) write to fd 1.  Keep the real stdout for the ONE JSON
+# line and send everything else that lands on fd 1 to stderr.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -167,7 +177,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -312,7 +322,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

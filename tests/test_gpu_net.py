@@ -140,3 +140,18 @@ def test_batched_frames_equal_single_frames():
         one.step()
         assert torch.equal(one.out["rgb"][0], big.out["rgb"][b])
         assert torch.equal(one.out["depth_u8"][0], big.out["depth_u8"][b])
+
+
+def test_multi_gpu_gather_equals_single_gpu():
+    """N ranks x 2 frames + NCCL all-gather == one GPU running all frames (bit for bit)."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tests", "_nccl_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
