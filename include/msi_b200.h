@@ -83,7 +83,14 @@ int msi_psv_build(const void* ref, const void* src, int img_dtype, int preproces
                   const float* poses, const float* baselines, const float* depths,
                   const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
                   int B, int H, int W, int P,
-                  float* out_f32, void* out_hi, void* out_lo, int c_stride, void* stream);
+                  float* out_f32, void* out_hi, void* out_lo, int c_stride,
+                  void* scratch, size_t scratch_bytes, void* stream);
+
+/* Optional scratch for msi_psv_build (16-byte aligned device memory, >= this many
+ * bytes): with it the sweep first packs both images to preprocessed RGBX float4
+ * and evaluates both eyes per thread (2 launches, ~2x faster); with scratch ==
+ * NULL it runs the single-kernel form.  Results are identical. */
+size_t msi_psv_scratch_bytes(int B, int H, int W);
 
 /* Sample coordinates only (spherical.project_ods, spherical.py:170-233, after
  * backproject + apply_pose): uv [B,2,P,H,W,2] (x=u, y=v) and valid [B,2,P,H,W]

@@ -26,7 +26,9 @@ SIGNATURES = {
     "msi_b200_abi_version": (c_int, []),
     "msi_last_error": (c_char_p, []),
     "msi_launch_count": (c_uint64, []),
-    "msi_psv_build": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "msi_psv_build": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P,
+                              c_size_t, _P]),
+    "msi_psv_scratch_bytes": (c_size_t, [_I, _I, _I]),
     "msi_sweep_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_rgba_assemble": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "msi_render_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -41,7 +41,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // fp16 elements = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, half the columns each
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxDynSmem = 227 * 1024 - 4096;      // 227 KB minus this kernel's static shared memory
 
 struct TcParams {
@@ -68,7 +69,7 @@ struct TcParams {
     // LayerNorm statistics
     int do_stats;
     int B;
-    int n_partials;      // slots per frame (>= gridDim.x * 4)
+    int n_partials;      // slots per frame (>= gridDim.x * kEpiWarps)
     double2* partials;   // [B][n_partials], zeroed before the launch
     unsigned int* counter;  // zeroed before the launch
     float2* stats;       // [B] (mean, rstd)
@@ -189,6 +190,10 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t base) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
 }
+// tanh(x) = 1 - 2 / (1 + e^(2x)); ex2.approx + fast division: abs error < 2e-7 on the whole range
+// (e^(2x) -> inf gives 1, -> 0 gives -1), ~6 instructions instead of ~30 for tanhf.
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -239,7 +244,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int s_is_last;
-    __shared__ double s_red[2][4];
+    __shared__ double s_red[2][kEpiWarps];
     __shared__ int s_dx[4][9], s_dy[4][9];
     __shared__ int s_ntaps[4];
 
@@ -262,7 +267,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -364,6 +369,8 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     } else {
         // =============================== epilogue (warps 2..5) ===============================
         const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+        const int ew = warp - 2;              // 0..7
+        const int c_begin = (ew >> 2) * (N_TILE / 2), c_end = c_begin + N_TILE / 2;  // this warp's columns
         const int row = quarter * 32 + lane;  // M index inside the tile
         const int ly = row / p.BW;
         const int lx = row - ly * p.BW;
@@ -376,7 +383,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                 if (cur_b >= 0) {
                     const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
                     if (lane == 0)
-                        p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * 4 + quarter] = make_double2(ds, dq);
+                        p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew] = make_double2(ds, dq);
                     s_sum = 0.f;
                     s_sq = 0.f;
                 }
@@ -405,13 +412,13 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
 #pragma unroll 1
-            for (int c = 0; c < N_TILE; c += 32) {
+            for (int c = c_begin; c < c_end; c += 32) {
                 uint32_t r[32];
                 uint32_t r2[SPLIT ? 32 : 1];
                 tmem_ld32(taddr + (uint32_t)c, r);
                 if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 32 >= N_TILE) {
+                if (c + 32 >= c_end) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -441,10 +448,10 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                         }
                         if (p.kind == kHead) {
                             const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + tc.n0 + c + j));
-                            v.x = tanhf(v.x + q.x);
-                            v.y = tanhf(v.y + q.y);
-                            v.z = tanhf(v.z + q.z);
-                            v.w = tanhf(v.w + q.w);
+                            v.x = fast_tanh(v.x + q.x);
+                            v.y = fast_tanh(v.y + q.y);
+                            v.z = fast_tanh(v.z + q.z);
+                            v.w = fast_tanh(v.w + q.w);
                         }
                         s_sum += (v.x + v.y) + (v.z + v.w);
                         s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
@@ -457,20 +464,20 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
             if (cur_b >= 0) {
                 const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
                 if (lane == 0)
-                    p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * 4 + quarter] = make_double2(ds, dq);
+                    p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew] = make_double2(ds, dq);
             }
             // last CTA to finish turns the partials into (mean, rstd) per frame
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int et = threadIdx.x - 64;  // 0..127 inside the epilogue group
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            const int et = threadIdx.x - 64;  // index inside the epilogue group
             if (et == 0) s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             if (s_is_last) {
                 __threadfence();
-                const int used = gridDim.x * 4;
+                const int used = gridDim.x * kEpiWarps;
                 for (int b = 0; b < p.B; ++b) {
                     double s = 0, q = 0;
-                    for (int i = et; i < used; i += 128) {
+                    for (int i = et; i < used; i += 32 * kEpiWarps) {
                         const double2 v = __ldcg(&p.partials[(size_t)b * p.n_partials + i]);
                         s += v.x;
                         q += v.y;
@@ -478,19 +485,22 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                     s = warp_sum_d(s);
                     q = warp_sum_d(q);
                     if (lane == 0) {
-                        s_red[0][quarter] = s;
-                        s_red[1][quarter] = q;
+                        s_red[0][ew] = s;
+                        s_red[1][ew] = q;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                     if (et == 0) {
-                        const double a = s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3];
-                        const double c = s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3];
+                        double a = 0, c = 0;
+                        for (int w = 0; w < kEpiWarps; ++w) {
+                            a += s_red[0][w];
+                            c += s_red[1][w];
+                        }
                         const double mean = a / p.n_per_sample;
                         double var = c / p.n_per_sample - mean * mean;
                         if (var < 0) var = 0;
                         p.stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-12)));
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 }
             }
         }
@@ -799,8 +809,8 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
     if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
     if (grid > p.total_tiles) grid = p.total_tiles;
     plan->grid = grid;
-    if (p.do_stats && grid * 4 > p.n_partials) {
-        set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * 4);
+    if (p.do_stats && grid * kEpiWarps > p.n_partials) {
+        set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * kEpiWarps);
         return MSI_ERR_STATE;
     }
     int rc;

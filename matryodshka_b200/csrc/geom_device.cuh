@@ -41,37 +41,69 @@ inline ErpConsts make_erp_consts(int H, int W) {
 
 // spherical.project_ods (spherical.py:170-233, tuple branch) for one 3-D point.
 // order = +1 / -1, r = ODS baseline.  Returns false (and u = v = 1) when disc < 0.
-__device__ __forceinline__ bool project_ods_point(float x, float y, float z, float order, float r,
-                                                  const ErpConsts& k, float& u, float& v) {
-    const float f = r * r - (x * x + z * z);
-    const bool zl = fabsf(z) > fabsf(x);
-    const float px = zl ? x : z;
-    const float pz = zl ? z : x;
-    const float pz2 = pz * pz;
-    const float a = 1.0f + (px * px) / pz2;
-    const float b = ((-2.0f * f) * px) / pz2;
-    const float c = f + (f * f) / pz2;
-    const float disc = b * b - (4.0f * a) * c;
-    const float sgn = (pz > 0.0f) ? 1.0f : ((pz < 0.0f) ? -1.0f : 0.0f);
-    float s = ((-order) * sgn) * sqrtf(disc);
-    s = zl ? s : -s;
-    const float dx0 = (-b + s) / (2.0f * a);
-    const float dz0 = (f - px * dx0) / pz;
-    const float dx = zl ? -dx0 : -dz0;
-    const float dz = zl ? -dz0 : -dx0;
+// The part of project_ods that does not depend on `order` (the eye): the quadratic of :187-192 and
+// sqrt(disc).  Both ODS eyes of one 3-D point share it, so the sweep evaluates it once per
+// (pixel, plane) when the two eyes have the same pose.
+struct OdsQuad {
+    float f, px, pz, a, b, sq, sgn, y;
+    bool zl, valid;
+};
+
+__device__ __forceinline__ OdsQuad ods_quadratic(float x, float y, float z, float r) {
+    OdsQuad q;
+    q.f = r * r - (x * x + z * z);
+    q.zl = fabsf(z) > fabsf(x);
+    q.px = q.zl ? x : z;
+    q.pz = q.zl ? z : x;
+    const float pz2 = q.pz * q.pz;
+    q.a = 1.0f + (q.px * q.px) / pz2;
+    q.b = ((-2.0f * q.f) * q.px) / pz2;
+    const float c = q.f + (q.f * q.f) / pz2;
+    const float disc = q.b * q.b - (4.0f * q.a) * c;
+    q.sgn = (q.pz > 0.0f) ? 1.0f : ((q.pz < 0.0f) ? -1.0f : 0.0f);
+    q.sq = sqrtf(disc);
+    q.valid = disc >= 0.0f;
+    q.y = y;
+    return q;
+}
+
+// The eye-dependent rest of project_ods (:195-229).  Returns false (and u = v = 1) when disc < 0.
+__device__ __forceinline__ bool ods_finish(const OdsQuad& q, float order, const ErpConsts& k, float& u, float& v) {
+    float s = ((-order) * q.sgn) * q.sq;
+    s = q.zl ? s : -s;
+    const float dx0 = (-q.b + s) / (2.0f * q.a);
+    const float dz0 = (q.f - q.px * dx0) / q.pz;
+    const float dx = q.zl ? -dx0 : -dz0;
+    const float dz = q.zl ? -dz0 : -dx0;
     const float theta = -atan2f(dz, dx);
-    float phi = atan2f(y, sqrtf(dx * dx + dz * dz));
+    float phi = atan2f(q.y, sqrtf(dx * dx + dz * dz));
     if (phi != phi) phi = 1.0f;
     phi = (phi <= k.half_pi) ? phi : k.half_pi;
     phi = (phi >= -k.half_pi) ? phi : -k.half_pi;
     u = ((theta + k.pi - k.pi_w) / k.den_u) * k.wm1;
     v = ((phi + k.half_pi - k.half_pi_h) / k.den_v) * k.hm1;
-    const bool valid = disc >= 0.0f;
-    if (!valid) {
+    if (!q.valid) {
         u = 1.0f;
         v = 1.0f;
     }
-    return valid;
+    return q.valid;
+}
+
+__device__ __forceinline__ bool project_ods_point(float x, float y, float z, float order, float r,
+                                                  const ErpConsts& k, float& u, float& v) {
+    const OdsQuad q = ods_quadratic(x, y, z, r);
+    return ods_finish(q, order, k, u, v);
+}
+
+// backproject_spherical (spherical.py:116-129) + apply_pose (projector.py:275-291) of one grid point
+__device__ __forceinline__ void sweep_point(float cs, float sn, float ct, float st, float depth,
+                                            const float* __restrict__ pose, float& x, float& y, float& z) {
+    const float x0 = depth * (cs * ct);
+    const float y0 = depth * st;
+    const float z0 = depth * (sn * ct);
+    x = ((pose[0] * x0 + pose[1] * y0) + pose[2] * z0) + pose[3];
+    y = ((pose[4] * x0 + pose[5] * y0) + pose[6] * z0) + pose[7];
+    z = ((pose[8] * x0 + pose[9] * y0) + pose[10] * z0) + pose[11];
 }
 
 // backproject_spherical (spherical.py:116-129) + apply_pose (projector.py:275-291) +
@@ -86,6 +118,49 @@ __device__ __forceinline__ bool sweep_uv(float cs, float sn, float ct, float st,
     const float y = ((pose[4] * x0 + pose[5] * y0) + pose[6] * z0) + pose[7];
     const float z = ((pose[8] * x0 + pose[9] * y0) + pose[10] * z0) + pose[11];
     return project_ods_point(x, y, z, order, r, k, u, v);
+}
+
+// intersect_sphere split in two: the layer-independent ray of one target pixel (:279-311, and the
+// a, b coefficients of :313-314) ...
+struct SphereRay {
+    float rx, ry, rz, cx, cy, cz, a, b;
+};
+
+__device__ __forceinline__ SphereRay sphere_ray(float cs, float sn, float ct, float st, const float* __restrict__ pos,
+                                                const float* __restrict__ center) {
+    SphereRay q;
+    const float rx0 = cs * ct;
+    const float ry0 = st;
+    const float rz0 = sn * ct;
+    q.rx = (pos[0] * rx0 + pos[1] * ry0) + pos[2] * rz0;
+    q.ry = (pos[4] * rx0 + pos[5] * ry0) + pos[6] * rz0;
+    q.rz = (pos[8] * rx0 + pos[9] * ry0) + pos[10] * rz0;
+    const float c0 = center[2], c1 = center[1], c2 = center[0];  // (cx,cy,cz) = (center[2],[1],[0]) :286-288
+    q.cx = ((pos[0] * c0 + pos[1] * c1) + pos[2] * c2) + pos[3];
+    q.cy = ((pos[4] * c0 + pos[5] * c1) + pos[6] * c2) + pos[7];
+    q.cz = ((pos[8] * c0 + pos[9] * c1) + pos[10] * c2) + pos[11];
+    q.a = (q.rx * q.rx + q.ry * q.ry) + q.rz * q.rz;
+    q.b = 2.0f * ((q.rx * q.cx + q.ry * q.cy) + q.rz * q.cz);
+    return q;
+}
+
+// ... and the per-layer hit + projection (:315-326, :235-246, :54-68).  Same operations in the same
+// order as sphere_uv below, so both forms give identical bits.
+__device__ __forceinline__ void sphere_hit_uv(const SphereRay& q, float radius, const ErpConsts& k, float& u, float& v) {
+    const float c = ((q.cx * q.cx + q.cy * q.cy) + q.cz * q.cz) - radius * radius;
+    const float disc = q.b * q.b - (4.0f * q.a) * c;
+    const float t = (-q.b + sqrtf(disc)) / (2.0f * q.a);
+    const float x = q.cx + t * q.rx;
+    const float y = q.cy + t * q.ry;
+    const float z = q.cz + t * q.rz;
+    const float theta = -atan2f(z, x);
+    const float phi = atan2f(y, sqrtf(x * x + z * z));
+    u = theta + k.pi;
+    u = u - k.pi_w;
+    u = u / k.den_u;
+    u = u * k.wm1;
+    v = (phi + k.half_pi - k.half_pi_h) / k.den_v;
+    v = v * k.hm1;
 }
 
 // spherical.intersect_sphere (spherical.py:268-326) + project_spherical (:235-246) +
@@ -134,6 +209,19 @@ __device__ __forceinline__ int floor_mod(int a, int n) {
     return m < 0 ? m + n : m;
 }
 
+// floor_mod(a + n, n) (sampling.py:162-165).  On the sweep / render paths a lies in [-n, 2n), where
+// two conditional subtractions replace the integer division; anything else takes the general route.
+__device__ __forceinline__ int wrap_index(int a, int n) {
+    const int t = a + n;
+    if ((unsigned)t < (unsigned)(3 * n)) {
+        int m = t;
+        m = (m >= n) ? m - n : m;
+        m = (m >= n) ? m - n : m;
+        return m;
+    }
+    return floor_mod(t, n);
+}
+
 __device__ __forceinline__ Bilinear bilinear_setup(float x, float y, int W, int H) {
     Bilinear s;
     const int x0 = (int)floorf(x);
@@ -144,10 +232,10 @@ __device__ __forceinline__ Bilinear bilinear_setup(float x, float y, int W, int 
     const float dy0 = y - (float)y0;
     const float dx1 = (float)x1 - x;
     const float dy1 = (float)y1 - y;
-    s.x0 = floor_mod(x0 + W, W);
-    s.y0 = floor_mod(y0 + H, H);
-    s.x1 = floor_mod(x1 + W, W);
-    s.y1 = floor_mod(y1 + H, H);
+    s.x0 = wrap_index(x0, W);
+    s.y0 = wrap_index(y0, H);
+    s.x1 = wrap_index(x1, W);
+    s.y1 = wrap_index(y1, H);
     s.wa = dy1 * dx1;
     s.wb = dy1 * dx0;
     s.wc = dy0 * dx1;

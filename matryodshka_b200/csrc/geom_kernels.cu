@@ -117,6 +117,111 @@ __global__ void __launch_bounds__(256) psv_build_kernel(PsvParams p) {
     }
 }
 
+// K1, two-eye form (used when the caller provides scratch and 256 % P == 0).
+//   pre-pass: both images -> float4 RGBX, preprocessed once per pixel (not once per tap);
+//   main:     one thread per (pixel, plane) produces BOTH eyes: when the two eyes have the same pose
+//             (ODS data: both identity) the quadratic of project_ods is evaluated once and only the
+//             sign of its root differs (order = +1 / -1), bit for bit as in two separate evaluations;
+//             taps are four 128-bit loads per eye; the block stages its 256/P pixels x 6P channels
+//             (6 KB, contiguous in the PSV) in shared memory and stores 128-bit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_images_kernel(const T* __restrict__ ref, const T* __restrict__ src, long long npix, int preprocess,
+                   float4* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= 2 * npix) return;
+    const int e = idx >= npix;
+    const long long pix = idx - (e ? npix : 0);
+    const T* img = e ? src : ref;
+    float4 o;
+    o.x = load_img<T>(img, (size_t)pix * 3 + 0, preprocess);
+    o.y = load_img<T>(img, (size_t)pix * 3 + 1, preprocess);
+    o.z = load_img<T>(img, (size_t)pix * 3 + 2, preprocess);
+    o.w = 0.f;
+    out[idx] = o;
+}
+
+__device__ __forceinline__ void sample_rgbx(const float4* __restrict__ img, size_t ib, int W, int H, float u, float v,
+                                            float& r0, float& r1, float& r2) {
+    const Bilinear s = bilinear_setup(u, v, W, H);
+    const float4 pa = __ldg(img + ib + (size_t)s.y0 * W + s.x0);
+    const float4 pb = __ldg(img + ib + (size_t)s.y0 * W + s.x1);
+    const float4 pc = __ldg(img + ib + (size_t)s.y1 * W + s.x0);
+    const float4 pd = __ldg(img + ib + (size_t)s.y1 * W + s.x1);
+    r0 = blend4(s, pa.x, pb.x, pc.x, pd.x);
+    r1 = blend4(s, pa.y, pb.y, pc.y, pd.y);
+    r2 = blend4(s, pa.z, pb.z, pc.z, pd.z);
+}
+
+__global__ void __launch_bounds__(256) psv_build_pair_kernel(PsvParams p, const float4* __restrict__ rgbx) {
+    __shared__ __align__(16) float stage[1536];
+    __shared__ int s_b[64], s_i[64], s_j[64], s_same[64];
+    const int P = p.P;
+    const unsigned ppb = 256u / (unsigned)P;  // pixels per block (<= 64: P >= 4)
+    const unsigned npix = (unsigned)p.B * (unsigned)p.H * (unsigned)p.W;  // < 2^31 (checked on the host)
+    const unsigned pix0 = blockIdx.x * ppb;
+    if (threadIdx.x < ppb) {
+        // decode the block's pixels once (32-bit), and compare the two eye poses of their frame once
+        const unsigned px = pix0 + threadIdx.x;
+        const unsigned row = px / (unsigned)p.W;
+        const unsigned bb = row / (unsigned)p.H;
+        s_j[threadIdx.x] = (int)(px - row * (unsigned)p.W);
+        s_i[threadIdx.x] = (int)(row - bb * (unsigned)p.H);
+        s_b[threadIdx.x] = (int)bb;
+        int same = 1;
+        if (px < npix) {
+            const float* pose0 = p.poses + (size_t)bb * 32;
+            for (int q = 0; q < 12; ++q) same &= (__ldg(pose0 + q) == __ldg(pose0 + 16 + q)) ? 1 : 0;
+        }
+        s_same[threadIdx.x] = same;
+    }
+    __syncthreads();
+    const unsigned lp = threadIdx.x / (unsigned)P;
+    const int pl = (int)(threadIdx.x - lp * (unsigned)P);
+    const unsigned pix = pix0 + lp;
+    if (pix < npix) {
+        const int j = s_j[lp], i = s_i[lp], b = s_b[lp];
+        const bool same = s_same[lp] != 0;
+        const float cs = __ldg(p.cos_s + j), sn = __ldg(p.sin_s + j), ct = __ldg(p.cos_t + i), st = __ldg(p.sin_t + i);
+        const float depth = __ldg(p.depths + pl);
+        const float r = __ldg(p.baselines + b);
+        const float* pose0 = p.poses + (size_t)b * 32;
+        const float* pose1 = pose0 + 16;
+        float x, y, z;
+        sweep_point(cs, sn, ct, st, depth, pose0, x, y, z);
+        const OdsQuad q0 = ods_quadratic(x, y, z, r);
+        OdsQuad q1 = q0;
+        if (!same) {
+            sweep_point(cs, sn, ct, st, depth, pose1, x, y, z);
+            q1 = ods_quadratic(x, y, z, r);
+        }
+        float u0, v0, u1, v1;
+        ods_finish(q0, 1.0f, p.k, u0, v0);
+        ods_finish(q1, -1.0f, p.k, u1, v1);
+        const size_t ib = (size_t)b * p.H * p.W;
+        float* s0 = stage + lp * 6 * P + 3 * pl;
+        sample_rgbx(rgbx, ib, p.W, p.H, u0, v0, s0[0], s0[1], s0[2]);
+        float* s1 = s0 + 3 * P;
+        sample_rgbx(rgbx + npix, ib, p.W, p.H, u1, v1, s1[0], s1[1], s1[2]);
+    }
+    __syncthreads();
+    const unsigned nvalid = (npix - pix0 < ppb) ? (npix - pix0) : ppb;  // pixels of this block inside the tensor
+    const int nfl = (int)nvalid * 6 * P;                                  // multiple of 6P
+    const size_t fbase = (size_t)pix0 * 6 * P;                            // multiple of 1536 floats
+    if (p.out_f32 != nullptr)
+        for (int q = threadIdx.x; q < nfl / 4; q += 256)
+            reinterpret_cast<float4*>(p.out_f32 + fbase)[q] = reinterpret_cast<const float4*>(stage)[q];
+    if (p.out_hi != nullptr)
+        for (int q = threadIdx.x; q < nfl / 8; q += 256) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) split_half(stage[8 * q + t] * MSI_ACT_SCALE, hi[t], lo[t]);
+            reinterpret_cast<uint4*>(p.out_hi + fbase)[q] = *reinterpret_cast<const uint4*>(hi);
+            if (p.out_lo != nullptr) reinterpret_cast<uint4*>(p.out_lo + fbase)[q] = *reinterpret_cast<const uint4*>(lo);
+        }
+}
+
 __global__ void __launch_bounds__(256) sweep_coords_kernel(PsvParams p, float* uv, uint8_t* valid) {
     // output order [B,2,P,H,W]: thread per element, W fastest
     const long long total = (long long)p.B * 2 * p.P * p.H * p.W;
@@ -232,26 +337,62 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
     const int L = p.L;
     const int ld = L + 1;
     float* frac = sm + 4 * 32 * ld;
+    __shared__ SphereRay s_ray[32];
+    __shared__ int s_b[32];
     const long long npix = (long long)p.B * p.H * p.W;
     const long long pix0 = (long long)blockIdx.x * 32;
 
     for (int l = threadIdx.x; l < L; l += 256) frac[l] = (float)((double)l / (double)L);
-
-    for (int s = threadIdx.x; s < 32 * L; s += 256) {
-        const int q = s / L;
-        const int l = s - q * L;
+    if (threadIdx.x >= 224) {
+        // the layer-independent ray of each of the block's 32 pixels, once
+        const int q = threadIdx.x - 224;
         const long long pix = pix0 + q;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        int b = 0;
+        SphereRay ray = {};
         if (pix < npix) {
             const int j = (int)(pix % p.W);
             const int i = (int)((pix / p.W) % p.H);
-            const int b = (int)(pix / ((long long)p.W * p.H));
-            o = sample_layer(p, b, i, j, l);
+            b = (int)(pix / ((long long)p.W * p.H));
+            ray = sphere_ray(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                             p.pose_rt + b * 16, p.tgt_pos + b * 3);
         }
-        sm[(0 * 32 + q) * ld + l] = o.x;
-        sm[(1 * 32 + q) * ld + l] = o.y;
-        sm[(2 * 32 + q) * ld + l] = o.z;
-        sm[(3 * 32 + q) * ld + l] = o.w;
+        s_ray[q] = ray;
+        s_b[q] = b;
+    }
+    __syncthreads();
+
+    {
+        // walk (pixel, layer) incrementally: no division in the sample loop
+        int q = threadIdx.x / L;
+        int l = threadIdx.x - q * L;
+        const int dq = 256 / L, dl = 256 - dq * L;
+        for (int s = threadIdx.x; s < 32 * L; s += 256) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix0 + q < npix) {
+                float u, v;
+                sphere_hit_uv(s_ray[q], __ldg(p.depths + l), p.k, u, v);
+                const Bilinear sb = bilinear_setup(u, v, p.W, p.H);
+                const float4* base = p.rgba + (size_t)s_b[q] * p.H * p.W * L + l;
+                const float4 pa = __ldg(base + ((size_t)sb.y0 * p.W + sb.x0) * L);
+                const float4 pb = __ldg(base + ((size_t)sb.y0 * p.W + sb.x1) * L);
+                const float4 pc = __ldg(base + ((size_t)sb.y1 * p.W + sb.x0) * L);
+                const float4 pd = __ldg(base + ((size_t)sb.y1 * p.W + sb.x1) * L);
+                o.x = blend4(sb, pa.x, pb.x, pc.x, pd.x);
+                o.y = blend4(sb, pa.y, pb.y, pc.y, pd.y);
+                o.z = blend4(sb, pa.z, pb.z, pc.z, pd.z);
+                o.w = blend4(sb, pa.w, pb.w, pc.w, pd.w);
+            }
+            sm[(0 * 32 + q) * ld + l] = o.x;
+            sm[(1 * 32 + q) * ld + l] = o.y;
+            sm[(2 * 32 + q) * ld + l] = o.z;
+            sm[(3 * 32 + q) * ld + l] = o.w;
+            q += dq;
+            l += dl;
+            if (l >= L) {
+                l -= L;
+                ++q;
+            }
+        }
     }
     __syncthreads();
 
@@ -406,10 +547,15 @@ static int fill_psv_params(PsvParams& p, const void* ref, const void* src, int p
     return MSI_OK;
 }
 
+extern "C" size_t msi_psv_scratch_bytes(int B, int H, int W) {
+    return (size_t)2 * (size_t)B * (size_t)H * (size_t)W * sizeof(float4);
+}
+
 extern "C" int msi_psv_build(const void* ref, const void* src, int img_dtype, int preprocess, const float* poses,
                              const float* baselines, const float* depths, const float* cos_s, const float* sin_s,
                              const float* cos_t, const float* sin_t, int B, int H, int W, int P, float* out_f32,
-                             void* out_hi, void* out_lo, int c_stride, void* stream) {
+                             void* out_hi, void* out_lo, int c_stride, void* scratch, size_t scratch_bytes,
+                             void* stream) {
     PsvParams p;
     int rc = fill_psv_params(p, ref, src, preprocess, poses, baselines, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, P);
     if (rc != MSI_OK) return rc;
@@ -427,7 +573,24 @@ extern "C" int msi_psv_build(const void* ref, const void* src, int img_dtype, in
         MSI_CUDA(cudaMemsetAsync(out_hi, 0, bytes, st));
         if (out_lo) MSI_CUDA(cudaMemsetAsync(out_lo, 0, bytes, st));
     }
-    const long long total = (long long)B * H * W * 2 * P;
+    const long long npix = (long long)B * H * W;
+    const bool pair = scratch != nullptr && scratch_bytes >= msi_psv_scratch_bytes(B, H, W) && (256 % P == 0) &&
+                      npix < (1LL << 31) &&
+                      (P % 4 == 0) && p.c_stride == 6 * P && ((uintptr_t)scratch % 16 == 0);
+    if (pair) {
+        float4* rgbx = reinterpret_cast<float4*>(scratch);
+        if (img_dtype == MSI_IMG_F32)
+            prep_images_kernel<float><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
+                reinterpret_cast<const float*>(ref), reinterpret_cast<const float*>(src), npix, preprocess, rgbx);
+        else
+            prep_images_kernel<uint8_t><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
+                reinterpret_cast<const uint8_t*>(ref), reinterpret_cast<const uint8_t*>(src), npix, preprocess, rgbx);
+        MSI_LAUNCH_CHECK();
+        psv_build_pair_kernel<<<ceil_div(npix, 256 / P), 256, 0, st>>>(p, rgbx);
+        MSI_LAUNCH_CHECK();
+        return MSI_OK;
+    }
+    const long long total = npix * 2 * P;
     const int grid = ceil_div(total, 256);
     if (img_dtype == MSI_IMG_F32)
         psv_build_kernel<float><<<grid, 256, 0, st>>>(p);

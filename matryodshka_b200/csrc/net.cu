@@ -200,7 +200,7 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
 
         const size_t n_per = (size_t)L.Hout * L.Wout * L.cout;
         L.n_partials = ln_partials_count((long long)n_per);
-        if (L.n_partials < kMaxPersistentCtas * 4) L.n_partials = kMaxPersistentCtas * 4;
+        if (L.n_partials < kMaxPersistentCtas * 8) L.n_partials = kMaxPersistentCtas * 8;
         f.raw = w;
         if (r.kind != kHead) w += align_up(B * n_per * sizeof(float));
         f.stats = w;

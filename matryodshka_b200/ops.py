@@ -71,7 +71,8 @@ def _dev_f32(x, device, shape=None):
     return t.contiguous()
 
 
-def psv_build(ref, src, poses, baselines, depths, *, preprocess=True, want_f32=True, hi_lo=None, c_stride=None):
+def psv_build(ref, src, poses, baselines, depths, *, preprocess=True, want_f32=True, hi_lo=None, c_stride=None,
+              use_scratch=True):
     """msi_psv_build.  ref/src: [B,H,W,3] float32 or uint8 CUDA tensors; poses [B,2,4,4];
     baselines [B]; depths [P].  Returns the float32 PSV [B,H,W,6P] (or None); ``hi_lo`` is an
     optional (hi, lo) pair of fp16 [B,H,W,c_stride] tensors filled with the conv-operand copy."""
@@ -97,10 +98,18 @@ def psv_build(ref, src, poses, baselines, depths, *, preprocess=True, want_f32=T
     if hi_lo is not None:
         hi, lo = hi_lo
         cs = int(c_stride if c_stride is not None else hi.shape[-1])
+    scratch = psv_scratch(B, H, W, dev) if use_scratch else None
     check(lib.msi_psv_build(ptr(ref.contiguous()), ptr(src.contiguous()), dt, 1 if preprocess else 0,
                             ptr(poses), ptr(baselines), ptr(depths), *tb.ptrs(), B, H, W, P,
-                            ptr(out), ptr(hi), ptr(lo), cs, stream_ptr()), "msi_psv_build")
+                            ptr(out), ptr(hi), ptr(lo), cs, ptr(scratch), scratch.numel() if scratch is not None else 0,
+                            stream_ptr()), "msi_psv_build")
     return out
+
+
+def psv_scratch(B, H, W, device):
+    """16-byte aligned scratch for the two-eye form of msi_psv_build."""
+    n = int(_lib.load().msi_psv_scratch_bytes(B, H, W))
+    return torch.empty(n, dtype=torch.uint8, device=device)
 
 
 def sweep_coords(poses, baselines, depths, B, H, W, device):

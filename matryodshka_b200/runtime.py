@@ -174,6 +174,7 @@ class MSIPipeline:
         self.tgt_pos = torch.zeros((B, 3), device=dev)
         self.depths = torch.tensor(self.planes, dtype=torch.float32, device=dev)
         self.hi, self.lo = self.net.input_buffers(B)
+        self.psv_scratch = ops.psv_scratch(B, H, W, dev)
         self.pred = torch.empty((B, H, W, 2 * num_planes), dtype=torch.float32, device=dev)
         self.rgba = torch.empty((B, H, W, num_planes, 4), dtype=torch.float32, device=dev)
         self.out = {
@@ -201,7 +202,8 @@ class MSIPipeline:
         st = stream_ptr()
         check(lib.msi_psv_build(ptr(self.ref), ptr(self.src), dt, 1, ptr(self.poses), ptr(self.baselines),
                                 ptr(self.depths), *tb.ptrs(), B, H, W, P, None, ptr(self.hi), ptr(self.lo),
-                                self.net.in_c_stride, st), "msi_psv_build")
+                                self.net.in_c_stride, ptr(self.psv_scratch), self.psv_scratch.numel(), st),
+              "msi_psv_build")
         self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred)
         check(lib.msi_rgba_assemble(ptr(self.pred), None, ptr(self.hi), ptr(self.lo), self.net.in_c_stride,
                                     B, H, W, P, ptr(self.rgba), None, None, st), "msi_rgba_assemble")

@@ -220,3 +220,25 @@ def test_invalid_arguments_raise():
     with pytest.raises(MsiError):
         ops.render_composite(torch.zeros((1, 8, 8, 4, 4), device=DEV), np.eye(4)[None], np.zeros((1, 3)),
                              [1.0, 2.0, 3.0, 4.0], want_rgb=False, want_depth=False)
+
+
+@pytest.mark.parametrize("same_pose", [True, False])
+def test_psv_two_eye_form_is_bit_identical_to_single_kernel_form(same_pose):
+    """The RGBX + two-eyes-per-thread form (scratch given) must reproduce the one-thread-per-
+    (pixel, eye, plane) form bit for bit, with shared and with distinct eye poses."""
+    B, H, W, P = 2, 32, 64, 32
+    ref, src = synth.ods_pair(B, H, W)
+    d = msi_np.inv_depths(1, 100, P)
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (B, 2, 1))
+    if not same_pose:
+        poses[:, 1, 3] = 0.004
+        poses[1, 0, 7] = -0.002
+    hi_a = torch.empty((B, H, W, 6 * P), dtype=torch.float16, device=DEV)
+    lo_a, hi_b, lo_b = torch.empty_like(hi_a), torch.empty_like(hi_a), torch.empty_like(hi_a)
+    a = ops.psv_build(_t(ref), _t(src), poses, [0.032, 0.05], d, hi_lo=(hi_a, lo_a), use_scratch=True)
+    b = ops.psv_build(_t(ref), _t(src), poses, [0.032, 0.05], d, hi_lo=(hi_b, lo_b), use_scratch=False)
+    assert torch.equal(a, b) and torch.equal(hi_a, hi_b) and torch.equal(lo_a, lo_b)
+    # uint8 images through the pre-pass
+    r8, s8 = _t((ref * 255).astype(np.uint8)), _t((src * 255).astype(np.uint8))
+    assert torch.equal(ops.psv_build(r8, s8, poses, [0.032, 0.05], d, use_scratch=True),
+                       ops.psv_build(r8, s8, poses, [0.032, 0.05], d, use_scratch=False))
