@@ -49,8 +49,9 @@ struct TcParams {
     int stages;
     int BH, BW;          // output-pixel patch of one M tile, BH * BW = 128
     int tiles_x, tiles_y, n_tiles;
-    int tiles_per_sample;  // tiles_x * tiles_y * n_tiles * ncls
-    int total_tiles;
+    int m_tiles;           // B * tiles_y * tiles_x pixel tiles per column (set per forward)
+    int units_per_col;     // ceil(m_tiles / CL)
+    int total_units;       // ncls * n_tiles * units_per_col
     int Mh, Mw;          // output positions per class
     int in_stride;       // conv stride (TMA traversal stride)
     int out_stride;      // 1, or 2 for deconv classes
@@ -79,6 +80,7 @@ struct TcParams {
 struct TcPlan {
     TcParams p;
     int n_tile, split;
+    int cl;                   // cluster size along M: CTAs of a cluster multicast the W tile to each other
     CUtensorMap a_map[2][2];  // [source][hi/lo]
     CUtensorMap w_map[2];     // hi/lo
     int grid;
@@ -200,34 +202,69 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Work decomposition.  A "column" is one weight tile (output-parity class, N tile); its m_tiles =
+// B * tiles_y * tiles_x pixel tiles all multiply the same W.  A work unit is CL consecutive pixel
+// tiles of one column, handled by the CL CTAs of a cluster in lockstep so that they can share the W
+// tile (each CTA fetches 1/CL of it and multicasts it to the others).  When m_tiles is not a multiple
+// of CL the last unit's surplus CTAs recompute the last real tile with their stores masked off.
 struct TileCoord {
     int b, cls, n0, ox0, oy0;
+    bool dummy;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int n_tile) {
+__device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int unit, int rank, int cl, int n_tile) {
     TileCoord t;
-    int r = tile;
-    const int tx = r % p.tiles_x;
-    r /= p.tiles_x;
-    const int ty = r % p.tiles_y;
-    r /= p.tiles_y;
-    const int nt = r % p.n_tiles;
-    r /= p.n_tiles;
-    t.cls = r % p.ncls;
-    t.b = r / p.ncls;
-    t.n0 = nt * n_tile;
+    const int col = unit / p.units_per_col;
+    int m = (unit - col * p.units_per_col) * cl + rank;
+    t.dummy = m >= p.m_tiles;
+    if (t.dummy) m = p.m_tiles - 1;
+    const int per_frame = p.tiles_x * p.tiles_y;
+    t.b = m / per_frame;
+    const int r = m - t.b * per_frame;
+    const int ty = r / p.tiles_x;
+    const int tx = r - ty * p.tiles_x;
+    t.cls = col / p.n_tiles;
+    t.n0 = (col - t.cls * p.n_tiles) * n_tile;
     t.ox0 = tx * p.BW;
     t.oy0 = ty * p.BH;
     return t;
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a W slice into the same smem offset of every CTA in cta_mask; each destination CTA's
+// mbarrier (same offset) receives the complete_tx for the bytes written into its own shared memory.
+__device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                  int c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
-template <int N_TILE, int SPLIT>
+template <int N_TILE, int SPLIT, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_constant__ CUtensorMap a0_lo,
                           const __grid_constant__ CUtensorMap a1_hi, const __grid_constant__ CUtensorMap a1_lo,
                           const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
                           const __grid_constant__ TcParams p) {
+    // CL = cluster size along M (1 or 2).  The W tensor maps have box {64, N_TILE / CL}.
     constexpr int kWTileBytes = N_TILE * kBlockK * 2;
+    constexpr int kWSliceRows = N_TILE / CL;
+    constexpr int kWSliceBytes = kWSliceRows * kBlockK * 2;
+    constexpr uint16_t kCtaMask = (uint16_t)((1u << CL) - 1u);
+    const int cta_rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
+    const int cluster_id = blockIdx.x / CL;
+    const int n_clusters = gridDim.x / CL;
     constexpr int kStageBytes = (kATileBytes + kWTileBytes) * (SPLIT ? 2 : 1);
     constexpr int kAccCols = SPLIT ? 2 * N_TILE : N_TILE;  // TMEM columns of one accumulator
     constexpr int kTmemCols = 2 * kAccCols;                // double-buffered
@@ -263,7 +300,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     if (threadIdx.x == 64) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must have consumed the slot
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
@@ -286,6 +323,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_smem);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast targets them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -294,8 +332,8 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(p, tile, N_TILE);
+        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters) {
+            const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
             const int ntaps = s_ntaps[tc.cls];
             const int bx = tc.ox0 * p.in_stride, by = tc.oy0 * p.in_stride;
             for (int t = 0; t < ntaps; ++t) {
@@ -310,10 +348,17 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                         const bool second = ch >= p.chunks[0];
                         const int c0 = (second ? ch - p.chunks[0] : ch) * kBlockK;
                         tma_load_4d(sa, second ? &a1_hi : &a0_hi, &full_bar[stage], c0, cx, cy, tc.b);
-                        tma_load_3d(sa + kOffWHi, &w_hi, &full_bar[stage], kk, tc.n0, tc.cls);
-                        if (SPLIT) {
-                            tma_load_4d(sa + kOffALo, second ? &a1_lo : &a0_lo, &full_bar[stage], c0, cx, cy, tc.b);
-                            tma_load_3d(sa + kOffWLo, &w_lo, &full_bar[stage], kk, tc.n0, tc.cls);
+                        if (SPLIT) tma_load_4d(sa + kOffALo, second ? &a1_lo : &a0_lo, &full_bar[stage], c0, cx, cy, tc.b);
+                        if (CL == 1) {
+                            tma_load_3d(sa + kOffWHi, &w_hi, &full_bar[stage], kk, tc.n0, tc.cls);
+                            if (SPLIT) tma_load_3d(sa + kOffWLo, &w_lo, &full_bar[stage], kk, tc.n0, tc.cls);
+                        } else {
+                            // this CTA fetches rows [rank * N/CL, (rank+1) * N/CL) of the W tile for everyone
+                            const uint32_t so = (uint32_t)(cta_rank * kWSliceBytes);
+                            const int n_row = tc.n0 + cta_rank * kWSliceRows;
+                            tma_load_3d_mcast(sa + kOffWHi + so, &w_hi, &full_bar[stage], kk, n_row, tc.cls, kCtaMask);
+                            if (SPLIT)
+                                tma_load_3d_mcast(sa + kOffWLo + so, &w_lo, &full_bar[stage], kk, n_row, tc.cls, kCtaMask);
                         }
                     }
                     __syncwarp();
@@ -332,8 +377,8 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-            const int cls = (tile / (p.tiles_x * p.tiles_y * p.n_tiles)) % p.ncls;
+        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
+            const int cls = (unit / p.units_per_col) / p.n_tiles;
             const int n_iters = s_ntaps[cls] * chunks_total;
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
@@ -356,7 +401,12 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                         // A_lo x W_hi -> accumulates into columns [0, N)
                         if (SPLIT) umma_f16(d_tmem, da_lo + adv, dw_hi + adv, idesc_n, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    // free the smem slot when these MMAs retire -- in every CTA of the cluster, because
+                    // the peers' next multicast W slices land in this CTA's slot too
+                    if (CL == 1)
+                        umma_commit(&empty_bar[stage]);
+                    else
+                        umma_commit_mcast(&empty_bar[stage], kCtaMask);
                     if (it == n_iters - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
                 }
                 __syncwarp();
@@ -377,20 +427,24 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         float s_sum = 0.f, s_sq = 0.f;
         int cur_b = -1;
         int local = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-            const TileCoord tc = decode_tile(p, tile, N_TILE);
+        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
+            const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
             if (p.do_stats && tc.b != cur_b) {
                 if (cur_b >= 0) {
+                    // this (frame, CTA, warp) slot belongs to this warp alone: plain read-modify-write
                     const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
-                    if (lane == 0)
-                        p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew] = make_double2(ds, dq);
+                    if (lane == 0) {
+                        double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
+                        const double2 old = *slot;
+                        *slot = make_double2(old.x + ds, old.y + dq);
+                    }
                     s_sum = 0.f;
                     s_sq = 0.f;
                 }
                 cur_b = tc.b;
             }
             const int my = tc.oy0 + ly, mx = tc.ox0 + lx;  // output position inside the class grid
-            const bool valid = (my < p.Mh) && (mx < p.Mw);
+            const bool valid = (my < p.Mh) && (mx < p.Mw) && !tc.dummy;
             int oy = my, ox = mx;
             if (p.out_stride == 2) {
                 oy = my * 2 + (tc.cls >> 1);
@@ -463,8 +517,11 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         if (p.do_stats) {
             if (cur_b >= 0) {
                 const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
-                if (lane == 0)
-                    p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew] = make_double2(ds, dq);
+                if (lane == 0) {
+                    double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
+                    const double2 old = *slot;
+                    *slot = make_double2(old.x + ds, old.y + dq);
+                }
             }
             // last CTA to finish turns the partials into (mean, rstd) per frame
             __threadfence();
@@ -508,6 +565,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its smem / barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -644,22 +702,46 @@ int num_sms() {
     return n;
 }
 
-template <int N_TILE, int SPLIT>
+template <int N_TILE, int SPLIT, int CL>
 int launch_tc(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
     static bool attr_set = false;
+    auto kern = conv_igemm_tcgen05_kernel<N_TILE, SPLIT, CL>;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_tcgen05_kernel<N_TILE, SPLIT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_igemm_tcgen05_kernel<%d,%d>, %d) failed: %s", N_TILE, SPLIT, kMaxDynSmem,
-                      cudaGetErrorString(e));
+            set_error("cudaFuncSetAttribute(conv_igemm_tcgen05_kernel<%d,%d,%d>, %d) failed: %s", N_TILE, SPLIT, CL,
+                      kMaxDynSmem, cudaGetErrorString(e));
             return MSI_ERR_CUDA;
         }
         attr_set = true;
     }
-    conv_igemm_tcgen05_kernel<N_TILE, SPLIT><<<plan->grid, kThreads, plan->smem_bytes, st>>>(
-        plan->a_map[0][0], plan->a_map[0][1], plan->a_map[1][0], plan->a_map[1][1], plan->w_map[0], plan->w_map[1], p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->a_map[0][0], plan->a_map[0][1], plan->a_map[1][0],
+                                       plan->a_map[1][1], plan->w_map[0], plan->w_map[1], p);
+    if (e != cudaSuccess) {
+        set_error("cudaLaunchKernelEx(conv_igemm_tcgen05_kernel<%d,%d,%d>, grid %d) failed: %s", N_TILE, SPLIT, CL,
+                  plan->grid, cudaGetErrorString(e));
+        return MSI_ERR_CUDA;
+    }
     return MSI_OK;
+}
+
+template <int N_TILE>
+int launch_tc_nt(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+    if (plan->cl == 2)
+        return plan->split ? launch_tc<N_TILE, 1, 2>(plan, p, st) : launch_tc<N_TILE, 0, 2>(plan, p, st);
+    return plan->split ? launch_tc<N_TILE, 1, 1>(plan, p, st) : launch_tc<N_TILE, 0, 1>(plan, p, st);
 }
 
 }  // namespace
@@ -709,7 +791,15 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
     p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
     p.n_tiles = L.cout / plan->n_tile;
-    p.tiles_per_sample = p.tiles_x * p.tiles_y * p.n_tiles * p.ncls;
+    // Optional: pair CTAs along M so that each fetches half of the W tile and multicasts it to its
+    // peer (MSI_CONV_CLUSTER=2).  Measured on B200 (profiles/): no gain -- 1.100 ms vs 1.087 ms per
+    // frame -- because the kernel is bound by bytes delivered INTO each SM, which multicast does not
+    // reduce; so the default stays 1.
+    {
+        const char* env = getenv("MSI_CONV_CLUSTER");
+        const int want = env ? atoi(env) : 1;
+        plan->cl = (want >= 2 && p.tiles_x * p.tiles_y >= 2) ? 2 : 1;
+    }
     p.Hout = L.Hout;
     p.Wout = L.Wout;
     p.cout = L.cout;
@@ -749,8 +839,8 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
         plan->a_map[1][0] = plan->a_map[0][0];
         plan->a_map[1][1] = plan->a_map[0][1];
     }
-    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[0], L.w_hi, L.K, L.cout, L.ncls, plan->n_tile);
-    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[1], L.w_lo, L.K, L.cout, L.ncls, plan->n_tile);
+    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[0], L.w_hi, L.K, L.cout, L.ncls, plan->n_tile / plan->cl);
+    if (rc == MSI_OK) rc = encode_w_map(&plan->w_map[1], L.w_lo, L.K, L.cout, L.ncls, plan->n_tile / plan->cl);
     if (rc != MSI_OK) {
         delete plan;
         return rc;
@@ -804,20 +894,21 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
     TcParams p = plan->p;
     p.out = out;
     p.B = B;
-    p.total_tiles = p.tiles_per_sample * B;
-    int grid = num_sms();
-    if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
-    if (grid > p.total_tiles) grid = p.total_tiles;
+    const int cl = plan->cl;
+    p.m_tiles = B * p.tiles_x * p.tiles_y;
+    p.units_per_col = (p.m_tiles + cl - 1) / cl;
+    p.total_units = p.ncls * p.n_tiles * p.units_per_col;
+    int clusters = num_sms();
+    if (clusters > kMaxPersistentCtas) clusters = kMaxPersistentCtas;
+    clusters /= cl;
+    if (clusters > p.total_units) clusters = p.total_units;
+    const int grid = clusters * cl;
     plan->grid = grid;
     if (p.do_stats && grid * kEpiWarps > p.n_partials) {
         set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * kEpiWarps);
         return MSI_ERR_STATE;
     }
-    int rc;
-    if (plan->n_tile == 64)
-        rc = plan->split ? launch_tc<64, 1>(plan, p, st) : launch_tc<64, 0>(plan, p, st);
-    else
-        rc = plan->split ? launch_tc<128, 1>(plan, p, st) : launch_tc<128, 0>(plan, p, st);
+    const int rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, st) : launch_tc_nt<128>(plan, p, st);
     if (rc != MSI_OK) return rc;
     MSI_LAUNCH_CHECK();
     return MSI_OK;

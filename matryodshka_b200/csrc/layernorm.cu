@@ -81,32 +81,51 @@ ln_finalize_kernel(const double2* __restrict__ partials, int n_partials, long lo
     }
 }
 
-// thread = 8 consecutive channels of one pixel
+// thread = kLnUnroll x 8 consecutive channels; the raw tensor is read once (streaming load)
+static constexpr int kLnUnroll = 2;
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
                 __half* __restrict__ out_lo) {
     const int b = blockIdx.y;
-    const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
-    if (i >= n_per_sample) return;
     const float2 st = stats[b];
-    const int c0 = (int)(i % C);
-    const size_t off = (size_t)b * n_per_sample + i;
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(raw + off));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(raw + off + 4));
-    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
+    // kLnUnroll groups of 8 elements per thread, all loads issued before the first use
+    long long idx[kLnUnroll];
+    float4 v0[kLnUnroll], v1[kLnUnroll];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float inv = st.y * __ldg(gamma + c0 + q);
-        const float sh = __ldg(beta + c0 + q) - st.x * inv;
-        float y = x[q] * inv + sh;
-        y = fmaxf(y, 0.f);
-        split_half(y * MSI_ACT_SCALE, hi[q], lo[q]);
+    for (int g = 0; g < kLnUnroll; ++g) {
+        idx[g] = (((long long)blockIdx.x * kLnUnroll + g) * 256 + threadIdx.x) * 8;
+        if (idx[g] < n_per_sample) {
+            const size_t off = (size_t)b * n_per_sample + idx[g];
+            v0[g] = __ldcs(reinterpret_cast<const float4*>(raw + off));
+            v1[g] = __ldcs(reinterpret_cast<const float4*>(raw + off + 4));
+        }
     }
-    *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+    for (int g = 0; g < kLnUnroll; ++g) {
+        if (idx[g] >= n_per_sample) continue;
+        const int c0 = (int)(idx[g] % C);
+        const size_t off = (size_t)b * n_per_sample + idx[g];
+        const float x[8] = {v0[g].x, v0[g].y, v0[g].z, v0[g].w, v1[g].x, v1[g].y, v1[g].z, v1[g].w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float inv = st.y * gm[q];
+            const float sh = bt[q] - st.x * inv;
+            float y = x[q] * inv + sh;
+            y = fmaxf(y, 0.f);
+            split_half(y * MSI_ACT_SCALE, hi[q], lo[q]);
+        }
+        *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+    }
 }
 
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
@@ -122,7 +141,7 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
         ln_finalize_kernel<<<B, 256, 0, st>>>(partials, np, n_per_sample, stats);
         MSI_LAUNCH_CHECK();
     }
-    ln_apply_kernel<<<dim3(ceil_div(n_per_sample, 256 * 8), B), 256, 0, st>>>(raw, n_per_sample, C, stats, gamma,
+    ln_apply_kernel<<<dim3(ceil_div(n_per_sample, 256 * 8 * kLnUnroll), B), 256, 0, st>>>(raw, n_per_sample, C, stats, gamma,
                                                                             beta, out_hi, out_lo);
     MSI_LAUNCH_CHECK();
     return MSI_OK;

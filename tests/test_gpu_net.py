@@ -155,3 +155,53 @@ def test_multi_gpu_gather_equals_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
                         os.path.join(root, "tests", "_nccl_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _pipeline_vs_oracle(H, W, P, B, frames_to_check, ngf=64):
+    ref, src = synth.ods_pair(B, H, W)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    tp = synth.target_positions(B)
+    pipe = MSIPipeline(wts, H, W, P, ngf, batch=B, device=DEV)
+    pipe.set_inputs(ref, src, tgt_pos=tp)
+    pipe.step()
+    torch.cuda.synchronize()
+    planes = msi_np.inv_depths(1, 100, P)
+    eye = np.eye(4, dtype=F32)[None]
+    for b in frames_to_check:
+        out, _ = msi_np.infer_msi(src[b:b + 1], ref[b:b + 1], synth.identity_poses(1), synth.identity_poses(1),
+                                  synth.intrinsics(1), P, planes, wts, ngf=ngf)
+        want = msi_np.msi_render_equirect_view(out["rgba_layers"], eye, tp[b:b + 1], planes)
+        wdep = msi_np.msi_render_equirect_depth(out["rgba_layers"], eye, tp[b:b + 1], planes)
+        e_rgba = np.abs(pipe.rgba[b:b + 1].cpu().numpy() - out["rgba_layers"]).max()
+        e_rgb = np.abs(pipe.out["rgb"][b:b + 1].cpu().numpy() - want).max()
+        e_dep = np.abs(pipe.out["depth"][b:b + 1].cpu().numpy() - wdep).max()
+        assert e_rgba < TOL and e_rgb < TOL and e_dep < TOL, (b, e_rgba, e_rgb, e_dep)
+    return pipe
+
+
+def test_config3_64_spheres_batch8():
+    """BASELINE configs[2]: 640x320 ERP, 64-sphere MSI, batch 8 on one GPU (deep-layer composite
+    stress): first and last frame against the oracle, all frames finite and distinct."""
+    pipe = _pipeline_vs_oracle(320, 640, 64, 8, frames_to_check=(0, 7))
+    rgb = pipe.out["rgb"]
+    assert torch.isfinite(rgb).all()
+    assert not torch.equal(rgb[0], rgb[1])
+
+
+def test_config4_high_res_1280x640():
+    """BASELINE configs[3] shape: 1280x640 ERP, 32 spheres (one of the 4 frames a rank owns)."""
+    _pipeline_vs_oracle(640, 1280, 32, 2, frames_to_check=(1,))
+
+
+def test_tcgen05_cluster_multicast_path(monkeypatch):
+    """MSI_CONV_CLUSTER=2: CTA pairs multicast the W tile; odd tile counts exercise the masked
+    surplus CTA.  Must equal the un-clustered kernel bit for bit (same MMAs, same order)."""
+    H, W, P, ngf, B = 24, 72, 32, 64, 3
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    monkeypatch.setenv("MSI_CONV_CLUSTER", "1")
+    a = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B).forward(_t(x))
+    monkeypatch.setenv("MSI_CONV_CLUSTER", "2")
+    b = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B).forward(_t(x))
+    assert torch.equal(a, b)
