@@ -99,28 +99,28 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a lost TMA transaction must fault the kernel, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
@@ -130,17 +130,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -166,8 +166,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -234,19 +234,19 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // TMA load of a W slice into the same smem offset of every CTA in cta_mask; each destination CTA's
 // mbarrier (same offset) receives the complete_tx for the bytes written into its own shared memory.
-__device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+__device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                   int c2, uint16_t cta_mask) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
         "[%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
         : "memory");
 }
 // tcgen05.commit arriving on the mbarrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
     asm volatile(
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        ::"r"(bar), "h"(cta_mask)
         : "memory");
 }
 
@@ -297,14 +297,21 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         s_dy[c][t] = p.taps[c].dy[t];
         if (t == 0) s_ntaps[c] = p.taps[c].n;
     }
+    // 32-bit shared addresses of the barriers, computed ONCE: converting a __shared__ pointer inside the
+    // issue loops costs an S2UR + address rebuild per use, and those loops are latency-critical
+    // (measured: the barrier ping-pong alone was ~500 cycles per K iteration before this).
+    const uint32_t full0 = smem_u32(&full_bar[0]);
+    const uint32_t empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]);
+    const uint32_t tempty0 = smem_u32(&tmem_empty_bar[0]);
     if (threadIdx.x == 64) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must have consumed the slot
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, CL);  // every CTA of the cluster must have consumed the slot
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(tfull0 + 8u * a, 1);
+            mbar_init(tempty0 + 8u * a, kEpiWarps);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -330,41 +337,49 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     if (warp == 0) {
         // =============================== TMA producer ===============================
         const bool leader = elect_one();
+        // loop state lives in registers; nothing in the inner loop re-reads kernel parameters
+        const int chunks0 = p.chunks[0], cs_total = p.cs_total, in_stride = p.in_stride;
+        const int total_units = p.total_units;
         int stage = 0;
         uint32_t phase = 0;
-        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters) {
+        uint32_t sa = smem_base, full_a = full0, empty_a = empty0;
+        for (int unit = cluster_id; unit < total_units; unit += n_clusters) {
             const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
             const int ntaps = s_ntaps[tc.cls];
-            const int bx = tc.ox0 * p.in_stride, by = tc.oy0 * p.in_stride;
+            const int bx = tc.ox0 * in_stride, by = tc.oy0 * in_stride;
+            // W slice this CTA fetches: all N rows (CL == 1) or rows [rank * N/CL, (rank+1) * N/CL)
+            const uint32_t so = (CL == 1) ? 0u : (uint32_t)(cta_rank * kWSliceBytes);
+            const int n_row = tc.n0 + ((CL == 1) ? 0 : cta_rank * kWSliceRows);
             for (int t = 0; t < ntaps; ++t) {
                 const int cx = bx + s_dx[tc.cls][t];
                 const int cy = by + s_dy[tc.cls][t];
-                int kk = t * p.cs_total;
+                int kk = t * cs_total;
                 for (int ch = 0; ch < chunks_total; ++ch, kk += kBlockK) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_wait(empty_a, phase ^ 1u);
                     if (leader) {
-                        const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
-                        mbar_expect_tx(&full_bar[stage], kTxBytes);
-                        const bool second = ch >= p.chunks[0];
-                        const int c0 = (second ? ch - p.chunks[0] : ch) * kBlockK;
-                        tma_load_4d(sa, second ? &a1_hi : &a0_hi, &full_bar[stage], c0, cx, cy, tc.b);
-                        if (SPLIT) tma_load_4d(sa + kOffALo, second ? &a1_lo : &a0_lo, &full_bar[stage], c0, cx, cy, tc.b);
+                        mbar_expect_tx(full_a, kTxBytes);
+                        const bool second = ch >= chunks0;
+                        const int c0 = (second ? ch - chunks0 : ch) * kBlockK;
+                        tma_load_4d(sa, second ? &a1_hi : &a0_hi, full_a, c0, cx, cy, tc.b);
+                        if (SPLIT) tma_load_4d(sa + kOffALo, second ? &a1_lo : &a0_lo, full_a, c0, cx, cy, tc.b);
                         if (CL == 1) {
-                            tma_load_3d(sa + kOffWHi, &w_hi, &full_bar[stage], kk, tc.n0, tc.cls);
-                            if (SPLIT) tma_load_3d(sa + kOffWLo, &w_lo, &full_bar[stage], kk, tc.n0, tc.cls);
+                            tma_load_3d(sa + kOffWHi, &w_hi, full_a, kk, n_row, tc.cls);
+                            if (SPLIT) tma_load_3d(sa + kOffWLo, &w_lo, full_a, kk, n_row, tc.cls);
                         } else {
-                            // this CTA fetches rows [rank * N/CL, (rank+1) * N/CL) of the W tile for everyone
-                            const uint32_t so = (uint32_t)(cta_rank * kWSliceBytes);
-                            const int n_row = tc.n0 + cta_rank * kWSliceRows;
-                            tma_load_3d_mcast(sa + kOffWHi + so, &w_hi, &full_bar[stage], kk, n_row, tc.cls, kCtaMask);
-                            if (SPLIT)
-                                tma_load_3d_mcast(sa + kOffWLo + so, &w_lo, &full_bar[stage], kk, n_row, tc.cls, kCtaMask);
+                            tma_load_3d_mcast(sa + kOffWHi + so, &w_hi, full_a, kk, n_row, tc.cls, kCtaMask);
+                            if (SPLIT) tma_load_3d_mcast(sa + kOffWLo + so, &w_lo, full_a, kk, n_row, tc.cls, kCtaMask);
                         }
                     }
                     __syncwarp();
+                    sa += kStageBytes;
+                    full_a += 8;
+                    empty_a += 8;
                     if (++stage == stages) {
                         stage = 0;
                         phase ^= 1u;
+                        sa = smem_base;
+                        full_a = full0;
+                        empty_a = empty0;
                     }
                 }
             }
@@ -374,45 +389,57 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         const bool leader = elect_one();
         constexpr uint32_t idesc_wide = make_idesc(SPLIT ? 2 * N_TILE : N_TILE);
         constexpr uint32_t idesc_n = make_idesc(N_TILE);
+        const int total_units = p.total_units, units_per_col = p.units_per_col, n_tiles = p.n_tiles;
         int stage = 0;
         uint32_t phase = 0;
+        // descriptor of the current stage's A_hi tile, advanced incrementally (the address field is
+        // (smem address >> 4); every stage base is 1024-byte aligned and below 256 KB)
+        const uint64_t desc0 = make_desc(smem_base);
+        constexpr uint64_t kDescStage = (uint64_t)(kStageBytes >> 4);
+        constexpr uint64_t kDescWHi = (uint64_t)(kOffWHi >> 4);
+        constexpr uint64_t kDescALo = (uint64_t)(kOffALo >> 4);
+        uint64_t da = desc0;
+        uint32_t full_a = full0, empty_a = empty0;
         int local = 0;
-        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
-            const int cls = (unit / p.units_per_col) / p.n_tiles;
+        for (int unit = cluster_id; unit < total_units; unit += n_clusters, ++local) {
+            const int cls = (unit / units_per_col) / n_tiles;
             const int n_iters = s_ntaps[cls] * chunks_total;
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
-            mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+            mbar_wait(tempty0 + 8u * acc, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+            const uint32_t tfull_a = tfull0 + 8u * acc;
             for (int it = 0; it < n_iters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(full_a, phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
-                    const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
-                    const uint64_t da_hi = make_desc(sa);
-                    const uint64_t dw_hi = make_desc(sa + kOffWHi);
-                    const uint64_t da_lo = make_desc(sa + kOffALo);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes per K step inside the swizzle row (>> 4)
                         // A_hi x [W_hi | W_lo] -> columns [0, 2N)   (fp16 mode: A x W -> [0, N))
-                        umma_f16(d_tmem, da_hi + adv, dw_hi + adv, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(d_tmem, da + adv, da + kDescWHi + adv, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);
                         // A_lo x W_hi -> accumulates into columns [0, N)
-                        if (SPLIT) umma_f16(d_tmem, da_lo + adv, dw_hi + adv, idesc_n, 1u);
+                        if (SPLIT) umma_f16(d_tmem, da + kDescALo + adv, da + kDescWHi + adv, idesc_n, 1u);
                     }
                     // free the smem slot when these MMAs retire -- in every CTA of the cluster, because
                     // the peers' next multicast W slices land in this CTA's slot too
                     if (CL == 1)
-                        umma_commit(&empty_bar[stage]);
+                        umma_commit(empty_a);
                     else
-                        umma_commit_mcast(&empty_bar[stage], kCtaMask);
-                    if (it == n_iters - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+                        umma_commit_mcast(empty_a, kCtaMask);
+                    if (it == n_iters - 1) umma_commit(tfull_a);  // accumulator complete
                 }
                 __syncwarp();
+                da += kDescStage;
+                full_a += 8;
+                empty_a += 8;
                 if (++stage == stages) {
                     stage = 0;
                     phase ^= 1u;
+                    da = desc0;
+                    full_a = full0;
+                    empty_a = empty0;
                 }
             }
         }
@@ -462,7 +489,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
             }
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
-            mbar_wait(&tmem_full_bar[acc], use & 1u);
+            mbar_wait(tfull0 + 8u * acc, use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
 #pragma unroll 1
@@ -476,7 +503,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
                 }
                 if (valid) {
 #pragma unroll

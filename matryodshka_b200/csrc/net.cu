@@ -352,13 +352,19 @@ extern "C" int msi_net_forward(msi_net* net, const float* in_f32, const void* in
     return net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, nullptr);
 }
 
-// Same forward with CUDA events recorded on `stream` around every conv launch and every LayerNorm
-// group; synchronises the stream and returns per-layer milliseconds (host arrays of
-// msi_net_num_layers() floats; ln_ms of the head is 0).  Not capturable into a graph.
+// Measurement forward: every layer runs once (the real forward), then its conv kernel and its
+// LayerNorm kernel are each re-launched kProfReps times back to back between two CUDA events on
+// `stream`.  Timing the warm repeats keeps CPU launch latency (which exceeds the duration of the
+// small layers' kernels when they are launched one by one) out of the kernel durations.  The
+// repeats rewrite identical outputs; the tcgen05 kernel's completion counter is past the grid size
+// on a repeat, so it does not re-finalise the LayerNorm statistics.  Synchronises the stream and
+// returns per-layer milliseconds per launch (host arrays of msi_net_num_layers() floats; ln_ms of the
+// head is 0).  Not capturable into a graph.
+static const int kProfReps = 4;
 extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
                                         int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host) {
     MSI_CHECK_ARG(conv_ms_host && ln_ms_host, "net_forward_profiled: null output");
-    std::vector<cudaEvent_t> ev(3 * kNumLayers);
+    std::vector<cudaEvent_t> ev(4 * kNumLayers);
     for (auto& e : ev) MSI_CUDA(cudaEventCreate(&e));
     int rc = net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, ev.data());
     if (rc == MSI_OK) {
@@ -370,9 +376,14 @@ extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const
     }
     if (rc == MSI_OK) {
         for (int i = 0; i < kNumLayers; ++i) {
-            cudaEventElapsedTime(&conv_ms_host[i], ev[3 * i], ev[3 * i + 1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[4 * i], ev[4 * i + 1]);
+            conv_ms_host[i] = ms / kProfReps;
             ln_ms_host[i] = 0.f;
-            if (net->layers[i].kind != kHead) cudaEventElapsedTime(&ln_ms_host[i], ev[3 * i + 1], ev[3 * i + 2]);
+            if (net->layers[i].kind != kHead) {
+                cudaEventElapsedTime(&ms, ev[4 * i + 2], ev[4 * i + 3]);
+                ln_ms_host[i] = ms / kProfReps;
+            }
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
@@ -426,19 +437,25 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
         ActBuf srcs[2];
         for (int s = 0; s < L.nsrc; ++s) srcs[s] = net->acts[L.src[s]];
         float* out = (L.kind == kHead) ? pred : L.raw;
-        if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i], st));
-        if (net->conv_impl == MSI_CONV_SIMT)
-            rc = conv_simt_forward(L, srcs, B, out, st);
-        else
-            rc = conv_tc_forward(L, B, out, st);
-        if (rc != MSI_OK) return rc;
-        if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i + 1], st));
+        const int conv_runs = ev ? 1 + kProfReps : 1;
+        for (int r = 0; r < conv_runs; ++r) {
+            if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i], st));
+            if (net->conv_impl == MSI_CONV_SIMT)
+                rc = conv_simt_forward(L, srcs, B, out, st);
+            else
+                rc = conv_tc_forward(L, B, out, st);
+            if (rc != MSI_OK) return rc;
+        }
+        if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 1], st));
         if (L.kind != kHead) {
             const long long n_per = (long long)L.Hout * L.Wout * L.cout;
-            rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                            net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, st);
-            if (rc != MSI_OK) return rc;
-            if (ev) MSI_CUDA(cudaEventRecord(ev[3 * i + 2], st));
+            for (int r = 0; r < conv_runs; ++r) {
+                if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i + 2], st));
+                rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
+                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, st);
+                if (rc != MSI_OK) return rc;
+            }
+            if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 3], st));
         }
     }
     return MSI_OK;
