@@ -249,18 +249,26 @@ def run_ours(args):
     dev_ms = e0.elapsed_time(e1)
 
     # ---- end-to-end region: host (pinned) images in, host uint8 view + depth out ----------------
-    h_ref, h_src = torch.from_numpy(ref), torch.from_numpy(src)
-    gathered = None
-    for _ in range(2):
-        pipe.step_e2e(h_ref, h_src)
+    # Every step copies its inputs host -> device from pinned memory and its results (uint8 view +
+    # depth) device -> host; the public streaming API (submit / collect) keeps two batches in flight so
+    # that those copies overlap the neighbouring batches' compute.  Wall clock, all K steps collected.
+    h_ref, h_src = torch.from_numpy(ref).pin_memory(), torch.from_numpy(src).pin_memory()
+    gather = (lambda: all_gather_frames(pipe.out["rgb_u8"], world)) if world > 1 else None
+
+    def e2e_loop(n):
+        for i in range(n):
+            pipe.submit(h_ref, h_src, after_compute=gather)
+            if i >= 1:
+                pipe.collect()
+        return pipe.collect()
+
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        pipe.step_e2e(h_ref, h_src)
-        if world > 1:
-            gathered = all_gather_frames(pipe.out["rgb_u8"], world)
+    last = e2e_loop(K)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    assert torch.equal(last[0], pipe.out["rgb_u8"].cpu()), "e2e result differs from the device-resident result"
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) ---------------
     scopes, conv_ms, ln_ms, flops = profile_net_layers(pipe.net, (pipe.hi, pipe.lo), pipe.pred, reps=max(3, min(K, 10)))
@@ -316,7 +324,8 @@ def run_ours(args):
                        "l2": f"per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "ms_per_step": e2e_ms / K,
-                    "input": "float32 host images (pinned) -> uint8 view + depth on host"},
+                    "input": "float32 host images (pinned) -> uint8 view + depth on host; MSIPipeline.submit/collect, "
+                             "2 batches in flight (H2D / compute / D2H on three streams)"},
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,
             "roofline": roofline,

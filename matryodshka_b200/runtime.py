@@ -254,6 +254,79 @@ class MSIPipeline:
         torch.cuda.current_stream().synchronize()
         return self.h_rgb_u8, self.h_depth_u8
 
+    # -- pipelined end-to-end: copies of neighbouring frames overlap with compute ---------------
+    def _init_streaming(self, depth=2):
+        dev = self.device
+        B, H, W = self.B, self.H, self.W
+        dt = self.ref.dtype
+        self._depth = depth
+        self._copy_s = torch.cuda.Stream(device=dev)
+        self._d2h_s = torch.cuda.Stream(device=dev)
+        self._in_stage = [(torch.empty((B, H, W, 3), dtype=dt, device=dev), torch.empty((B, H, W, 3), dtype=dt, device=dev))
+                          for _ in range(depth)]
+        self._out_stage = [(torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
+                            torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)) for _ in range(depth)]
+        self._h_out = [(torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
+                        torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()) for _ in range(depth)]
+        mk = lambda: [torch.cuda.Event() for _ in range(depth)]
+        self._ev_h2d, self._ev_in_free, self._ev_done, self._ev_d2h = mk(), mk(), mk(), mk()
+        self._submitted = 0
+        self._collected = 0
+
+    def submit(self, ref_host, src_host, after_compute=None):
+        """Enqueue one batch: H2D on a copy stream, the hot path on the current stream, D2H of the
+        uint8 view + depth on a third stream.  ``ref_host`` / ``src_host`` should be pinned (they are
+        staged through pinned memory otherwise).  Up to ``depth`` batches are in flight; call
+        ``collect()`` for every submit, in order.  ``after_compute`` (optional callable) runs on the
+        compute stream right after the path -- the multi-GPU all-gather hooks in there."""
+        if not hasattr(self, "_depth"):
+            self._init_streaming()
+        if self._submitted - self._collected >= self._depth:
+            raise _lib.MsiError("submit(): pipeline full, call collect() first")
+        k = self._submitted % self._depth
+        cur = torch.cuda.current_stream(self.device)
+        ref_host, src_host = torch.as_tensor(ref_host), torch.as_tensor(src_host)
+        if not ref_host.is_pinned():
+            self.h_ref.copy_(ref_host)
+            ref_host = self.h_ref
+        if not src_host.is_pinned():
+            self.h_src.copy_(src_host)
+            src_host = self.h_src
+        in_ref, in_src = self._in_stage[k]
+        with torch.cuda.stream(self._copy_s):
+            self._copy_s.wait_event(self._ev_in_free[k])      # compute has consumed this staging slot
+            in_ref.copy_(ref_host, non_blocking=True)
+            in_src.copy_(src_host, non_blocking=True)
+            self._ev_h2d[k].record(self._copy_s)
+        cur.wait_event(self._ev_h2d[k])
+        self.ref.copy_(in_ref, non_blocking=True)
+        self.src.copy_(in_src, non_blocking=True)
+        self._ev_in_free[k].record(cur)
+        self.step()
+        if after_compute is not None:
+            after_compute()
+        cur.wait_event(self._ev_d2h[k])                        # the previous D2H out of this slot is done
+        o_rgb, o_dep = self._out_stage[k]
+        o_rgb.copy_(self.out["rgb_u8"], non_blocking=True)
+        o_dep.copy_(self.out["depth_u8"], non_blocking=True)
+        self._ev_done[k].record(cur)
+        with torch.cuda.stream(self._d2h_s):
+            self._d2h_s.wait_event(self._ev_done[k])
+            self._h_out[k][0].copy_(o_rgb, non_blocking=True)
+            self._h_out[k][1].copy_(o_dep, non_blocking=True)
+            self._ev_d2h[k].record(self._d2h_s)
+        self._submitted += 1
+
+    def collect(self):
+        """Wait for the oldest in-flight batch; returns its (rgb_u8, depth_u8) pinned host tensors
+        (valid until ``depth`` more batches have been submitted)."""
+        if self._collected >= self._submitted:
+            raise _lib.MsiError("collect(): nothing in flight")
+        k = self._collected % self._depth
+        self._ev_d2h[k].synchronize()
+        self._collected += 1
+        return self._h_out[k]
+
     @property
     def h2d_bytes_per_step(self):
         return self.h_ref.numel() * self.h_ref.element_size() * 2

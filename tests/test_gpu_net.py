@@ -205,3 +205,32 @@ def test_tcgen05_cluster_multicast_path(monkeypatch):
     monkeypatch.setenv("MSI_CONV_CLUSTER", "2")
     b = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B).forward(_t(x))
     assert torch.equal(a, b)
+
+
+def test_streaming_submit_collect_matches_step():
+    """MSIPipeline.submit / collect (H2D, compute, D2H on three streams, two batches in flight)
+    returns, in order, exactly what the synchronous device-resident step computes."""
+    H, W, P, ngf = 32, 64, 32, 64
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    pipe = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV)
+    frames = [synth.ods_pair(1, H, W, seed=100 + i) for i in range(5)]
+    want = []
+    for ref, src in frames:
+        pipe.set_inputs(ref, src)
+        pipe.step()
+        torch.cuda.synchronize()
+        want.append((pipe.out["rgb_u8"].cpu().clone(), pipe.out["depth_u8"].cpu().clone()))
+    got = []
+    for i, (ref, src) in enumerate(frames):
+        pipe.submit(torch.from_numpy(ref).pin_memory(), torch.from_numpy(src))  # pinned and pageable inputs
+        if i >= 1:
+            r = pipe.collect()
+            got.append((r[0].clone(), r[1].clone()))
+    r = pipe.collect()
+    got.append((r[0].clone(), r[1].clone()))
+    assert len(got) == 5
+    for (a, b), (c, d) in zip(want, got):
+        assert torch.equal(a, c) and torch.equal(b, d)
+    from matryodshka_b200._lib import MsiError
+    with pytest.raises(MsiError):
+        pipe.collect()
