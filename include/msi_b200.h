@@ -146,6 +146,25 @@ int msi_project_layers(const float* rgba, const float* tgt_pose_rt, const float*
                        const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
                        int B, int H, int W, int L, float* out, void* stream);
 
+/* Point-wise forms of geometry/spherical.py + projector.apply_pose (stage-level API).
+ *   MSI_OP_BACKPROJECT_SPHERICAL (spherical.py:116-129): a = S, b = T [n], c = depths [planes]
+ *        -> o0, o1, o2 = x, y, z [planes, n]
+ *   MSI_OP_APPLY_POSE (projector.py:275-291): a, b, c = x, y, z [planes, n]; pose [16] or [planes,16]
+ *        -> o0, o1, o2
+ *   MSI_OP_PROJECT_ODS (spherical.py:170-233): a, b, c = x, y, z [n]; order = +1 / -1; baseline
+ *        -> o0 = uv [n, 2], valid [n] (optional)
+ *   MSI_OP_PROJECT_SPHERICAL (spherical.py:235-246): a, b, c = x, y, z [n] -> o0 = uv [n, 2]
+ *   MSI_OP_THETA_PHI_TO_PIXELS (spherical.py:54-68): a = theta, b = phi [n] -> o0 = uv [n, 2]
+ * H, W = ERP size used by the pixel mappings. */
+#define MSI_OP_BACKPROJECT_SPHERICAL 0
+#define MSI_OP_APPLY_POSE 1
+#define MSI_OP_PROJECT_ODS 2
+#define MSI_OP_PROJECT_SPHERICAL 3
+#define MSI_OP_THETA_PHI_TO_PIXELS 4
+int msi_point_op(int op, const float* a, const float* b, const float* c, long long n, int planes,
+                 const float* pose, int pose_per_plane, float order, float baseline, int H, int W,
+                 float* o0, float* o1, float* o2, uint8_t* valid, void* stream);
+
 /* sampling.resample (sampling.py:135-197): image [N,H,W,C], coords [N,h,w,2] -> out [N,h,w,C];
  * bilinear, floor-mod wrap-around in x and y. */
 int msi_resample(const float* image, const float* coords, int N, int H, int W, int C, int h, int w,

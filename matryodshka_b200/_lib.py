@@ -34,6 +34,8 @@ SIGNATURES = {
     "msi_render_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "msi_intersect_sphere_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "msi_project_layers": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "msi_point_op": (c_int, [_I, _P, _P, _P, ctypes.c_longlong, _I, _P, _I, ctypes.c_float, ctypes.c_float, _I, _I,
+                             _P, _P, _P, _P, _P]),
     "msi_resample": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "msi_over_composite": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "msi_net_create": (c_int, [POINTER(c_void_p), _I, _I, _I, _I, _I, _I, _I, _I]),

@@ -706,6 +706,110 @@ extern "C" int msi_project_layers(const float* rgba, const float* tgt_pose_rt, c
     return MSI_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Point-wise forms of the geometry/spherical.py functions (the stage-level API of the mirror):
+// one kernel, the operation selected by `op`.
+// ------------------------------------------------------------------------------------------
+namespace msi {
+struct PointOpParams {
+    int op;
+    long long n;          // points per plane
+    int planes;           // backproject: number of depths
+    const float *a, *b, *c;  // inputs (meaning depends on op)
+    const float* pose;    // apply_pose: [planes][16] or one [16]
+    int pose_per_plane;
+    float order, r;
+    float *o0, *o1, *o2;  // outputs
+    uint8_t* valid;
+    ErpConsts k;
+};
+
+__global__ void __launch_bounds__(256) point_op_kernel(PointOpParams p) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = p.n * (p.op <= MSI_OP_APPLY_POSE ? p.planes : 1);
+    if (idx >= total) return;
+    switch (p.op) {
+        case MSI_OP_BACKPROJECT_SPHERICAL: {  // a = S, b = T [n]; c = depth [planes] -> x, y, z [planes][n]
+            const long long i = idx % p.n;
+            const int pl = (int)(idx / p.n);
+            const float S = __ldg(p.a + i), T = __ldg(p.b + i), d = __ldg(p.c + pl);
+            const float ct = cosf(T);
+            p.o0[idx] = d * (cosf(S) * ct);
+            p.o1[idx] = d * sinf(T);
+            p.o2[idx] = d * (sinf(S) * ct);
+            break;
+        }
+        case MSI_OP_APPLY_POSE: {  // a, b, c = x, y, z [planes][n]
+            const int pl = (int)(idx / p.n);
+            const float* m = p.pose + (p.pose_per_plane ? pl * 16 : 0);
+            const float x = __ldg(p.a + idx), y = __ldg(p.b + idx), z = __ldg(p.c + idx);
+            p.o0[idx] = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+            p.o1[idx] = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+            p.o2[idx] = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+            break;
+        }
+        case MSI_OP_PROJECT_ODS: {  // a, b, c = x, y, z [n] -> uv [n][2], valid [n]
+            float u, v;
+            const bool ok = project_ods_point(__ldg(p.a + idx), __ldg(p.b + idx), __ldg(p.c + idx), p.order, p.r, p.k, u, v);
+            p.o0[2 * idx] = u;
+            p.o0[2 * idx + 1] = v;
+            if (p.valid != nullptr) p.valid[idx] = ok ? 1 : 0;
+            break;
+        }
+        case MSI_OP_PROJECT_SPHERICAL: {  // a, b, c = x, y, z [n] -> uv [n][2]
+            const float x = __ldg(p.a + idx), y = __ldg(p.b + idx), z = __ldg(p.c + idx);
+            const float theta = -atan2f(z, x);
+            const float phi = atan2f(y, sqrtf(x * x + z * z));
+            float u = theta + p.k.pi;
+            u = u - p.k.pi_w;
+            u = u / p.k.den_u;
+            p.o0[2 * idx] = u * p.k.wm1;
+            p.o0[2 * idx + 1] = ((phi + p.k.half_pi - p.k.half_pi_h) / p.k.den_v) * p.k.hm1;
+            break;
+        }
+        default: {  // MSI_OP_THETA_PHI_TO_PIXELS: a = theta, b = phi [n] -> uv [n][2]
+            float u = __ldg(p.a + idx) + p.k.pi;
+            u = u - p.k.pi_w;
+            u = u / p.k.den_u;
+            p.o0[2 * idx] = u * p.k.wm1;
+            p.o0[2 * idx + 1] = ((__ldg(p.b + idx) + p.k.half_pi - p.k.half_pi_h) / p.k.den_v) * p.k.hm1;
+            break;
+        }
+    }
+}
+}  // namespace msi
+
+extern "C" int msi_point_op(int op, const float* a, const float* b, const float* c, long long n, int planes,
+                            const float* pose, int pose_per_plane, float order, float baseline, int H, int W,
+                            float* o0, float* o1, float* o2, uint8_t* valid, void* stream) {
+    MSI_CHECK_ARG(op >= MSI_OP_BACKPROJECT_SPHERICAL && op <= MSI_OP_THETA_PHI_TO_PIXELS, "point_op: bad op %d", op);
+    MSI_CHECK_ARG(a && b && o0 && n > 0, "point_op: null pointer or n <= 0");
+    if (op <= MSI_OP_APPLY_POSE) MSI_CHECK_ARG(c && o1 && o2 && planes > 0, "point_op: op %d needs c, o1, o2, planes", op);
+    if (op == MSI_OP_APPLY_POSE) MSI_CHECK_ARG(pose != nullptr, "point_op: apply_pose needs a pose");
+    if (op == MSI_OP_PROJECT_ODS || op == MSI_OP_PROJECT_SPHERICAL) MSI_CHECK_ARG(c != nullptr, "point_op: needs z");
+    if (op >= MSI_OP_PROJECT_ODS) MSI_CHECK_ARG(H > 1 && W > 1, "point_op: needs the ERP size");
+    PointOpParams p;
+    p.op = op;
+    p.n = n;
+    p.planes = planes > 0 ? planes : 1;
+    p.a = a;
+    p.b = b;
+    p.c = c;
+    p.pose = pose;
+    p.pose_per_plane = pose_per_plane;
+    p.order = order;
+    p.r = baseline;
+    p.o0 = o0;
+    p.o1 = o1;
+    p.o2 = o2;
+    p.valid = valid;
+    p.k = make_erp_consts(H > 1 ? H : 2, W > 1 ? W : 2);
+    const long long total = n * (op <= MSI_OP_APPLY_POSE ? p.planes : 1);
+    point_op_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
 extern "C" int msi_resample(const float* image, const float* coords, int N, int H, int W, int C, int h, int w,
                             float* out, void* stream) {
     MSI_CHECK_ARG(image && coords && out, "resample: null pointer");

@@ -43,3 +43,11 @@ def over_composite(rgbas):
 def over_composite_depth(rgbas):
     """projector.py:225-244."""
     return ops.over_composite(torch.stack(list(rgbas), 0), depth_mode=True)
+
+
+def apply_pose(points, pose):
+    """projector.py:275-291.  points = (x, y, z) each [P, H, W]; pose [P, 4, 4] (or [1, 4, 4])."""
+    x, y, z = points
+    P = x.shape[0]
+    return tuple(t.reshape(x.shape) for t in ops.point_op(
+        ops.OP_APPLY_POSE, x.reshape(P, -1), y.reshape(P, -1), z.reshape(P, -1), pose=pose))

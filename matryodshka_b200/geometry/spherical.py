@@ -35,3 +35,34 @@ def project_ods_sweep(depths, pose, intrinsics, order, width, height, device="cu
     uv, valid = ops.sweep_coords(pose, base, depths, 1, height, width, device)
     e = 0 if order > 0 else 1
     return uv[0, e], valid[0, e].bool()
+
+
+def theta_phi_to_pixels(theta, phi, width, height):
+    """spherical.py:54-68 -> uv [..., 2] source pixel coordinates of the angles."""
+    uv = ops.point_op(ops.OP_THETA_PHI_TO_PIXELS, theta.reshape(-1), phi.reshape(-1), H=height, W=width)
+    return uv.reshape(tuple(theta.shape) + (2,))
+
+
+def backproject_spherical(S, T, depth, intrinsics=None):
+    """spherical.py:116-129.  S, T [H, W]; depth [P] -> (x, y, z) each [P, H, W]."""
+    depth = torch.as_tensor(depth, dtype=torch.float32, device=S.device).reshape(-1)
+    x, y, z = ops.point_op(ops.OP_BACKPROJECT_SPHERICAL, S.reshape(-1), T.reshape(-1), depth)
+    shp = (depth.numel(),) + tuple(S.shape)
+    return x.reshape(shp), y.reshape(shp), z.reshape(shp)
+
+
+def project_ods(points, order, pose, intrinsics, width, height):
+    """spherical.py:170-233, tuple branch: points = (x, y, z) each [P, H, W]; order +1 / -1;
+    intrinsics[0][0][0] = ODS baseline.  Returns uv [P, H, W, 2] ((1, 1) where disc < 0)."""
+    x, y, z = points
+    k = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(-1, 3, 3)
+    uv = ops.point_op(ops.OP_PROJECT_ODS, x.reshape(-1), y.reshape(-1), z.reshape(-1), order=order,
+                      baseline=float(k[0, 0, 0]), H=height, W=width)
+    return uv.reshape(tuple(x.shape) + (2,))
+
+
+def project_spherical(points, order, pose, intrinsics, width, height):
+    """spherical.py:235-246."""
+    x, y, z = points
+    uv = ops.point_op(ops.OP_PROJECT_SPHERICAL, x.reshape(-1), y.reshape(-1), z.reshape(-1), H=height, W=width)
+    return uv.reshape(tuple(x.shape) + (2,))

@@ -235,3 +235,39 @@ def over_composite(layers, depth_mode=False):
     check(lib.msi_over_composite(ptr(layers.contiguous()), L, B, H, W, 1 if depth_mode else 0, ptr(out),
                                  stream_ptr()), "msi_over_composite")
     return out
+
+
+OP_BACKPROJECT_SPHERICAL, OP_APPLY_POSE, OP_PROJECT_ODS, OP_PROJECT_SPHERICAL, OP_THETA_PHI_TO_PIXELS = range(5)
+
+
+def point_op(op, a, b, c=None, *, planes=1, pose=None, order=1.0, baseline=0.0, H=2, W=2, want_valid=False):
+    """msi_point_op: the point-wise geometry/spherical.py functions on flat float32 CUDA tensors.
+    Returns (o0, o1, o2) for back-projection / apply_pose, uv [n,2] (and valid) for the projections."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    dev = a.device
+    c = c.contiguous().float() if c is not None else None
+    if op == OP_BACKPROJECT_SPHERICAL:
+        n = a.numel()
+        planes = c.numel()
+        outs = [torch.empty((planes, n), dtype=torch.float32, device=dev) for _ in range(3)]
+    elif op == OP_APPLY_POSE:
+        planes = a.shape[0]
+        n = a.numel() // planes
+        outs = [torch.empty_like(a) for _ in range(3)]
+    else:
+        n = a.numel()
+        outs = [torch.empty((n, 2), dtype=torch.float32, device=dev), None, None]
+    pose_t, per_plane = None, 0
+    if pose is not None:
+        pose_t = _dev_f32(pose, dev).reshape(-1, 16).contiguous()
+        per_plane = 1 if pose_t.shape[0] > 1 else 0
+    valid = torch.empty((n,), dtype=torch.uint8, device=dev) if want_valid else None
+    check(lib.msi_point_op(op, ptr(a), ptr(b), ptr(c), n, planes, ptr(pose_t), per_plane, float(order), float(baseline),
+                           int(H), int(W), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(valid), stream_ptr()),
+          "msi_point_op")
+    if op <= OP_APPLY_POSE:
+        return tuple(outs)
+    return (outs[0], valid) if want_valid else outs[0]

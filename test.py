@@ -1,0 +1,230 @@
+#!/usr/bin/env python
+"""Inference driver with the reference's flags and output tree (reference test.py:36-83, :87-281).
+
+    python test.py --cameras_glob 'glob/test/reg/*.txt' --image_dir /data/360TestData \
+                   --input_type ODS --experiment_name ods-wotemp-elpips-coord --coord_net
+
+For every camera line ``scene img_ref img_src img_tgt baseline tx ty tz``
+(datasets.py:413-424) it loads ``<image_dir>/<scene>_pos<img>.jpeg`` (area-resized to
+--height x --width, datasets.py:507-518), infers the MSI, renders the target view + depth and writes
+``<output_root>/<experiment_name>/<scene>_<ids>/{tgt_image_*,output_tgt_*,output_depth_*,src_image_*,
+ref_image_*,msi_alpha_%02d,msi_rgb_%02d,blend_weight_%03d}.png``, ``blend_weights.npy``,
+``alphas.npy`` and ``step.txt`` -- the files the reference's eval.py reads (eval.py:132-136).
+
+Differences from the reference (it needs a TF-1.14 session, this needs a B200):
+* weights come from ``<checkpoint_dir>/<experiment_name>/weights.npz`` (arrays keyed by the TF
+  checkpoint variable names); a TF checkpoint reader is not built.  ``--random_init`` uses seeded
+  random weights, ``--synthetic N`` fabricates N synthetic ODS triples (no dataset needed);
+* high_res / on_video test types, psp / ODS re-renders and the GCN path are not built.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def str2bool(v):
+    return str(v).lower() in ("1", "true", "t", "yes", "y", "")
+
+
+def parse_flags(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    a = ap.add_argument
+    # i/o (test.py:39-47)
+    a("--cameras_glob", default="glob/test/regular/*.txt")
+    a("--image_dir", default="/path/to/test_640x320")
+    a("--hres_image_dir", default="/path/to/test_4096x2048")
+    a("--output_root", default="./test")
+    a("--checkpoint_dir", default="checkpoints")
+    a("--experiment_name", default="")
+    a("--shuffle_seq_length", type=int, default=3)
+    # model (test.py:49-62)
+    a("--operation", default="train")
+    a("--input_type", default="ODS")
+    a("--coord_net", nargs="?", const=True, default=False, type=str2bool)
+    a("--transform_inverse_reg", nargs="?", const=True, default=False, type=str2bool)
+    a("--jitter", nargs="?", const=True, default=False, type=str2bool)
+    a("--which_color_pred", default="blend_psv")
+    a("--ngf", type=int, default=64)
+    a("--min_depth", type=float, default=1)
+    a("--max_depth", type=float, default=100)
+    a("--num_psv_planes", type=int, default=32)
+    a("--num_msi_planes", type=int, default=32)
+    a("--random_seed", type=int, default=8964)
+    a("--net_only", nargs="?", const=True, default=False, type=str2bool)
+    a("--smoothed", nargs="?", const=True, default=False, type=str2bool)
+    a("--supervision", default="tgt")
+    a("--rot_factor", type=float, default=1.0)
+    a("--tr_factor", type=float, default=1.0)
+    # test script specific (test.py:75-83)
+    a("--test_type", default="")
+    a("--prefix", default="")
+    a("--test_outputs", default="rgba_layers_src_image_ref_image_tgt_image_blend_weights_alphas")
+    a("--num_runs", type=int, default=-1)
+    a("--gcn", nargs="?", const=True, default=False, type=str2bool)
+    a("--subdiv", type=int, default=7)
+    # loader.py:30-42
+    a("--height", type=int, default=320)
+    a("--width", type=int, default=640)
+    a("--batch_size", type=int, default=1)
+    # ours
+    a("--random_init", action="store_true", help="seeded random weights instead of weights.npz")
+    a("--synthetic", type=int, default=0, help="fabricate N synthetic ODS triples instead of reading a dataset")
+    a("--conv_impl", default="tcgen05", choices=["tcgen05", "simt"])
+    a("--device", default="cuda:0")
+    return ap.parse_args(argv)
+
+
+def write_image(filename, image):
+    """utils.py:76-81: clip to [0, 255], cast to uint8, save."""
+    from PIL import Image
+    byte_image = np.clip(image, 0, 255).astype("uint8")
+    if byte_image.ndim == 3 and byte_image.shape[2] == 1:
+        byte_image = byte_image[..., 0]
+    Image.fromarray(byte_image).save(filename)
+
+
+def load_image(path, height, width):
+    """JPEG -> float32 [H, W, 3] in [0, 1], area-resized (datasets.py:507-518)."""
+    from PIL import Image
+    img = Image.open(path).convert("RGB")
+    if img.size != (width, height):
+        img = img.resize((width, height), Image.BOX)
+    return np.asarray(img, dtype=np.float32) / 255.0
+
+
+def read_camera_lines(pattern):
+    """Camera files: ``scene id0 id1 id2 baseline tx ty tz`` per line (datasets.py:413-424)."""
+    seqs = []
+    for f in sorted(glob.glob(pattern)):
+        for line in open(f).read().split("\n"):
+            t = line.split()
+            if len(t) < 8:
+                continue
+            seqs.append(dict(scene_id=t[0], image_id=t[1:4], baseline=float(t[4]),
+                             tgt_pos=np.array([float(x) for x in t[5:8]], np.float32)))
+    return seqs
+
+
+def make_synthetic_dataset(root, n, height, width, seed):
+    """Writes n synthetic (ref, src, tgt) JPEG triples + one camera file; returns (glob, image_dir)."""
+    from PIL import Image
+    from matryodshka_b200 import synth
+    img_dir = os.path.join(root, "images")
+    cam_dir = os.path.join(root, "glob")
+    os.makedirs(img_dir, exist_ok=True)
+    os.makedirs(cam_dir, exist_ok=True)
+    lines = []
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        ref, src = synth.ods_pair(1, height, width, seed + 10 * i)
+        tgt = synth.band_limited_images(1, height, width, seed + 10 * i + 5)
+        for k, im in enumerate((ref[0], src[0], tgt[0])):
+            Image.fromarray((im * 255).astype(np.uint8)).save(os.path.join(img_dir, f"synth_pos{3 * i + k:03d}.jpeg"),
+                                                               quality=95)
+        tp = rng.uniform(-0.05, 0.05, 3)
+        lines.append(f"synth {3 * i:03d} {3 * i + 1:03d} {3 * i + 2:03d} 0.032 {tp[0]:.5f} {tp[1]:.5f} {tp[2]:.5f}")
+    with open(os.path.join(cam_dir, "synth.txt"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return os.path.join(cam_dir, "*.txt"), img_dir
+
+
+def load_weights(flags):
+    from matryodshka_b200 import synth
+    if flags.random_init:
+        return synth.net_weights(6 * flags.num_psv_planes, 2 * flags.num_msi_planes, flags.ngf, flags.random_seed), 0
+    path = os.path.join(flags.checkpoint_dir, flags.experiment_name, "weights.npz")
+    if not os.path.exists(path):
+        raise SystemExit(f"{path} not found: export the TF checkpoint variables to an .npz keyed by their TF names "
+                         "(net/conv1_1/weights ...), or pass --random_init")
+    z = np.load(path)
+    step = int(z["global_step"]) if "global_step" in z.files else 0
+    return {k: z[k] for k in z.files if k != "global_step"}, step
+
+
+def main(argv=None):
+    flags = parse_flags(argv)
+    assert flags.batch_size == 1, "Currently, batch_size must be 1 when testing."  # test.py:89
+    if flags.gcn or flags.input_type != "ODS" or flags.test_type not in ("",):
+        raise SystemExit("only the low-res ODS inference path is built (no gcn / PP / high_res / on_video)")
+    import torch
+    from matryodshka_b200.msi import MSI, MSIConfig
+
+    if flags.synthetic > 0:
+        flags.cameras_glob, flags.image_dir = make_synthetic_dataset(
+            os.path.join(flags.output_root, "_synthetic_input"), flags.synthetic, flags.height, flags.width,
+            flags.random_seed)
+    seqs = read_camera_lines(flags.cameras_glob)
+    if flags.num_runs >= 0:
+        seqs = seqs[:flags.num_runs]
+    if not seqs:
+        raise SystemExit(f"no camera lines under {flags.cameras_glob}")
+
+    weights, step = load_weights(flags)
+    cfg = MSIConfig(height=flags.height, width=flags.width, num_psv_planes=flags.num_psv_planes,
+                    num_msi_planes=flags.num_msi_planes, min_depth=flags.min_depth, max_depth=flags.max_depth,
+                    ngf=flags.ngf, which_color_pred=flags.which_color_pred, coord_net=bool(flags.coord_net),
+                    input_type=flags.input_type, operation=flags.operation, conv_impl=flags.conv_impl)
+    model = MSI(weights=weights, config=cfg, device=flags.device)
+    psv_planes = model.inv_depths(flags.min_depth, flags.max_depth, flags.num_psv_planes)
+    msi_planes = model.inv_depths(flags.min_depth, flags.max_depth, flags.num_msi_planes)
+    dev = torch.device(flags.device)
+    eye = np.eye(4, dtype=np.float32)[None]
+    out_root = os.path.join(flags.output_root, flags.experiment_name)
+    os.makedirs(out_root, exist_ok=True)
+
+    for run, s in enumerate(seqs):
+        imgs = [load_image(os.path.join(flags.image_dir, f"{s['scene_id']}_pos{i}.jpeg"), flags.height, flags.width)
+                for i in s["image_id"]]
+        ref, src, tgt = (torch.from_numpy(im[None]).to(dev) for im in imgs)  # data_loader.py:133-135
+        intrinsics = np.array([[[s["baseline"], 0, 0], [0, 1, 0], [0, 0, 1]]], np.float32)  # data_loader.py:160
+        outs, _ = model.infer_msi(src, ref, None, None, eye, eye, intrinsics, flags.which_color_pred,
+                                  flags.num_msi_planes, psv_planes, flags.test_outputs, ngf=flags.ngf)
+        r = model.msi_render_equirect(outs["rgba_layers"], eye, s["tgt_pos"][None], msi_planes)
+        torch.cuda.synchronize(dev)
+
+        dirname = s["scene_id"] + "_%s%s%s" % tuple(s["image_id"])  # test.py:208-217
+        output_dir = os.path.join(out_root, dirname)
+        os.makedirs(output_dir, exist_ok=True)
+        print("Saving to %s" % output_dir)
+        if run == 0:
+            with open(os.path.join(out_root, "step.txt"), "w") as fh:
+                fh.write("%d" % step)
+        to = flags.test_outputs
+        if "tgt_image" in to:
+            write_image(output_dir + "/tgt_image_%s.png" % dirname, imgs[2] * 255.0)
+            write_image(output_dir + "/output_tgt_%s.png" % dirname, r["rgb_u8"][0].cpu().numpy())
+            write_image(output_dir + "/output_depth_%s.png" % dirname, r["depth_u8"][0].cpu().numpy())
+        if "src_image" in to:
+            write_image(output_dir + "/src_image_%s.png" % dirname, imgs[1] * 255.0)
+        if "ref_image" in to:
+            write_image(output_dir + "/ref_image_%s.png" % dirname, imgs[0] * 255.0)
+        if "psv" in to:
+            psv = outs["psv"].cpu().numpy()
+            for j in range(flags.num_psv_planes):
+                write_image(output_dir + "/psv_plane_%.3d.png" % j, (psv[0, :, :, j * 3:(j + 1) * 3] + 1.0) / 2.0 * 255)
+        if "blend" in flags.which_color_pred and "blend_weights" in to:
+            bw = outs["blend_weights"].cpu().numpy()
+            np.save(output_dir + "/blend_weights.npy", bw)
+            for i in range(flags.num_msi_planes):
+                write_image(output_dir + "/blend_weight_%.3d.png" % i, bw[0, :, :, i] * 255.0)
+        if "alphas" in to:
+            np.save(output_dir + "/alphas.npy", outs["alphas"].cpu().numpy())
+        if "rgba_layers" in to:
+            rgba = outs["rgba_layers"].cpu().numpy()
+            for i in range(flags.num_msi_planes):
+                write_image(output_dir + "/msi_alpha_%.2d.png" % i, rgba[0, :, :, i, 3] * 255.0)
+                write_image(output_dir + "/msi_rgb_%.2d.png" % i, (rgba[0, :, :, i, :3] + 1.0) / 2.0 * 255)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,34 @@
+"""The test.py-equivalent driver writes the reference's output tree (test.py:219-281)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_driver_writes_reference_output_tree(tmp_path):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("msi_test_driver", os.path.join(root, "test.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    out = str(tmp_path / "out")
+    rc = drv.main(["--synthetic", "2", "--random_init", "--coord_net", "--experiment_name", "exp", "--output_root", out,
+                   "--height", "32", "--width", "64"])
+    assert rc == 0
+    exp = os.path.join(out, "exp")
+    assert open(os.path.join(exp, "step.txt")).read() == "0"
+    dirs = sorted(d for d in os.listdir(exp) if os.path.isdir(os.path.join(exp, d)))
+    assert dirs == ["synth_000001002", "synth_003004005"]
+    d = os.path.join(exp, dirs[0])
+    files = set(os.listdir(d))
+    for f in ["tgt_image_%s.png", "output_tgt_%s.png", "output_depth_%s.png", "src_image_%s.png", "ref_image_%s.png"]:
+        assert f % dirs[0] in files
+    for i in range(32):
+        assert "msi_alpha_%.2d.png" % i in files and "msi_rgb_%.2d.png" % i in files and "blend_weight_%.3d.png" % i in files
+    bw, al = np.load(os.path.join(d, "blend_weights.npy")), np.load(os.path.join(d, "alphas.npy"))
+    assert bw.shape == (1, 32, 64, 32) and al.shape == (1, 32, 64, 32) and bw.min() >= 0 and al.max() <= 1
+    from PIL import Image
+    im = np.asarray(Image.open(os.path.join(d, "output_tgt_%s.png" % dirs[0])))
+    assert im.shape == (32, 64, 3) and im.std() > 1

@@ -242,3 +242,35 @@ def test_psv_two_eye_form_is_bit_identical_to_single_kernel_form(same_pose):
     r8, s8 = _t((ref * 255).astype(np.uint8)), _t((src * 255).astype(np.uint8))
     assert torch.equal(ops.psv_build(r8, s8, poses, [0.032, 0.05], d, use_scratch=True),
                        ops.psv_build(r8, s8, poses, [0.032, 0.05], d, use_scratch=False))
+
+
+def test_stage_level_spherical_functions():
+    """geometry.spherical.{lat_long_grid, backproject_spherical, project_ods, project_spherical,
+    theta_phi_to_pixels} and projector.apply_pose, composed as sweep_one composes them."""
+    from matryodshka_b200.geometry import projector as pj, spherical as sp
+    H, W, P = 16, 32, 3
+    d = F32([40.0, 6.0, 1.2])
+    S, T = sp.lat_long_grid((H, W), device=DEV)
+    So, To = g.lat_long_grid((H, W))
+    assert np.array_equal(S.cpu().numpy(), So) and np.array_equal(T.cpu().numpy(), To)
+    x, y, z = sp.backproject_spherical(S, T, d)
+    xo, yo, zo = g.backproject_spherical(So, To, d)
+    assert np.abs(x.cpu().numpy() - xo).max() < 1e-5 * 40 and np.abs(y.cpu().numpy() - yo).max() < 1e-5 * 40
+    a = 0.05
+    pose = np.array([[np.cos(a), 0, np.sin(a), 0.01], [0, 1, 0, 0.02], [-np.sin(a), 0, np.cos(a), -0.01],
+                     [0, 0, 0, 1]], F32)[None]
+    # apply_pose and the projections on the ORACLE's points: same inputs -> exact / few-ulp outputs
+    pts = tuple(_t(t) for t in (xo, yo, zo))
+    px, py, pz = pj.apply_pose(pts, pose)
+    qx, qy, qz = g.apply_pose((xo, yo, zo), np.broadcast_to(pose, (P, 4, 4)))
+    assert np.array_equal(px.cpu().numpy(), qx) and np.array_equal(pz.cpu().numpy(), qz)
+    uv = sp.project_ods((_t(qx), _t(qy), _t(qz)), -1, None, synth.intrinsics(1), W, H).cpu().numpy()
+    uvo, aux = g.project_ods((qx, qy, qz), -1, None, synth.intrinsics(1), W, H, return_aux=True)
+    assert np.array_equal(uv[~aux["valid"]], uvo[~aux["valid"]])
+    assert np.abs(uv - uvo)[aux["valid"]].max() < 2e-3
+    us = sp.project_spherical((_t(qx), _t(qy), _t(qz)), 1, None, None, W, H).cpu().numpy()
+    assert np.abs(us - g.project_spherical((qx, qy, qz), 1, None, None, W, H)).max() < 2e-3
+    th = np.linspace(-3, 3, 50).astype(F32)
+    ph = np.linspace(-1.5, 1.5, 50).astype(F32)
+    tp = sp.theta_phi_to_pixels(_t(th), _t(ph), W, H).cpu().numpy()
+    assert np.array_equal(tp, g.theta_phi_to_pixels(th, ph, W, H))
