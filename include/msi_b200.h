@@ -176,6 +176,33 @@ int msi_over_composite(const float* layers, int L, int B, int H, int W, int dept
                        void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * High-res plane-streamed re-render (reference driver test.py:284-394), one PSV
+ * plane at a time so that a 4096x2048 sweep never holds more than one layer:
+ *
+ * msi_highres_plane: the high-res PSV plane of both eyes for ONE depth
+ *   (format_network_input with a single plane, test.py:312-317), the plane's
+ *   low-res blend weight / alpha upsampled bilinearly with align_corners
+ *   (:319-325) and the blend (:327-334) -> rgba [Hh,Wh,4].
+ *   hres_ref/src [1,Hh,Wh,3]; poses [2,16]; baseline [1]; depth [1];
+ *   tables for the Hh x Wh grid; blend_weights / alphas [1,lh,lw,L] (low-res net
+ *   outputs), plane = index into L.
+ * msi_highres_composite: reproject that layer to the target position
+ *   (msi_render_equirect_view_single, :338) and fold it into the running
+ *   composite in place (:374-382): acc_rgb, acc_depth [Hh,Wh,3] float32; plane 0
+ *   initialises them.
+ * ------------------------------------------------------------------------- */
+int msi_highres_plane(const void* hres_ref, const void* hres_src, int img_dtype, int preprocess,
+                      const float* poses, const float* baseline, const float* depth,
+                      const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                      int Hh, int Wh, const float* blend_weights, const float* alphas,
+                      int lh, int lw, int L, int plane, float* rgba, void* stream);
+int msi_highres_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                          const float* depth,
+                          const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                          int Hh, int Wh, int plane, int num_planes, float* acc_rgb, float* acc_depth,
+                          void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Stage 2 -- the conv net
  * replaces: nets.msi_coord_train_net (matryodshka/nets.py:471-515): 14 coord
  * convs 3x3 + LayerNorm + ReLU, 3 transposed convs 4x4 s2 + LayerNorm + ReLU,

@@ -38,6 +38,8 @@ SIGNATURES = {
                              _P, _P, _P, _P, _P]),
     "msi_resample": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "msi_over_composite": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "msi_highres_plane": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "msi_highres_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_net_create": (c_int, [POINTER(c_void_p), _I, _I, _I, _I, _I, _I, _I, _I]),
     "msi_net_destroy": (None, [_P]),
     "msi_net_workspace_bytes": (c_size_t, [_P]),

@@ -831,3 +831,148 @@ extern "C" int msi_over_composite(const float* layers, int L, int B, int H, int 
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// High-res plane-streamed re-render (reference driver test.py:284-394): per PSV plane,
+//   A  highres_plane_kernel: one high-res PSV plane for both eyes (format_network_input with a
+//      single depth, :312-317) + the plane's low-res blend weight / alpha upsampled bilinearly with
+//      align_corners (:319-325) + the blend (:327-334) -> one RGBA layer [Hh, Wh] float4;
+//   B  highres_composite_kernel: reproject that layer to the target position
+//      (msi_render_equirect_view_single, :338) and fold it into the running colour / depth
+//      composite (:374-382) in place -- the reference does this step in NumPy on the host.
+// ------------------------------------------------------------------------------------------
+namespace msi {
+
+struct UpW {
+    int lo, hi;
+    float lerp;
+};
+// [TF-1.14 ResizeBilinear, align_corners, legacy scaler]
+__device__ __forceinline__ UpW up_weights(int o, float scale, int in_size) {
+    UpW w;
+    const float in = (float)o * scale;
+    const float fl = floorf(in);
+    w.lo = max((int)fl, 0);
+    w.hi = min((int)ceilf(in), in_size - 1);
+    w.lerp = in - fl;
+    return w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+highres_plane_kernel(PsvParams p, const float* __restrict__ bw, const float* __restrict__ al, int lh, int lw, int L,
+                     int plane, float sy, float sx, float4* __restrict__ rgba) {
+    // p: B = 1, P = 1 (depths points at the plane's depth), images = the high-res pair
+    const long long npix = (long long)p.H * p.W;
+    const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (pix >= npix) return;
+    const int j = (int)(pix % p.W);
+    const int i = (int)(pix / p.W);
+    const float cs = __ldg(p.cos_s + j), sn = __ldg(p.sin_s + j), ct = __ldg(p.cos_t + i), st = __ldg(p.sin_t + i);
+    const float depth = __ldg(p.depths);
+    const float r = __ldg(p.baselines);
+    float rgb[2][3];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float u, v;
+        sweep_uv(cs, sn, ct, st, depth, p.poses + e * 16, e == 0 ? 1.0f : -1.0f, r, p.k, u, v);
+        const Bilinear s = bilinear_setup(u, v, p.W, p.H);
+        const T* img = reinterpret_cast<const T*>(p.img[e]);
+        const size_t oa = ((size_t)s.y0 * p.W + s.x0) * 3, ob = ((size_t)s.y0 * p.W + s.x1) * 3;
+        const size_t oc = ((size_t)s.y1 * p.W + s.x0) * 3, od = ((size_t)s.y1 * p.W + s.x1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            rgb[e][c] = blend4(s, load_img<T>(img, oa + c, p.preprocess), load_img<T>(img, ob + c, p.preprocess),
+                               load_img<T>(img, oc + c, p.preprocess), load_img<T>(img, od + c, p.preprocess));
+    }
+    const UpW wy = up_weights(i, sy, lh), wx = up_weights(j, sx, lw);
+    auto up = [&](const float* m) {
+        const float tl = __ldg(m + ((size_t)wy.lo * lw + wx.lo) * L + plane);
+        const float tr = __ldg(m + ((size_t)wy.lo * lw + wx.hi) * L + plane);
+        const float bl = __ldg(m + ((size_t)wy.hi * lw + wx.lo) * L + plane);
+        const float br = __ldg(m + ((size_t)wy.hi * lw + wx.hi) * L + plane);
+        const float top = tl + (tr - tl) * wx.lerp;
+        const float bottom = bl + (br - bl) * wx.lerp;
+        return top + (bottom - top) * wy.lerp;
+    };
+    const float uw = up(bw), ua = up(al);
+    const float omw = 1.0f - uw;
+    float4 o;
+    o.x = uw * rgb[0][0] + omw * rgb[1][0];
+    o.y = uw * rgb[0][1] + omw * rgb[1][1];
+    o.z = uw * rgb[0][2] + omw * rgb[1][2];
+    o.w = ua;
+    rgba[pix] = o;
+}
+
+__global__ void __launch_bounds__(256)
+highres_composite_kernel(RenderParams p, int plane, int num_planes, float* __restrict__ acc_rgb,
+                         float* __restrict__ acc_depth) {
+    // p: B = 1, L = 1, rgba = the plane's layer, depths points at the plane's depth
+    const long long npix = (long long)p.H * p.W;
+    const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (pix >= npix) return;
+    const int j = (int)(pix % p.W);
+    const int i = (int)(pix / p.W);
+    const float4 s = sample_layer(p, 0, i, j, 0);
+    float* o = acc_rgb + pix * 3;
+    float* d = acc_depth + pix * 3;
+    if (plane == 0) {
+        o[0] = s.x;
+        o[1] = s.y;
+        o[2] = s.z;
+        d[0] = d[1] = d[2] = 0.0f;
+    } else {
+        const float oma = 1.0f - s.w;
+        o[0] = o[0] * oma + s.x * s.w;
+        o[1] = o[1] * oma + s.y * s.w;
+        o[2] = o[2] * oma + s.z * s.w;
+        const float f = (float)((double)plane / (double)num_planes);
+        const float dd = f * s.w + d[0] * oma;
+        d[0] = d[1] = d[2] = dd;
+    }
+}
+
+}  // namespace msi
+
+extern "C" int msi_highres_plane(const void* hres_ref, const void* hres_src, int img_dtype, int preprocess,
+                                 const float* poses, const float* baseline, const float* depth, const float* cos_s,
+                                 const float* sin_s, const float* cos_t, const float* sin_t, int Hh, int Wh,
+                                 const float* blend_weights, const float* alphas, int lh, int lw, int L, int plane,
+                                 float* rgba, void* stream) {
+    PsvParams p;
+    int rc = fill_psv_params(p, hres_ref, hres_src, preprocess, poses, baseline, depth, cos_s, sin_s, cos_t, sin_t, 1, Hh,
+                             Wh, 1);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(hres_ref && hres_src && blend_weights && alphas && rgba, "highres_plane: null pointer");
+    MSI_CHECK_ARG(lh > 1 && lw > 1 && L > 0 && plane >= 0 && plane < L, "highres_plane: bad low-res shape / plane");
+    MSI_CHECK_ARG(img_dtype == MSI_IMG_F32 || img_dtype == MSI_IMG_U8, "highres_plane: bad img_dtype %d", img_dtype);
+    const float sy = (float)(lh - 1) / (float)(Hh - 1);
+    const float sx = (float)(lw - 1) / (float)(Wh - 1);
+    const long long npix = (long long)Hh * Wh;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (img_dtype == MSI_IMG_F32)
+        highres_plane_kernel<float><<<ceil_div(npix, 256), 256, 0, st>>>(p, blend_weights, alphas, lh, lw, L, plane, sy, sx,
+                                                                         reinterpret_cast<float4*>(rgba));
+    else
+        highres_plane_kernel<uint8_t><<<ceil_div(npix, 256), 256, 0, st>>>(p, blend_weights, alphas, lh, lw, L, plane, sy,
+                                                                           sx, reinterpret_cast<float4*>(rgba));
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_highres_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                                     const float* depth, const float* cos_s, const float* sin_s, const float* cos_t,
+                                     const float* sin_t, int Hh, int Wh, int plane, int num_planes, float* acc_rgb,
+                                     float* acc_depth, void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, rgba, tgt_pose_rt, tgt_pos, depth, cos_s, sin_s, cos_t, sin_t, 1, Hh, Wh, 1);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(rgba && acc_rgb && acc_depth, "highres_composite: null pointer");
+    MSI_CHECK_ARG(plane >= 0 && plane < num_planes, "highres_composite: plane %d outside [0, %d)", plane, num_planes);
+    const long long npix = (long long)Hh * Wh;
+    highres_composite_kernel<<<ceil_div(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p, plane, num_planes, acc_rgb, acc_depth);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}

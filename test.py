@@ -15,7 +15,10 @@ Differences from the reference (it needs a TF-1.14 session, this needs a B200):
 * weights come from ``<checkpoint_dir>/<experiment_name>/weights.npz`` (arrays keyed by the TF
   checkpoint variable names); a TF checkpoint reader is not built.  ``--random_init`` uses seeded
   random weights, ``--synthetic N`` fabricates N synthetic ODS triples (no dataset needed);
-* high_res / on_video test types, psp / ODS re-renders and the GCN path are not built.
+* ``--test_type high_res`` / ``high_res_only`` (test.py:284-394) re-render at --hres_height x
+  --hres_width from the saved blend_weights.npy / alphas.npy, plane by plane on the GPU, and write
+  output_hrestgt_*.png / output_hresdepth_*.png; with --synthetic the high-res images are fabricated too;
+* on_video, psp / ODS re-renders and the GCN path are not built.
 """
 from __future__ import annotations
 
@@ -75,6 +78,8 @@ def parse_flags(argv=None):
     a("--height", type=int, default=320)
     a("--width", type=int, default=640)
     a("--batch_size", type=int, default=1)
+    a("--hres_height", type=int, default=2048)
+    a("--hres_width", type=int, default=4096)
     # ours
     a("--random_init", action="store_true", help="seeded random weights instead of weights.npz")
     a("--synthetic", type=int, default=0, help="fabricate N synthetic ODS triples instead of reading a dataset")
@@ -114,11 +119,11 @@ def read_camera_lines(pattern):
     return seqs
 
 
-def make_synthetic_dataset(root, n, height, width, seed):
+def make_synthetic_dataset(root, n, height, width, seed, sub="images"):
     """Writes n synthetic (ref, src, tgt) JPEG triples + one camera file; returns (glob, image_dir)."""
     from PIL import Image
     from matryodshka_b200 import synth
-    img_dir = os.path.join(root, "images")
+    img_dir = os.path.join(root, sub)
     cam_dir = os.path.join(root, "glob")
     os.makedirs(img_dir, exist_ok=True)
     os.makedirs(cam_dir, exist_ok=True)
@@ -153,8 +158,8 @@ def load_weights(flags):
 def main(argv=None):
     flags = parse_flags(argv)
     assert flags.batch_size == 1, "Currently, batch_size must be 1 when testing."  # test.py:89
-    if flags.gcn or flags.input_type != "ODS" or flags.test_type not in ("",):
-        raise SystemExit("only the low-res ODS inference path is built (no gcn / PP / high_res / on_video)")
+    if flags.gcn or flags.input_type != "ODS" or flags.test_type not in ("", "high_res", "high_res_only"):
+        raise SystemExit("only the ODS inference path is built (test_type '', high_res, high_res_only; no gcn / PP / on_video)")
     import torch
     from matryodshka_b200.msi import MSI, MSIConfig
 
@@ -162,6 +167,10 @@ def main(argv=None):
         flags.cameras_glob, flags.image_dir = make_synthetic_dataset(
             os.path.join(flags.output_root, "_synthetic_input"), flags.synthetic, flags.height, flags.width,
             flags.random_seed)
+        if "high_res" in flags.test_type:
+            _, flags.hres_image_dir = make_synthetic_dataset(
+                os.path.join(flags.output_root, "_synthetic_input"), flags.synthetic, flags.hres_height,
+                flags.hres_width, flags.random_seed, sub="hres_images")
     seqs = read_camera_lines(flags.cameras_glob)
     if flags.num_runs >= 0:
         seqs = seqs[:flags.num_runs]
@@ -182,6 +191,8 @@ def main(argv=None):
     os.makedirs(out_root, exist_ok=True)
 
     for run, s in enumerate(seqs):
+        if flags.test_type == "high_res_only":
+            break
         imgs = [load_image(os.path.join(flags.image_dir, f"{s['scene_id']}_pos{i}.jpeg"), flags.height, flags.width)
                 for i in s["image_id"]]
         ref, src, tgt = (torch.from_numpy(im[None]).to(dev) for im in imgs)  # data_loader.py:133-135
@@ -223,6 +234,24 @@ def main(argv=None):
             for i in range(flags.num_msi_planes):
                 write_image(output_dir + "/msi_alpha_%.2d.png" % i, rgba[0, :, :, i, 3] * 255.0)
                 write_image(output_dir + "/msi_rgb_%.2d.png" % i, (rgba[0, :, :, i, :3] + 1.0) / 2.0 * 255)
+
+    if "high_res" in flags.test_type:  # test.py:284-394
+        from matryodshka_b200.highres import deprocess_high_res, high_res_rerender
+        for s in seqs:
+            dirname = s["scene_id"] + "_%s%s%s" % tuple(s["image_id"])
+            output_dir = os.path.join(out_root, dirname)
+            bw = torch.from_numpy(np.load(output_dir + "/blend_weights.npy")).to(dev)
+            al = torch.from_numpy(np.load(output_dir + "/alphas.npy")).to(dev)
+            hres = [load_image(os.path.join(flags.hres_image_dir, f"{s['scene_id']}_pos{i}.jpeg"), flags.hres_height,
+                               flags.hres_width) for i in s["image_id"][:2]]
+            href, hsrc = (torch.from_numpy(im[None]).to(dev) for im in hres)
+            intrinsics = np.array([[[s["baseline"], 0, 0], [0, 1, 0], [0, 0, 1]]], np.float32)
+            print("Rendering %s at %dx%d, %d planes." % (output_dir, flags.hres_width, flags.hres_height,
+                                                          flags.num_psv_planes))
+            rgb, dep = high_res_rerender(href, hsrc, bw, al, eye, eye, intrinsics, s["tgt_pos"][None], psv_planes)
+            u8, d8 = deprocess_high_res(rgb, dep)
+            write_image(output_dir + "/output_hrestgt_%s.png" % dirname, u8.cpu().numpy())
+            write_image(output_dir + "/output_hresdepth_%s.png" % dirname, d8.cpu().numpy())
     return 0
 
 

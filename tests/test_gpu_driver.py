@@ -32,3 +32,21 @@ def test_driver_writes_reference_output_tree(tmp_path):
     from PIL import Image
     im = np.asarray(Image.open(os.path.join(d, "output_tgt_%s.png" % dirs[0])))
     assert im.shape == (32, 64, 3) and im.std() > 1
+
+
+def test_driver_high_res_mode(tmp_path):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("msi_test_driver", os.path.join(root, "test.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    out = str(tmp_path / "out")
+    rc = drv.main(["--synthetic", "1", "--random_init", "--coord_net", "--experiment_name", "exp", "--output_root", out,
+                   "--height", "32", "--width", "64", "--hres_height", "96", "--hres_width", "192",
+                   "--test_type", "high_res"])
+    assert rc == 0
+    d = os.path.join(out, "exp", "synth_000001002")
+    from PIL import Image
+    im = np.asarray(Image.open(os.path.join(d, "output_hrestgt_synth_000001002.png")))
+    dep = np.asarray(Image.open(os.path.join(d, "output_hresdepth_synth_000001002.png")))
+    assert im.shape == (96, 192, 3) and dep.shape == (96, 192, 3) and im.std() > 1
