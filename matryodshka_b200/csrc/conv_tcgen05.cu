@@ -550,11 +550,15 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                     *slot = make_double2(old.x + ds, old.y + dq);
                 }
             }
-            // last CTA to finish turns the partials into (mean, rstd) per frame
-            __threadfence();
+            // last CTA to finish turns the partials into (mean, rstd) per frame.  Barrier, then ONE
+            // thread fences at GPU scope and bumps the counter: the barrier orders the other threads'
+            // partial-sum writes before it and the fence is cumulative (the grid-sync pattern).
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             const int et = threadIdx.x - 64;  // index inside the epilogue group
-            if (et == 0) s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+            if (et == 0) {
+                __threadfence();
+                s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             if (s_is_last) {
                 __threadfence();
