@@ -134,6 +134,15 @@ int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const floa
                          float* out_rgb, float* out_depth, uint8_t* out_rgb_u8, uint8_t* out_depth_u8,
                          void* stream);
 
+/* The MSI seen from one ODS eye: MSI.msi_render_ods_view (msi.py:502-525) ->
+ * projector.projective_forward_ods (projector.py:101-127) -> spherical.intersect_ods
+ * (spherical.py:328-365) + over_composite.  pose_rt [B,16] (the "jitter pose"), order = +1 (left /
+ * ref eye) or -1 (right / src eye), baselines [B]; out_rgb [B,H,W,3] float32 and/or uint8. */
+int msi_render_ods(const float* rgba, const float* pose_rt, float order, const float* baselines,
+                   const float* depths,
+                   const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                   int B, int H, int W, int L, float* out_rgb, uint8_t* out_rgb_u8, void* stream);
+
 /* Sample coordinates only (spherical.intersect_sphere): uv [B,L,H,W,2]. */
 int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
                                 const float* cos_s, const float* sin_s, const float* cos_t,

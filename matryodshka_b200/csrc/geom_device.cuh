@@ -144,6 +144,30 @@ __device__ __forceinline__ SphereRay sphere_ray(float cs, float sn, float ct, fl
     return q;
 }
 
+// The ray of spherical.intersect_ods (spherical.py:328-365) + transform_ray (:70-94): an ODS eye
+// (order = +1 left / -1 right, viewing-circle radius = baseline) looks along
+// (cosS cosT, sinT, -sinS cosT) from (-sinS b order, 0, -cosS b order); both are moved by `pose`.
+// The target offset is NOT used by the reference here.
+__device__ __forceinline__ SphereRay sphere_ray_ods(float cs, float sn, float ct, float st,
+                                                    const float* __restrict__ pos, float order, float baseline) {
+    SphereRay q;
+    const float rx0 = cs * ct;
+    const float ry0 = st;
+    const float rz0 = (-sn) * ct;
+    const float cx0 = ((-sn) * baseline) * order;
+    const float cy0 = 0.0f;
+    const float cz0 = ((-cs) * baseline) * order;
+    q.rx = (pos[0] * rx0 + pos[1] * ry0) + pos[2] * rz0;
+    q.ry = (pos[4] * rx0 + pos[5] * ry0) + pos[6] * rz0;
+    q.rz = (pos[8] * rx0 + pos[9] * ry0) + pos[10] * rz0;
+    q.cx = ((pos[0] * cx0 + pos[1] * cy0) + pos[2] * cz0) + pos[3];
+    q.cy = ((pos[4] * cx0 + pos[5] * cy0) + pos[6] * cz0) + pos[7];
+    q.cz = ((pos[8] * cx0 + pos[9] * cy0) + pos[10] * cz0) + pos[11];
+    q.a = (q.rx * q.rx + q.ry * q.ry) + q.rz * q.rz;
+    q.b = 2.0f * ((q.rx * q.cx + q.ry * q.cy) + q.rz * q.cz);
+    return q;
+}
+
 // ... and the per-layer hit + projection (:315-326, :235-246, :54-68).  Same operations in the same
 // order as sphere_uv below, so both forms give identical bits.
 __device__ __forceinline__ void sphere_hit_uv(const SphereRay& q, float radius, const ErpConsts& k, float& u, float& v) {

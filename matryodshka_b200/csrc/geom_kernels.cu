@@ -307,6 +307,9 @@ struct RenderParams {
     uint8_t* out_rgb_u8;
     uint8_t* out_depth_u8;
     ErpConsts k;
+    int ods_mode;            // 0: target ERP view (intersect_sphere); 1: ODS eye view (intersect_ods)
+    float ods_order;         // +1 / -1
+    const float* baselines;  // [B] (ODS mode)
 };
 
 __device__ __forceinline__ float4 sample_layer(const RenderParams& p, int b, int i, int j, int l) {
@@ -353,8 +356,12 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
             const int j = (int)(pix % p.W);
             const int i = (int)((pix / p.W) % p.H);
             b = (int)(pix / ((long long)p.W * p.H));
-            ray = sphere_ray(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
-                             p.pose_rt + b * 16, p.tgt_pos + b * 3);
+            if (p.ods_mode)
+                ray = sphere_ray_ods(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                                     p.pose_rt + b * 16, p.ods_order, __ldg(p.baselines + b));
+            else
+                ray = sphere_ray(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                                 p.pose_rt + b * 16, p.tgt_pos + b * 3);
         }
         s_ray[q] = ray;
         s_b[q] = b;
@@ -650,6 +657,9 @@ static int fill_render_params(RenderParams& p, const float* rgba, const float* p
     p.out_rgb_u8 = nullptr;
     p.out_depth_u8 = nullptr;
     p.k = make_erp_consts(H, W);
+    p.ods_mode = 0;
+    p.ods_order = 1.0f;
+    p.baselines = nullptr;
     return MSI_OK;
 }
 
@@ -668,6 +678,35 @@ extern "C" int msi_render_composite(const float* rgba, const float* tgt_pose_rt,
     p.out_depth_u8 = out_depth_u8;
     const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
     MSI_CHECK_ARG(smem <= 200 * 1024, "render: L=%d needs %zu B of shared memory", L, smem);
+    static std::atomic<size_t> smem_opted{48 * 1024};
+    if (smem > smem_opted.load()) {
+        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_opted.store(smem);
+    }
+    const long long npix = (long long)B * H * W;
+    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+// MSI.msi_render_ods_view (msi.py:502-525) -> projector.projective_forward_ods (projector.py:101-127) ->
+// spherical.intersect_ods (spherical.py:328-365) + over_composite: the MSI seen from one ODS eye.
+extern "C" int msi_render_ods(const float* rgba, const float* pose_rt, float order, const float* baselines,
+                              const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
+                              const float* sin_t, int B, int H, int W, int L, float* out_rgb, uint8_t* out_rgb_u8,
+                              void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, rgba, pose_rt, pose_rt, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(rgba && baselines && (out_rgb || out_rgb_u8), "render_ods: null pointer");
+    MSI_CHECK_ARG(order == 1.0f || order == -1.0f, "render_ods: order must be +1 or -1");
+    p.out_rgb = out_rgb;
+    p.out_rgb_u8 = out_rgb_u8;
+    p.ods_mode = 1;
+    p.ods_order = order;
+    p.baselines = baselines;
+    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
+    MSI_CHECK_ARG(smem <= 200 * 1024, "render_ods: L=%d needs %zu B of shared memory", L, smem);
     static std::atomic<size_t> smem_opted{48 * 1024};
     if (smem > smem_opted.load()) {
         MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -200,3 +200,11 @@ class MSI(object):
         return ops.project_layers(rgba_layers, tgt_pose_rt, tgt_pos, planes)
 
     msi_render_equirect_depth_single = msi_render_equirect_view_single
+
+    def msi_render_ods_view(self, rgba_layers, order, jitter_pose, tgt_pos, planes, intrinsics):
+        """msi.py:502-525: the MSI seen from one ODS eye (order +1 = left / ref, -1 = right / src)
+        under ``jitter_pose`` [B,4,4].  As in the reference, ``tgt_pos`` is not used by the ODS ray
+        generator (spherical.intersect_ods) and the baseline is intrinsics[0][0][0] for every frame."""
+        B = rgba_layers.shape[0]
+        base = float(_host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[0, 0, 0])
+        return ops.render_ods(rgba_layers, jitter_pose, order, [base] * B, list(planes))

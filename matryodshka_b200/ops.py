@@ -181,6 +181,26 @@ def render_composite(rgba, tgt_pose_rt, tgt_pos, depths, *, want_rgb=True, want_
     return res
 
 
+def render_ods(rgba, pose_rt, order, baselines, depths, *, want_u8=False):
+    """msi_render_ods: the MSI [B,H,W,L,4] seen from one ODS eye (order +1 / -1) under pose_rt
+    [B,4,4].  Returns rgb [B,H,W,3] float32 (and the uint8 deprocessed image when want_u8)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, L, four = rgba.shape
+    assert four == 4
+    dev = rgba.device
+    depths = _dev_f32(depths, dev, (-1,))
+    assert depths.numel() == L
+    pose = _dev_f32(pose_rt, dev, (B, 16))
+    base = _dev_f32(baselines, dev, (B,))
+    tb = erp_tables(H, W, dev)
+    rgb = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    u8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+    check(lib.msi_render_ods(ptr(rgba.contiguous()), ptr(pose), float(order), ptr(base), ptr(depths), *tb.ptrs(),
+                             B, H, W, L, ptr(rgb), ptr(u8), stream_ptr()), "msi_render_ods")
+    return (rgb, u8) if want_u8 else rgb
+
+
 def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device):
     """msi_intersect_sphere_coords -> uv [B,L,H,W,2]."""
     _lib.require_cuda()

@@ -196,6 +196,38 @@ def intersect_sphere(pos, center, radius, num_planes, num_batch, width, height, 
         return project_spherical((x, y, z), 1, None, None, width, height, dt).astype(dt)
 
 
+def intersect_ods(pose, center, order, intrinsics, radius, num_planes, num_batch, width, height, dt=F32):
+    """spherical.py:328-365 (+ transform_ray :70-94, get_sphere_intersections :96-111,
+    project_spherical :235-246).  pose [4,4]; order +1 (left) / -1 (right); intrinsics[0][0][0] =
+    baseline; radius [L].  ``center`` is accepted and ignored, as in the reference.  uv [L,H,W,2]."""
+    pose = np.asarray(pose, dtype=dt)
+    radius = np.asarray(radius, dtype=dt).reshape(num_planes, 1, 1)
+    baseline = dt(np.asarray(intrinsics)[0][0][0])
+    S, T = lat_long_grid((height, width), dt)
+    S = np.broadcast_to(S[None], (num_planes, height, width))
+    T = np.broadcast_to(T[None], (num_planes, height, width))
+    cosT = np.cos(T)
+    rx = np.cos(S) * cosT
+    ry = np.sin(T)
+    rz = -np.sin(S) * cosT
+    cx = -np.sin(S) * baseline * dt(order)
+    cy = np.zeros_like(S)
+    cz = -np.cos(S) * baseline * dt(order)
+    rx, ry, rz = _matvec_rows(pose[:3, :3], [rx, ry, rz], dt)
+    pt = _matvec_rows(pose, [cx, cy, cz, np.ones_like(cx)], dt)
+    cx, cy, cz = pt[0], pt[1], pt[2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = rx * rx + ry * ry + rz * rz
+        b = dt(2) * (rx * cx + ry * cy + rz * cz)
+        c = cx * cx + cy * cy + cz * cz - radius * radius
+        disc = np.square(b) - dt(4) * a * c
+        t = (-b + np.sqrt(disc)) / (dt(2) * a)
+        x = cx + t * rx
+        y = cy + t * ry
+        z = cz + t * rz
+        return project_spherical((x, y, z), order, None, intrinsics, width, height, dt).astype(dt)
+
+
 # --------------------------------------------------------------------------- #
 # sampling.py
 # --------------------------------------------------------------------------- #

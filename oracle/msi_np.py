@@ -176,6 +176,20 @@ def msi_render_equirect_depth(rgba_layers, tgt_pose_rt, tgt_pos, planes, intrins
     return g.over_composite_depth([proj[i] for i in range(len(planes))], dt)
 
 
+def msi_render_ods_view(rgba_layers, order, jitter_pose, tgt_pos, planes, intrinsics, dt=F32):
+    """msi.py:502-525 -> projector.projective_forward_ods (projector.py:101-127): the MSI seen from
+    one ODS eye, over-composited.  jitter_pose [B,4,4]; intrinsics [B,3,3] (only [0][0][0] is read)."""
+    rgba_layers = np.asarray(rgba_layers, dtype=dt)
+    B, H, W, L, _ = rgba_layers.shape
+    depths = np.asarray(planes, dtype=dt)
+    layers = np.transpose(rgba_layers, (3, 0, 1, 2, 4))  # [L, B, H, W, 4]
+    coords = [g.intersect_ods(np.asarray(jitter_pose, dtype=dt)[i], None, order, intrinsics, depths, L, B, W, H, dt)
+              for i in range(B)]
+    coords = np.stack(coords, axis=0).transpose(1, 0, 2, 3, 4)
+    proj = [g.resample(layers[l], coords[l], dt) for l in range(L)]
+    return g.over_composite(proj, dt)
+
+
 def msi_render_equirect_view_single(rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None, dt=F32):
     """msi.py:431-452: reprojected layers without compositing [L, B, H, W, 4]."""
     return _project_layers(rgba_layers, tgt_pose_rt, tgt_pos, planes, dt)
