@@ -32,6 +32,8 @@
 //            NHWC stores + LayerNorm partial sums
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "net_internal.cuh"
 
 namespace msi {
@@ -75,10 +77,22 @@ struct TcParams {
     unsigned int* counter;  // zeroed before the launch
     float2* stats;       // [B] (mean, rstd)
     double n_per_sample;
+    // halo kernel (conv_halo_tcgen05_kernel): the A operand of all taps of one 64-channel chunk is ONE
+    // halo tile in shared memory; tap (dy, dx) = the same tile read through a row-shifted descriptor
+    int orient;          // 0: x is the fast (8-wide) tile dimension, BW = 8, BH = 16; 1: y fast, BH = 8, BW = 16
+    int PF, PS;          // halo extent along the fast / slow dimension (pixels)
+    int a_rows;          // PF * PS smem rows of 128 bytes per precision half
+    int a_slot_bytes;    // [hi halo | lo halo], rounded up to 1024
+    int a_stages;
+    int T;               // taps per W ring slot
+    int w_stages;
+    int halo_x0[4], halo_y0[4];  // per class: halo origin relative to the tile origin (min dx, min dy)
+    long long* trace;    // debugging: CTA 0 records clock64() of its pipeline events here (null = off)
 };
 
 struct TcPlan {
     TcParams p;
+    int halo;                 // 1: conv_halo_tcgen05_kernel (a_map[s][0] = 5-D hi+lo map, w_map[0] = 4-D [kb][hi|lo][cout][64])
     int n_tile, split;
     int cl;                   // cluster size along M: CTAs of a cluster multicast the W tile to each other
     CUtensorMap a_map[2][2];  // [source][hi/lo]
@@ -141,6 +155,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -248,6 +269,162 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mas
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
         ::"r"(bar), "h"(cta_mask)
         : "memory");
+}
+
+// Epilogue role, shared by both kernels: tcgen05.ld -> un-scale + coord bias (+ bias, tanh for the
+// head) -> float32 NHWC stores + LayerNorm partial sums; the last CTA finalises (mean, rstd).
+// ew = index of this warp among the kEpiWarps epilogue warps, quarter = its TMEM lane quarter
+// (hardware: warp id % 4), (lx, ly) = position of this thread's accumulator row inside the M tile.
+template <int N_TILE, int SPLIT, int CL>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, const int quarter, const int lane,
+                                              const int lx, const int ly, const int cluster_id, const int n_clusters,
+                                              const int cta_rank, const uint32_t tmem_base, const uint32_t tfull0,
+                                              const uint32_t tempty0, int* s_is_last, double (*s_red)[kEpiWarps]) {
+    constexpr int kAccCols = SPLIT ? 2 * N_TILE : N_TILE;
+    const int c_begin = (ew >> 2) * (N_TILE / 2), c_end = c_begin + N_TILE / 2;  // this warp's columns
+    float s_sum = 0.f, s_sq = 0.f;
+    int cur_b = -1;
+    int local = 0;
+    for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
+        const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
+        if (p.do_stats && tc.b != cur_b) {
+            if (cur_b >= 0) {
+                // this (frame, CTA, warp) slot belongs to this warp alone: plain read-modify-write
+                const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
+                if (lane == 0) {
+                    double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
+                    const double2 old = *slot;
+                    *slot = make_double2(old.x + ds, old.y + dq);
+                }
+                s_sum = 0.f;
+                s_sq = 0.f;
+            }
+            cur_b = tc.b;
+        }
+        const int my = tc.oy0 + ly, mx = tc.ox0 + lx;  // output position inside the class grid
+        const bool valid = (my < p.Mh) && (mx < p.Mw) && !tc.dummy;
+        int oy = my, ox = mx;
+        if (p.out_stride == 2) {
+            oy = my * 2 + (tc.cls >> 1);
+            ox = mx * 2 + (tc.cls & 1);
+        }
+        float* orow = p.out + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * p.cout + tc.n0;
+        const float* cb = nullptr;
+        if (p.cbias != nullptr && valid) {
+            int mask = 0;
+            for (int kw = 0; kw < p.cb_k; ++kw) {
+                const int ix = ox * p.cb_stride + kw * p.cb_rate - p.cb_pad_l;
+                if (ix >= 0 && ix < p.cb_Win) mask |= 1 << kw;
+            }
+            cb = p.cbias + ((size_t)oy * 8 + mask) * p.cout + tc.n0;
+        }
+        const int acc = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(tfull0 + 8u * acc, use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && local < 512) p.trace[6 * 1024 + 2 * local] = clock64();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 32) {
+            uint32_t r[32];
+            uint32_t r2[SPLIT ? 32 : 1];
+            tmem_ld32(taddr + (uint32_t)c, r);
+            if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 32 >= c_end) {
+                // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v;
+                    if (SPLIT) {
+                        v.x = (__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0])) * p.unscale;
+                        v.y = (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) * p.unscale;
+                        v.z = (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) * p.unscale;
+                        v.w = (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) * p.unscale;
+                    } else {
+                        v.x = __uint_as_float(r[j + 0]) * p.unscale;
+                        v.y = __uint_as_float(r[j + 1]) * p.unscale;
+                        v.z = __uint_as_float(r[j + 2]) * p.unscale;
+                        v.w = __uint_as_float(r[j + 3]) * p.unscale;
+                    }
+                    if (cb != nullptr) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(cb + c + j));
+                        v.x += q.x;
+                        v.y += q.y;
+                        v.z += q.z;
+                        v.w += q.w;
+                    }
+                    if (p.kind == kHead) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + tc.n0 + c + j));
+                        v.x = fast_tanh(v.x + q.x);
+                        v.y = fast_tanh(v.y + q.y);
+                        v.z = fast_tanh(v.z + q.z);
+                        v.w = fast_tanh(v.w + q.w);
+                    }
+                    s_sum += (v.x + v.y) + (v.z + v.w);
+                    s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    *reinterpret_cast<float4*>(orow + c + j) = v;
+                }
+            }
+        }
+        if (p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && local < 512) p.trace[6 * 1024 + 2 * local + 1] = clock64();
+    }
+    if (p.do_stats) {
+        if (cur_b >= 0) {
+            const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
+            if (lane == 0) {
+                double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
+                const double2 old = *slot;
+                *slot = make_double2(old.x + ds, old.y + dq);
+            }
+        }
+        // last CTA to finish turns the partials into (mean, rstd) per frame.  Barrier, then ONE
+        // thread fences at GPU scope and bumps the counter: the barrier orders the other threads'
+        // partial-sum writes before it and the fence is cumulative (the grid-sync pattern).
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const int et = ew * 32 + lane;  // index inside the epilogue group
+        if (et == 0) {
+            __threadfence();
+            *s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (*s_is_last) {
+            __threadfence();
+            const int used = gridDim.x * kEpiWarps;
+            for (int b = 0; b < p.B; ++b) {
+                double s = 0, q = 0;
+                for (int i = et; i < used; i += 32 * kEpiWarps) {
+                    const double2 v = __ldcg(&p.partials[(size_t)b * p.n_partials + i]);
+                    s += v.x;
+                    q += v.y;
+                }
+                s = warp_sum_d(s);
+                q = warp_sum_d(q);
+                if (lane == 0) {
+                    s_red[0][ew] = s;
+                    s_red[1][ew] = q;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                if (et == 0) {
+                    double a = 0, c = 0;
+                    for (int w = 0; w < kEpiWarps; ++w) {
+                        a += s_red[0][w];
+                        c += s_red[1][w];
+                    }
+                    const double mean = a / p.n_per_sample;
+                    double var = c / p.n_per_sample - mean * mean;
+                    if (var < 0) var = 0;
+                    p.stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-12)));
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            }
+        }
+    }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
@@ -444,159 +621,235 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
             }
         }
     } else {
-        // =============================== epilogue (warps 2..5) ===============================
-        const int quarter = warp & 3;         // TMEM lane quarter this warp may access
-        const int ew = warp - 2;              // 0..7
-        const int c_begin = (ew >> 2) * (N_TILE / 2), c_end = c_begin + N_TILE / 2;  // this warp's columns
-        const int row = quarter * 32 + lane;  // M index inside the tile
+        // =============================== epilogue (warps 2..9) ===============================
+        const int row = (warp & 3) * 32 + lane;  // M index inside the tile
         const int ly = row / p.BW;
-        const int lx = row - ly * p.BW;
-        float s_sum = 0.f, s_sq = 0.f;
-        int cur_b = -1;
-        int local = 0;
-        for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
-            const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
-            if (p.do_stats && tc.b != cur_b) {
-                if (cur_b >= 0) {
-                    // this (frame, CTA, warp) slot belongs to this warp alone: plain read-modify-write
-                    const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
-                    if (lane == 0) {
-                        double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
-                        const double2 old = *slot;
-                        *slot = make_double2(old.x + ds, old.y + dq);
-                    }
-                    s_sum = 0.f;
-                    s_sq = 0.f;
-                }
-                cur_b = tc.b;
-            }
-            const int my = tc.oy0 + ly, mx = tc.ox0 + lx;  // output position inside the class grid
-            const bool valid = (my < p.Mh) && (mx < p.Mw) && !tc.dummy;
-            int oy = my, ox = mx;
-            if (p.out_stride == 2) {
-                oy = my * 2 + (tc.cls >> 1);
-                ox = mx * 2 + (tc.cls & 1);
-            }
-            float* orow = p.out + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * p.cout + tc.n0;
-            const float* cb = nullptr;
-            if (p.cbias != nullptr && valid) {
-                int mask = 0;
-                for (int kw = 0; kw < p.cb_k; ++kw) {
-                    const int ix = ox * p.cb_stride + kw * p.cb_rate - p.cb_pad_l;
-                    if (ix >= 0 && ix < p.cb_Win) mask |= 1 << kw;
-                }
-                cb = p.cbias + ((size_t)oy * 8 + mask) * p.cout + tc.n0;
-            }
-            const int acc = local & 1;
-            const uint32_t use = (uint32_t)(local >> 1);
-            mbar_wait(tfull0 + 8u * acc, use & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; c += 32) {
-                uint32_t r[32];
-                uint32_t r2[SPLIT ? 32 : 1];
-                tmem_ld32(taddr + (uint32_t)c, r);
-                if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 32 >= c_end) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-                }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v;
-                        if (SPLIT) {
-                            v.x = (__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0])) * p.unscale;
-                            v.y = (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) * p.unscale;
-                            v.z = (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) * p.unscale;
-                            v.w = (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) * p.unscale;
-                        } else {
-                            v.x = __uint_as_float(r[j + 0]) * p.unscale;
-                            v.y = __uint_as_float(r[j + 1]) * p.unscale;
-                            v.z = __uint_as_float(r[j + 2]) * p.unscale;
-                            v.w = __uint_as_float(r[j + 3]) * p.unscale;
-                        }
-                        if (cb != nullptr) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(cb + c + j));
-                            v.x += q.x;
-                            v.y += q.y;
-                            v.z += q.z;
-                            v.w += q.w;
-                        }
-                        if (p.kind == kHead) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + tc.n0 + c + j));
-                            v.x = fast_tanh(v.x + q.x);
-                            v.y = fast_tanh(v.y + q.y);
-                            v.z = fast_tanh(v.z + q.z);
-                            v.w = fast_tanh(v.w + q.w);
-                        }
-                        s_sum += (v.x + v.y) + (v.z + v.w);
-                        s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                        *reinterpret_cast<float4*>(orow + c + j) = v;
-                    }
-                }
-            }
-        }
-        if (p.do_stats) {
-            if (cur_b >= 0) {
-                const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
-                if (lane == 0) {
-                    double2* slot = &p.partials[(size_t)cur_b * p.n_partials + blockIdx.x * kEpiWarps + ew];
-                    const double2 old = *slot;
-                    *slot = make_double2(old.x + ds, old.y + dq);
-                }
-            }
-            // last CTA to finish turns the partials into (mean, rstd) per frame.  Barrier, then ONE
-            // thread fences at GPU scope and bumps the counter: the barrier orders the other threads'
-            // partial-sum writes before it and the fence is cumulative (the grid-sync pattern).
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-            const int et = threadIdx.x - 64;  // index inside the epilogue group
-            if (et == 0) {
-                __threadfence();
-                s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-            if (s_is_last) {
-                __threadfence();
-                const int used = gridDim.x * kEpiWarps;
-                for (int b = 0; b < p.B; ++b) {
-                    double s = 0, q = 0;
-                    for (int i = et; i < used; i += 32 * kEpiWarps) {
-                        const double2 v = __ldcg(&p.partials[(size_t)b * p.n_partials + i]);
-                        s += v.x;
-                        q += v.y;
-                    }
-                    s = warp_sum_d(s);
-                    q = warp_sum_d(q);
-                    if (lane == 0) {
-                        s_red[0][ew] = s;
-                        s_red[1][ew] = q;
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-                    if (et == 0) {
-                        double a = 0, c = 0;
-                        for (int w = 0; w < kEpiWarps; ++w) {
-                            a += s_red[0][w];
-                            c += s_red[1][w];
-                        }
-                        const double mean = a / p.n_per_sample;
-                        double var = c / p.n_per_sample - mean * mean;
-                        if (var < 0) var = 0;
-                        p.stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-12)));
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-                }
-            }
-        }
+        epilogue_role<N_TILE, SPLIT, CL>(p, warp - 2, warp & 3, lane, row - ly * p.BW, ly, cluster_id, n_clusters, cta_rank,
+                                         tmem_base, tfull0, tempty0, &s_is_last, s_red);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its smem / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---- the halo kernel ---------------------------------------------------------------------------
+// Same GEMM, different operand delivery.  Measured on B200 (scripts/probe_umma.cu, profiles/): one SM
+// ingests at most ~55-65 B/clk through TMA, and the kernel above re-fetches the activation tile for
+// every tap (9x for a 3x3 conv): 64 KB per 768 MMA-clocks = 85 B/clk, so it is bound by operand
+// delivery, not by the tensor pipe.  Here the producer loads, per 64-channel chunk, ONE halo tile
+// {64 ch, PF, PS} x {hi, lo} (a single 5-D TMA box) and the MMA warp reads all taps out of it: a
+// K-major SWIZZLE_128B descriptor may start at any 128-byte row and use any stride between 8-row
+// groups (probe A), so tap (dy, dx) is the halo tile's descriptor advanced by (dy * PF + dx) rows
+// with SBO = PF rows.  That needs one 8-pixel group per tile row: the M tile is 16 x 8 pixels (or
+// 8 x 16 through a tensor map with H and W swapped).  The weights of T taps arrive as one 4-D box
+// [tap][hi|lo][N][64] from a K-block-major packing.  Ingest drops to 25-45 B/clk.
+//   warp 0  A producer (halo ring, a_stages slots)      warp 2  W producer (w_stages slots of T taps)
+//   warp 1  MMA issuer + TMEM allocator                 warps 3-10  epilogue (shared with the kernel above)
+constexpr int kHaloThreads = 96 + 32 * kEpiWarps;
+constexpr int kTraceRegion = 1024, kTraceRegions = 10;
+__device__ __forceinline__ void trace_ev(long long* tr, int region, int idx) {
+    if (tr != nullptr && blockIdx.x == 0 && idx < kTraceRegion) tr[region * kTraceRegion + idx] = clock64();
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                         const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
+    constexpr int kAccCols = 2 * N_TILE;
+    constexpr int kTmemCols = 2 * kAccCols;
+    constexpr int kWTapBytes = 2 * N_TILE * kBlockK * 2;  // [W_hi | W_lo] of one tap
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full_bar[2];
+    __shared__ __align__(8) uint64_t a_empty_bar[2];
+    __shared__ __align__(8) uint64_t w_full_bar[8];
+    __shared__ __align__(8) uint64_t w_empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int s_is_last;
+    __shared__ double s_red[2][kEpiWarps];
+    __shared__ int s_off[4][9];  // smem row offset of every tap inside the halo tile
+    __shared__ int s_ntaps[4];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int chunks_total = p.chunks[0] + p.chunks[1];
+    const int a_stages = p.a_stages, w_stages = p.w_stages, T = p.T;
+    const uint32_t a_slot_bytes = (uint32_t)p.a_slot_bytes;
+    const uint32_t w_slot_bytes = (uint32_t)(T * kWTapBytes);
+    const uint32_t w_ring = smem_base + (uint32_t)a_stages * a_slot_bytes;
+
+    if (threadIdx.x < 36) {
+        const int c = threadIdx.x / 9, t = threadIdx.x % 9;
+        const int ddx = p.taps[c].dx[t] - p.halo_x0[c], ddy = p.taps[c].dy[t] - p.halo_y0[c];
+        s_off[c][t] = (p.orient == 0) ? ddy * p.PF + ddx : ddx * p.PF + ddy;
+        if (t == 0) s_ntaps[c] = p.taps[c].n;
+    }
+    const uint32_t afull0 = smem_u32(&a_full_bar[0]);
+    const uint32_t aempty0 = smem_u32(&a_empty_bar[0]);
+    const uint32_t wfull0 = smem_u32(&w_full_bar[0]);
+    const uint32_t wempty0 = smem_u32(&w_empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]);
+    const uint32_t tempty0 = smem_u32(&tmem_empty_bar[0]);
+    if (threadIdx.x == 96) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(afull0 + 8u * s, 1);
+            mbar_init(aempty0 + 8u * s, 1);
+            mbar_init(tfull0 + 8u * s, 1);
+            mbar_init(tempty0 + 8u * s, kEpiWarps);
+        }
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(wfull0 + 8u * s, 1);
+            mbar_init(wempty0 + 8u * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&a0);
+        if (p.nsrc == 2) prefetch_tmap(&a1);
+    }
+    if (warp == 2 && lane == 0) prefetch_tmap(&wmap);
+    if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_smem);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+    const int n_ctas = gridDim.x;
+    if (threadIdx.x == 0) trace_ev(p.trace, 7, 0);
+
+    if (warp == 0) {
+        // =============================== A (halo) producer ===============================
+        if (lane == 0) {
+            const int chunks0 = p.chunks[0];
+            const uint32_t a_tx = (uint32_t)(2 * p.a_rows * 128);
+            int tr_i = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas) {
+                const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
+                const int hx = tc.ox0 + p.halo_x0[tc.cls], hy = tc.oy0 + p.halo_y0[tc.cls];
+                const int cf = (p.orient == 0) ? hx : hy, cs = (p.orient == 0) ? hy : hx;
+                for (int ch = 0; ch < chunks_total; ++ch) {
+                    mbar_wait(aempty0 + 8u * stage, phase ^ 1u);
+                    trace_ev(p.trace, 4, tr_i++);
+                    mbar_expect_tx(afull0 + 8u * stage, a_tx);
+                    const bool second = ch >= chunks0;
+                    tma_load_5d(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
+                                (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                    if (++stage == a_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // =============================== W producer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            int tr_i = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas) {
+                const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
+                const int ntaps = s_ntaps[tc.cls];
+                int kb = tc.cls * chunks_total * ntaps;
+                const int n_slots = chunks_total * (ntaps / T);
+                for (int sl = 0; sl < n_slots; ++sl, kb += T) {
+                    mbar_wait(wempty0 + 8u * stage, phase ^ 1u);
+                    trace_ev(p.trace, 2, tr_i);
+                    mbar_expect_tx(wfull0 + 8u * stage, w_slot_bytes);
+                    tma_load_4d(w_ring + (uint32_t)stage * w_slot_bytes, &wmap, wfull0 + 8u * stage, 0, tc.n0, 0, kb);
+                    trace_ev(p.trace, 3, tr_i++);
+                    if (++stage == w_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_wide = make_idesc(2 * N_TILE);
+        constexpr uint32_t idesc_n = make_idesc(N_TILE);
+        constexpr uint64_t kDescFlags = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        const uint64_t a_desc_hi = kDescFlags | ((uint64_t)(p.PF * 8) << 32);  // SBO = PF rows of 128 bytes (>> 4)
+        const uint64_t lo_adv = (uint64_t)(p.a_rows * 8);                       // hi halo -> lo halo
+        int a_stage = 0, w_stage = 0;
+        uint32_t a_phase = 0, w_phase = 0;
+        int local = 0;
+        int tr_slot = 0, tr_chunk = 0;
+        trace_ev(leader ? p.trace : nullptr, 7, 1);
+        for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas, ++local) {
+            const int cls = (unit / p.units_per_col) / p.n_tiles;
+            const int ntaps = s_ntaps[cls];
+            const int slots_per_chunk = ntaps / T;
+            const int acc = local & 1;
+            const uint32_t use = (uint32_t)(local >> 1);
+            mbar_wait(tempty0 + 8u * acc, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            trace_ev(leader ? p.trace : nullptr, 8, local);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+            uint32_t accumulate = 0u;
+            for (int ch = 0; ch < chunks_total; ++ch) {
+                mbar_wait(afull0 + 8u * a_stage, a_phase);
+                trace_ev(leader ? p.trace : nullptr, 5, tr_chunk++);
+                const uint64_t da_tile = a_desc_hi | (uint64_t)(((smem_base + (uint32_t)a_stage * a_slot_bytes) >> 4) & 0x3FFF);
+                for (int sl = 0; sl < slots_per_chunk; ++sl) {
+                    mbar_wait(wfull0 + 8u * w_stage, w_phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (leader) {
+                        trace_ev(p.trace, 0, tr_slot);
+                        uint64_t db = make_desc(w_ring + (uint32_t)w_stage * w_slot_bytes);
+                        for (int t = 0; t < T; ++t, db += (uint64_t)(kWTapBytes >> 4)) {
+                            const uint64_t da = da_tile + (uint64_t)(s_off[cls][sl * T + t] * 8);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                umma_f16(d_tmem, da + adv, db + adv, idesc_wide, accumulate);  // A_hi x [W_hi | W_lo]
+                                accumulate = 1u;
+                                umma_f16(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);    // A_lo x W_hi
+                            }
+                        }
+                        umma_commit(wempty0 + 8u * w_stage);
+                        if (sl == slots_per_chunk - 1) {
+                            umma_commit(aempty0 + 8u * a_stage);
+                            if (ch == chunks_total - 1) umma_commit(tfull0 + 8u * acc);
+                        }
+                        trace_ev(p.trace, 1, tr_slot);
+                    }
+                    ++tr_slot;
+                    __syncwarp();
+                    if (++w_stage == w_stages) {
+                        w_stage = 0;
+                        w_phase ^= 1u;
+                    }
+                }
+                if (++a_stage == a_stages) {
+                    a_stage = 0;
+                    a_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // =============================== epilogue (warps 3..10) ===============================
+        const int row = (warp & 3) * 32 + lane;  // M index inside the tile: 8-pixel group = row / 8
+        const int lx = (p.orient == 0) ? (row & 7) : (row >> 3);
+        const int ly = (p.orient == 0) ? (row >> 3) : (row & 7);
+        epilogue_role<N_TILE, 1, 1>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base, tfull0,
+                                    tempty0, &s_is_last, s_red);
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) trace_ev(p.trace, 7, 2);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -644,6 +897,40 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams q) {
     split_half(v * MSI_WEIGHT_SCALE, h, l);
     q.hi[idx] = h;
     q.lo[idx] = l;
+}
+
+// K-block-major packing of the halo kernel: [kb][hi|lo][cout][64] with kb = (cls * chunks + chunk) *
+// ntaps + tap, so that the [W_hi | W_lo] tiles of T consecutive taps of one chunk are ONE 4-D TMA box.
+__global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, int chunks_total, int ntaps) {
+    const long long total = (long long)q.ncls * chunks_total * ntaps * q.cout * kBlockK;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int k64 = (int)(idx % kBlockK);
+    const int n = (int)((idx / kBlockK) % q.cout);
+    const int kb = (int)(idx / ((long long)kBlockK * q.cout));
+    const int t = kb % ntaps;
+    const int chunk = (kb / ntaps) % chunks_total;
+    const int cls = kb / (ntaps * chunks_total);
+    int pc = chunk * kBlockK + k64;  // packed channel
+    int c = -1;                      // channel in the concatenated TF tensor
+    if (pc < q.cstride[0]) {
+        if (pc < q.cin[0]) c = pc;
+    } else if (q.nsrc == 2) {
+        pc -= q.cstride[0];
+        if (pc < q.cin[1]) c = q.cin[0] + pc;
+    }
+    float v = 0.f;
+    if (c >= 0) {
+        const int wt = q.taps[cls].wtap[t];
+        if (q.kind == kDeconv)
+            v = q.w[((size_t)wt * q.cout + n) * q.cin_total + c];
+        else
+            v = q.w[((size_t)wt * (q.cin_total + 1) + c) * q.cout + n];
+    }
+    __half h, l;
+    split_half(v * MSI_WEIGHT_SCALE, h, l);
+    q.hi[(((size_t)kb * 2 + 0) * q.cout + n) * kBlockK + k64] = h;
+    q.hi[(((size_t)kb * 2 + 1) * q.cout + n) * kBlockK + k64] = l;
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -701,6 +988,59 @@ int encode_w_map(CUtensorMap* m, const __half* base, int K, int cout, int ncls, 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(weights K=%d cout=%d ncls=%d) failed: %d", K, cout, ncls, (int)r);
+        return MSI_ERR_CUDA;
+    }
+    return MSI_OK;
+}
+
+// 5-D activation map of the halo kernel: {C, fast, slow, hi|lo, B}, box {64, PF, PS, 2, 1}.  The hi
+// and lo tensors are two carve-outs of one workspace, so "lo" is "hi" at a constant byte offset.
+int encode_act_map5(CUtensorMap* m, const __half* hi, const __half* lo, int C, int W, int H, int B, int orient, int PF,
+                    int PS) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return MSI_ERR_CUDA;
+    }
+    const long long hl = (const char*)lo - (const char*)hi;
+    if (hl <= 0 || hl % 16 != 0) {
+        set_error("conv_tc: hi/lo activation buffers are not at a positive 16-byte-aligned offset");
+        return MSI_ERR_UNSUPPORTED;
+    }
+    const cuuint64_t row = (cuuint64_t)C * 2, img_row = (cuuint64_t)W * C * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(orient == 0 ? W : H), (cuuint64_t)(orient == 0 ? H : W), 2,
+                          (cuuint64_t)B};
+    cuuint64_t strides[4] = {orient == 0 ? row : img_row, orient == 0 ? img_row : row, (cuuint64_t)hl,
+                             (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)PF, (cuuint32_t)PS, 2, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)hi, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(halo activation C=%d W=%d H=%d B=%d orient=%d box=%dx%d) failed: %d", C, W, H, B,
+                  orient, PF, PS, (int)r);
+        return MSI_ERR_CUDA;
+    }
+    return MSI_OK;
+}
+
+// 4-D weight map of the halo kernel over [kb][hi|lo][cout][64], box {64, n_tile, 2, T}
+int encode_w_map4(CUtensorMap* m, const __half* base, int cout, int nkb, int n_tile, int T) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return MSI_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)kBlockK, (cuuint64_t)cout, 2, (cuuint64_t)nkb};
+    cuuint64_t strides[3] = {(cuuint64_t)kBlockK * 2, (cuuint64_t)cout * kBlockK * 2, (cuuint64_t)2 * cout * kBlockK * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile, 2, (cuuint32_t)T};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(halo weights cout=%d nkb=%d n_tile=%d T=%d) failed: %d", cout, nkb, n_tile, T, (int)r);
         return MSI_ERR_CUDA;
     }
     return MSI_OK;
@@ -773,6 +1113,86 @@ int launch_tc_nt(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
     if (plan->cl == 2)
         return plan->split ? launch_tc<N_TILE, 1, 2>(plan, p, st) : launch_tc<N_TILE, 0, 2>(plan, p, st);
     return plan->split ? launch_tc<N_TILE, 1, 1>(plan, p, st) : launch_tc<N_TILE, 0, 1>(plan, p, st);
+}
+
+long long* g_trace_dev = nullptr;
+long long* trace_buffer() {
+    if (!g_trace_dev) {
+        if (cudaMalloc(&g_trace_dev, sizeof(long long) * kTraceRegion * kTraceRegions) != cudaSuccess) {
+            cudaGetLastError();
+            g_trace_dev = nullptr;
+        } else {
+            cudaMemset(g_trace_dev, 0, sizeof(long long) * kTraceRegion * kTraceRegions);
+        }
+    }
+    return g_trace_dev;
+}
+
+template <int N_TILE>
+int launch_halo(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = conv_halo_tcgen05_kernel<N_TILE>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_halo_tcgen05_kernel<%d>, %d) failed: %s", N_TILE, kMaxDynSmem,
+                      cudaGetErrorString(e));
+            return MSI_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    kern<<<plan->grid, kHaloThreads, plan->smem_bytes, st>>>(plan->a_map[0][0], plan->a_map[1][0], plan->w_map[0], p);
+    return MSI_OK;
+}
+
+// Halo-kernel plan: tile orientation, halo extents, ring sizes, 5-D / 4-D tensor maps.  Returns
+// MSI_ERR_UNSUPPORTED when the layer does not fit (the caller then uses the per-tap kernel).
+int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batch) {
+    TcParams& p = plan->p;
+    const int c0 = ((p.Mw + 7) / 8) * ((p.Mh + 15) / 16), c1 = ((p.Mw + 15) / 16) * ((p.Mh + 7) / 8);
+    p.orient = (c1 < c0) ? 1 : 0;
+    p.BW = p.orient == 0 ? 8 : 16;
+    p.BH = p.orient == 0 ? 16 : 8;
+    int ext_x = -1, ext_y = -1;
+    for (int c = 0; c < p.ncls; ++c) {
+        int minx = 1 << 20, maxx = -(1 << 20), miny = 1 << 20, maxy = -(1 << 20);
+        for (int t = 0; t < p.taps[c].n; ++t) {
+            minx = std::min(minx, p.taps[c].dx[t]);
+            maxx = std::max(maxx, p.taps[c].dx[t]);
+            miny = std::min(miny, p.taps[c].dy[t]);
+            maxy = std::max(maxy, p.taps[c].dy[t]);
+        }
+        p.halo_x0[c] = minx;
+        p.halo_y0[c] = miny;
+        const int ex = p.BW + maxx - minx, ey = p.BH + maxy - miny;
+        if (c > 0 && (ex != ext_x || ey != ext_y || p.taps[c].n != p.taps[0].n)) return MSI_ERR_UNSUPPORTED;
+        ext_x = ex;
+        ext_y = ey;
+    }
+    p.PF = p.orient == 0 ? ext_x : ext_y;
+    p.PS = p.orient == 0 ? ext_y : ext_x;
+    p.a_rows = p.PF * p.PS;
+    p.a_slot_bytes = (2 * p.a_rows * 128 + 1023) / 1024 * 1024;
+    p.a_stages = 2;
+    const int ntaps = p.taps[0].n;
+    p.T = (plan->n_tile == 64) ? ((ntaps % 3 == 0) ? 3 : 2) : 1;
+    if (ntaps % p.T != 0 || p.PS > 256 || p.PF > 256) return MSI_ERR_UNSUPPORTED;
+    const int w_slot = p.T * 2 * plan->n_tile * kBlockK * 2;
+    p.w_stages = (kMaxDynSmem - 1024 - p.a_stages * p.a_slot_bytes) / w_slot;
+    if (p.w_stages > 8) p.w_stages = 8;
+    if (p.w_stages < 2) return MSI_ERR_UNSUPPORTED;
+    plan->smem_bytes = 1024 + p.a_stages * p.a_slot_bytes + p.w_stages * w_slot;
+    p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
+    p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
+    if (L.w_lo != L.w_hi + (size_t)L.ncls * L.cout * L.K) return MSI_ERR_UNSUPPORTED;  // one [.. hi|lo ..] buffer
+    int rc = MSI_OK;
+    for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s)
+        rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, srcs[s].lo, srcs[s].c_stride, srcs[s].W, srcs[s].H, max_batch,
+                             p.orient, p.PF, p.PS);
+    if (rc == MSI_OK && L.nsrc == 1) plan->a_map[1][0] = plan->a_map[0][0];
+    const int nkb = L.ncls * (p.chunks[0] + p.chunks[1]) * ntaps;
+    if (rc == MSI_OK) rc = encode_w_map4(&plan->w_map[0], L.w_hi, L.cout, nkb, plan->n_tile, p.T);
+    return rc;
 }
 
 }  // namespace
@@ -858,6 +1278,22 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     p.stats = L.stats;
     p.n_per_sample = (double)L.Hout * L.Wout * L.cout;
 
+    {
+        const char* env = getenv("MSI_CONV_HALO");
+        const bool want = !(env && atoi(env) == 0) && plan->split && plan->cl == 1 &&
+                          ((L.kind == kConv && L.stride == 1) || L.kind == kDeconv);
+        if (want) {
+            TcPlan saved = *plan;
+            if (plan_halo(plan, L, srcs, max_batch) == MSI_OK) {
+                plan->halo = 1;
+                const char* tr = getenv("MSI_TC_TRACE");  // debugging: scope name of the layer to trace
+                plan->p.trace = (tr && strcmp(tr, L.scope) == 0) ? trace_buffer() : nullptr;
+                L.tc_plan = plan;
+                return MSI_OK;
+            }
+            *plan = saved;  // does not fit: per-tap kernel
+        }
+    }
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s) {
         rc = encode_act_map(&plan->a_map[s][0], srcs[s].hi, srcs[s].c_stride, srcs[s].W, srcs[s].H, max_batch, p.BW,
@@ -879,6 +1315,19 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     L.tc_plan = plan;
     return MSI_OK;
 }
+
+}  // namespace msi
+
+// Debugging hook (not part of include/msi_b200.h): copies the pipeline-event clocks that CTA 0 of the
+// layer named by MSI_TC_TRACE recorded during its last launch.  Returns the number of entries.
+extern "C" int msi_debug_conv_trace(long long* host_out, int max_entries) {
+    const int n = msi::kTraceRegion * msi::kTraceRegions;
+    if (!msi::g_trace_dev || !host_out || max_entries < n) return 0;
+    if (cudaMemcpy(host_out, msi::g_trace_dev, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+
+namespace msi {
 
 void conv_tc_plan_destroy(LayerPlan& L) {
     if (L.tc_plan) {
@@ -909,7 +1358,12 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
     else
         q.taps[0] = conv_taps(L);
     const long long total = (long long)L.ncls * L.cout * L.K;
-    pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q);
+    const TcPlan* plan = reinterpret_cast<const TcPlan*>(L.tc_plan);
+    if (plan && plan->halo)
+        pack_weights_halo_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q, plan->p.chunks[0] + plan->p.chunks[1],
+                                                                        plan->p.taps[0].n);
+    else
+        pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
@@ -939,7 +1393,11 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
         set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * kEpiWarps);
         return MSI_ERR_STATE;
     }
-    const int rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, st) : launch_tc_nt<128>(plan, p, st);
+    int rc;
+    if (plan->halo)
+        rc = (plan->n_tile == 64) ? launch_halo<64>(plan, p, st) : launch_halo<128>(plan, p, st);
+    else
+        rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, st) : launch_tc_nt<128>(plan, p, st);
     if (rc != MSI_OK) return rc;
     MSI_LAUNCH_CHECK();
     return MSI_OK;
