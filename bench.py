@@ -206,7 +206,7 @@ def run_ours(args):
     import torch.distributed as dist
     from matryodshka_b200 import _lib, synth
     from matryodshka_b200.nets import net_flops
-    from matryodshka_b200.runtime import MSIPipeline, all_gather_frames, profile_net_layers
+    from matryodshka_b200.runtime import MSIFrameLanes, all_gather_frames, profile_net_layers
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,19 +226,36 @@ def run_ours(args):
     ref, src = synth.ods_pair(Bp, H, W, seed)
     wts = synth.net_weights(6 * P, 2 * P, ngf, 8964)
     tp = synth.target_positions(Bp, seed)
-    pipe = MSIPipeline(wts, H, W, P, ngf, batch=Bp, device=dev, conv_impl=args.conv_impl, precision=args.precision,
-                       use_graph=not args.no_graph)
-    pipe.set_inputs(ref, src, tgt_pos=tp)
+    # `lanes` frames in flight: independent pipelines (own workspace / CUDA graph / stream) fed round-robin,
+    # so that one frame's kernels fill the tail and ramp bubbles of the other's (runtime.MSIFrameLanes)
+    n_lanes = max(1, args.lanes)
+    lanes = MSIFrameLanes(wts, H, W, P, ngf, lanes=n_lanes, batch=Bp, device=dev, conv_impl=args.conv_impl,
+                          precision=args.precision, use_graph=not args.no_graph)
+    lanes.set_inputs(ref, src, tgt_pos=tp)
+    pipe = lanes.lanes[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    gather = (lambda lane: all_gather_frames(lane.out["rgb_u8"], world)) if world > 1 else None
+
     def one_step():
-        pipe.step()
-        if world > 1:
-            all_gather_frames(pipe.out["rgb_u8"], world)
+        lanes.step(after_compute=gather)
+
+    def timed(n, step_fn):
+        """Device time of n steps: CUDA events on the current stream around fork / join of the lane streams."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        lanes.fork()
+        for _ in range(n):
+            step_fn()
+        lanes.join()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
 
     # launches per step, counted on one eager (un-graphed) step
     was_graph = pipe.use_graph
@@ -249,38 +266,45 @@ def run_ours(args):
     launches_per_step = _lib.launch_count() - c0
     pipe.use_graph = was_graph
 
-    for _ in range(Wm):
+    lanes.fork()
+    for _ in range(Wm * n_lanes):
         one_step()
+    lanes.join()
     barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # ---- device-resident timed region: inputs already in HBM ------------------------------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        one_step()
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
+    dev_ms = timed(K, one_step)
+    # the same K steps on ONE lane (one frame at a time), reported beside the headline for reference
+    single_ms = dev_ms
+    if n_lanes > 1:
+        def lane0_step():
+            with torch.cuda.stream(lanes.streams[0]):
+                pipe.step()
+                if gather is not None:
+                    gather(pipe)
+        single_ms = timed(K, lane0_step)
 
     # ---- end-to-end region: host (pinned) images in, host uint8 view + depth out ----------------
     # Every step copies its inputs host -> device from pinned memory and its results (uint8 view +
     # depth) device -> host; the public streaming API (submit / collect) keeps two batches in flight so
     # that those copies overlap the neighbouring batches' compute.  Wall clock, all K steps collected.
     h_ref, h_src = torch.from_numpy(ref).pin_memory(), torch.from_numpy(src).pin_memory()
-    gather = (lambda: all_gather_frames(pipe.out["rgb_u8"], world)) if world > 1 else None
+    in_flight = 2 * n_lanes  # every lane double-buffers its copies
 
     def e2e_loop(n):
+        last = None
         for i in range(n):
-            pipe.submit(h_ref, h_src, after_compute=gather)
-            if i >= 1:
-                pipe.collect()
-        return pipe.collect()
+            lanes.submit(h_ref, h_src, after_compute=gather)
+            if i >= in_flight - 1:
+                last = lanes.collect()
+        for _ in range(min(n, in_flight - 1)):
+            last = lanes.collect()
+        return last
 
-    e2e_loop(3)
+    e2e_loop(2 * in_flight)
     barrier()
     t0 = time.perf_counter()
     last = e2e_loop(K)
@@ -297,9 +321,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, single_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms, single_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -343,13 +367,15 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{W}x{H} ERP, {P}-sphere MSI, batch={Bp}/GPU, ngf={ngf} (BASELINE.json configs[1])",
                        "frames_per_step": world * Bp, "conv_impl": args.conv_impl, "precision": args.precision,
-                       "cuda_graph": not args.no_graph,
+                       "cuda_graph": not args.no_graph, "frames_in_flight": n_lanes,
+                       "one_frame_at_a_time": {"value": frames / (single_ms * 1e-3), "unit": UNIT,
+                                               "ms_per_step": single_ms / K},
                        "collective": "all_gather of rendered uint8 frames" if world > 1 else "none",
                        "l2": f"per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "ms_per_step": e2e_ms / K,
-                    "input": "float32 host images (pinned) -> uint8 view + depth on host; MSIPipeline.submit/collect, "
-                             "2 batches in flight (H2D / compute / D2H on three streams)"},
+                    "input": "float32 host images (pinned) -> uint8 view + depth on host; MSIFrameLanes.submit/collect, "
+                             f"{n_lanes} lane(s) x 2 batches in flight (H2D / compute / D2H on three streams per lane)"},
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,
             "roofline": roofline,
@@ -375,6 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--conv-impl", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
+    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU (independent pipelines on own streams)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-profile", action="store_true",

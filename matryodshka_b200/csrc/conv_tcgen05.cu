@@ -87,6 +87,7 @@ struct TcParams {
     int T;               // taps per W ring slot
     int w_stages;
     int halo_x0[4], halo_y0[4];  // per class: halo origin relative to the tile origin (min dx, min dy)
+    int stage_out;       // 1: the epilogue transposes its tiles through shared memory (coalesced stores)
     long long* trace;    // debugging: CTA 0 records clock64() of its pipeline events here (null = off)
 };
 
@@ -113,6 +114,13 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor is still running; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible, pdl_trigger() lets the successor grid start being scheduled.
+// Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -127,6 +135,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Non-blocking test (try_wait suspends the thread for up to a hardware time limit when the phase
+// has not completed -- measured ~8000 clk on B200 -- so it cannot be used to peek at a barrier).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -271,16 +292,39 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mas
         : "memory");
 }
 
+// ---- debugging trace (MSI_TC_TRACE) ----
+constexpr int kTraceRegion = 1024, kTraceRegions = 10;
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// region 9: [0] = launch counter; launch i records event k (nanoseconds, %globaltimer) at [8 + 16 * i + k]
+__device__ __forceinline__ void trace_g(long long* tr, int launch, int k) {
+    if (tr != nullptr && launch >= 0 && launch < 60) tr[9 * kTraceRegion + 8 + 16 * launch + k] = globaltimer_ns();
+}
+__device__ __forceinline__ void trace_ev(long long* tr, int region, int idx) {
+    if (tr != nullptr && blockIdx.x == 0 && idx < kTraceRegion) tr[region * kTraceRegion + idx] = clock64();
+}
+
 // Epilogue role, shared by both kernels: tcgen05.ld -> un-scale + coord bias (+ bias, tanh for the
 // head) -> float32 NHWC stores + LayerNorm partial sums; the last CTA finalises (mean, rstd).
 // ew = index of this warp among the kEpiWarps epilogue warps, quarter = its TMEM lane quarter
 // (hardware: warp id % 4), (lx, ly) = position of this thread's accumulator row inside the M tile.
-template <int N_TILE, int SPLIT, int CL>
+// STAGE: a lane owns one accumulator ROW, so a direct float4 store touches 32 different 128-byte
+// lines per warp instruction (measured: ~7400 clk of epilogue per 128 x 128 tile, and the burst slows
+// the TMA loads of the next tile).  With STAGE each warp writes its 32 rows x 32 columns into a
+// private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by the row: conflict-free) and reads it
+// back so that 8 lanes cover one row: a warp store then touches 4 full lines.
+template <int N_TILE, int SPLIT, int CL, bool STAGE = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, const int quarter, const int lane,
                                               const int lx, const int ly, const int cluster_id, const int n_clusters,
                                               const int cta_rank, const uint32_t tmem_base, const uint32_t tfull0,
-                                              const uint32_t tempty0, int* s_is_last, double (*s_red)[kEpiWarps]) {
+                                              const uint32_t tempty0, int* s_is_last, double (*s_red)[kEpiWarps],
+                                              const int tr_launch = -1, const uint32_t stage_base = 0) {
     constexpr int kAccCols = SPLIT ? 2 * N_TILE : N_TILE;
+    const uint32_t stage_w = stage_base + (uint32_t)ew * 4096u + (uint32_t)lane * 128u;  // this lane's row (write side)
+    const int t_sub = lane >> 3, t_chunk = lane & 7;  // read side: row 4k + t_sub, 16-byte chunk t_chunk
     const int c_begin = (ew >> 2) * (N_TILE / 2), c_end = c_begin + N_TILE / 2;  // this warp's columns
     float s_sum = 0.f, s_sq = 0.f;
     int cur_b = -1;
@@ -309,6 +353,23 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
             ox = mx * 2 + (tc.cls & 1);
         }
         float* orow = p.out + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * p.cout + tc.n0;
+        float* tptr[STAGE ? 8 : 1];  // STAGE: where this lane stores chunk t_chunk of tile rows 4k + t_sub (null = masked)
+        if (STAGE) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int trow = quarter * 32 + 4 * k + t_sub;
+                const int tlx = (p.orient == 0) ? (trow & 7) : (trow >> 3);
+                const int tly = (p.orient == 0) ? (trow >> 3) : (trow & 7);
+                const int my2 = tc.oy0 + tly, mx2 = tc.ox0 + tlx;
+                int oy2 = my2, ox2 = mx2;
+                if (p.out_stride == 2) {
+                    oy2 = my2 * 2 + (tc.cls >> 1);
+                    ox2 = mx2 * 2 + (tc.cls & 1);
+                }
+                const bool ok = (my2 < p.Mh) && (mx2 < p.Mw) && !tc.dummy;
+                tptr[k] = ok ? p.out + (((size_t)tc.b * p.Hout + oy2) * p.Wout + ox2) * p.cout + tc.n0 + t_chunk * 4 : nullptr;
+            }
+        }
         const float* cb = nullptr;
         if (p.cbias != nullptr && valid) {
             int mask = 0;
@@ -368,12 +429,32 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                     }
                     s_sum += (v.x + v.y) + (v.z + v.w);
                     s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                    *reinterpret_cast<float4*>(orow + c + j) = v;
+                    if (STAGE)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_w + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
+                                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                     : "memory");
+                    else
+                        *reinterpret_cast<float4*>(orow + c + j) = v;
                 }
+            }
+            if (STAGE) {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int lrow = 4 * k + t_sub;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(stage_base + (uint32_t)ew * 4096u + (uint32_t)lrow * 128u + (uint32_t)((t_chunk ^ (lrow & 7)) << 4))
+                                 : "memory");
+                    if (tptr[k] != nullptr) *reinterpret_cast<float4*>(tptr[k] + c) = v;
+                }
+                __syncwarp();
             }
         }
         if (p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && local < 512) p.trace[6 * 1024 + 2 * local + 1] = clock64();
     }
+    if (ew == 0 && lane == 0) trace_g(p.trace, tr_launch, 5);
     if (p.do_stats) {
         if (cur_b >= 0) {
             const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
@@ -423,7 +504,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             }
+            // trace: the finalising CTA is the last one to finish its epilogue = the end of the grid's work
+            if (ew == 0 && lane == 0 && p.trace != nullptr) {
+                const long long n = p.trace[9 * kTraceRegion] - 1;  // index of the current launch (CTA 0 bumped it at entry)
+                trace_g(p.trace, (int)n, 8);
+            }
         }
+        if (ew == 0 && lane == 0) trace_g(p.trace, tr_launch, 6);
     }
 }
 
@@ -510,6 +597,8 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast targets them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_trigger();
+    pdl_wait();  // everything above overlapped the previous kernel's tail; its output is read below
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -651,12 +740,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 //   warp 0  A producer (halo ring, a_stages slots)      warp 2  W producer (w_stages slots of T taps)
 //   warp 1  MMA issuer + TMEM allocator                 warps 3-10  epilogue (shared with the kernel above)
 constexpr int kHaloThreads = 96 + 32 * kEpiWarps;
-constexpr int kTraceRegion = 1024, kTraceRegions = 10;
-__device__ __forceinline__ void trace_ev(long long* tr, int region, int idx) {
-    if (tr != nullptr && blockIdx.x == 0 && idx < kTraceRegion) tr[region * kTraceRegion + idx] = clock64();
-}
-
-template <int N_TILE>
+template <int N_TILE, int T>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                          const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
@@ -665,6 +749,11 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     constexpr int kWTapBytes = 2 * N_TILE * kBlockK * 2;  // [W_hi | W_lo] of one tap
 
     extern __shared__ uint8_t smem_raw[];
+    __shared__ int s_launch;  // trace only
+    if (p.trace != nullptr && threadIdx.x == 0) {
+        s_launch = (blockIdx.x == 0) ? (int)atomicAdd((unsigned long long*)&p.trace[9 * kTraceRegion], 1ull) : -1;
+        trace_g(p.trace, s_launch, 0);
+    }
     __shared__ __align__(8) uint64_t a_full_bar[2];
     __shared__ __align__(8) uint64_t a_empty_bar[2];
     __shared__ __align__(8) uint64_t w_full_bar[8];
@@ -681,7 +770,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int chunks_total = p.chunks[0] + p.chunks[1];
-    const int a_stages = p.a_stages, w_stages = p.w_stages, T = p.T;
+    const int a_stages = p.a_stages, w_stages = p.w_stages;
     const uint32_t a_slot_bytes = (uint32_t)p.a_slot_bytes;
     const uint32_t w_slot_bytes = (uint32_t)(T * kWTapBytes);
     const uint32_t w_ring = smem_base + (uint32_t)a_stages * a_slot_bytes;
@@ -723,6 +812,13 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     const uint32_t tmem_base = tmem_base_smem;
     const int n_ctas = gridDim.x;
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 0);
+    const int tr_launch = (p.trace != nullptr) ? s_launch : -1;
+    if (threadIdx.x == 0) trace_g(p.trace, tr_launch, 1);
+    // Programmatic dependent launch: the set-up above and the first weight loads below overlap the
+    // tail of the previous kernel (the weights do not depend on it); every other role waits here.
+    pdl_trigger();
+    if (warp != 2) pdl_wait();
+    if (threadIdx.x == 0) trace_g(p.trace, tr_launch, 2);
 
     if (warp == 0) {
         // =============================== A (halo) producer ===============================
@@ -776,6 +872,9 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
+        // The issue thread is the critical resource (measured: ~80 clk per MMA issue + ~300 clk per
+        // barrier round trip), so the full barrier of the NEXT slot is tested before this slot's MMAs
+        // are issued (its latency hides behind them) and the tap offsets are read before the wait.
         const bool leader = elect_one();
         constexpr uint32_t idesc_wide = make_idesc(2 * N_TILE);
         constexpr uint32_t idesc_n = make_idesc(N_TILE);
@@ -784,13 +883,13 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         const uint64_t lo_adv = (uint64_t)(p.a_rows * 8);                       // hi halo -> lo halo
         int a_stage = 0, w_stage = 0;
         uint32_t a_phase = 0, w_phase = 0;
+        bool a_ready = false, w_ready = false;
         int local = 0;
         int tr_slot = 0, tr_chunk = 0;
         trace_ev(leader ? p.trace : nullptr, 7, 1);
         for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas, ++local) {
             const int cls = (unit / p.units_per_col) / p.n_tiles;
-            const int ntaps = s_ntaps[cls];
-            const int slots_per_chunk = ntaps / T;
+            const int slots_per_chunk = s_ntaps[cls] / T;
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
             mbar_wait(tempty0 + 8u * acc, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -799,17 +898,34 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
             uint32_t accumulate = 0u;
             for (int ch = 0; ch < chunks_total; ++ch) {
-                mbar_wait(afull0 + 8u * a_stage, a_phase);
+                if (!a_ready) mbar_wait(afull0 + 8u * a_stage, a_phase);
+                if (tr_chunk == 0 && leader) trace_g(p.trace, tr_launch, 3);
                 trace_ev(leader ? p.trace : nullptr, 5, tr_chunk++);
                 const uint64_t da_tile = a_desc_hi | (uint64_t)(((smem_base + (uint32_t)a_stage * a_slot_bytes) >> 4) & 0x3FFF);
+                if (++a_stage == a_stages) {
+                    a_stage = 0;
+                    a_phase ^= 1u;
+                }
+                a_ready = mbar_test_wait(afull0 + 8u * a_stage, a_phase);  // next chunk's halo, used next iteration
+                const uint32_t a_done_bar = aempty0 + 8u * (a_stage == 0 ? a_stages - 1 : a_stage - 1);
                 for (int sl = 0; sl < slots_per_chunk; ++sl) {
-                    mbar_wait(wfull0 + 8u * w_stage, w_phase);
+                    int off[T];
+#pragma unroll
+                    for (int t = 0; t < T; ++t) off[t] = s_off[cls][sl * T + t] * 8;
+                    const uint32_t cur = (uint32_t)w_stage;
+                    if (!w_ready) mbar_wait(wfull0 + 8u * cur, w_phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (++w_stage == w_stages) {
+                        w_stage = 0;
+                        w_phase ^= 1u;
+                    }
+                    w_ready = mbar_test_wait(wfull0 + 8u * w_stage, w_phase);  // next slot, used next iteration
                     if (leader) {
                         trace_ev(p.trace, 0, tr_slot);
-                        uint64_t db = make_desc(w_ring + (uint32_t)w_stage * w_slot_bytes);
+                        uint64_t db = make_desc(w_ring + cur * w_slot_bytes);
+#pragma unroll
                         for (int t = 0; t < T; ++t, db += (uint64_t)(kWTapBytes >> 4)) {
-                            const uint64_t da = da_tile + (uint64_t)(s_off[cls][sl * T + t] * 8);
+                            const uint64_t da = da_tile + (uint64_t)off[t];
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t adv = (uint64_t)(k * 2);
@@ -818,38 +934,36 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                                 umma_f16(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);    // A_lo x W_hi
                             }
                         }
-                        umma_commit(wempty0 + 8u * w_stage);
+                        umma_commit(wempty0 + 8u * cur);
                         if (sl == slots_per_chunk - 1) {
-                            umma_commit(aempty0 + 8u * a_stage);
+                            umma_commit(a_done_bar);
                             if (ch == chunks_total - 1) umma_commit(tfull0 + 8u * acc);
                         }
                         trace_ev(p.trace, 1, tr_slot);
                     }
                     ++tr_slot;
                     __syncwarp();
-                    if (++w_stage == w_stages) {
-                        w_stage = 0;
-                        w_phase ^= 1u;
-                    }
-                }
-                if (++a_stage == a_stages) {
-                    a_stage = 0;
-                    a_phase ^= 1u;
                 }
             }
         }
+        if (leader) trace_g(p.trace, tr_launch, 4);
     } else {
         // =============================== epilogue (warps 3..10) ===============================
         const int row = (warp & 3) * 32 + lane;  // M index inside the tile: 8-pixel group = row / 8
         const int lx = (p.orient == 0) ? (row & 7) : (row >> 3);
         const int ly = (p.orient == 0) ? (row >> 3) : (row & 7);
-        epilogue_role<N_TILE, 1, 1>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base, tfull0,
-                                    tempty0, &s_is_last, s_red);
+        if (p.stage_out)
+            epilogue_role<N_TILE, 1, 1, true>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base, tfull0,
+                                              tempty0, &s_is_last, s_red, tr_launch, w_ring + (uint32_t)w_stages * w_slot_bytes);
+        else
+            epilogue_role<N_TILE, 1, 1, false>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base,
+                                               tfull0, tempty0, &s_is_last, s_red, tr_launch);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 2);
+    if (threadIdx.x == 0 && *(volatile int*)&s_is_last >= 0) trace_g(p.trace, tr_launch, 7);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -1074,7 +1188,7 @@ int num_sms() {
 }
 
 template <int N_TILE, int SPLIT, int CL>
-int launch_tc(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+int launch_tc(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
     auto kern = conv_igemm_tcgen05_kernel<N_TILE, SPLIT, CL>;
     if (!attr_set) {
@@ -1091,13 +1205,15 @@ int launch_tc(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->a_map[0][0], plan->a_map[0][1], plan->a_map[1][0],
                                        plan->a_map[1][1], plan->w_map[0], plan->w_map[1], p);
     if (e != cudaSuccess) {
@@ -1109,10 +1225,10 @@ int launch_tc(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
 }
 
 template <int N_TILE>
-int launch_tc_nt(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+int launch_tc_nt(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st) {
     if (plan->cl == 2)
-        return plan->split ? launch_tc<N_TILE, 1, 2>(plan, p, st) : launch_tc<N_TILE, 0, 2>(plan, p, st);
-    return plan->split ? launch_tc<N_TILE, 1, 1>(plan, p, st) : launch_tc<N_TILE, 0, 1>(plan, p, st);
+        return plan->split ? launch_tc<N_TILE, 1, 2>(plan, p, pdl, st) : launch_tc<N_TILE, 0, 2>(plan, p, pdl, st);
+    return plan->split ? launch_tc<N_TILE, 1, 1>(plan, p, pdl, st) : launch_tc<N_TILE, 0, 1>(plan, p, pdl, st);
 }
 
 long long* g_trace_dev = nullptr;
@@ -1128,20 +1244,38 @@ long long* trace_buffer() {
     return g_trace_dev;
 }
 
-template <int N_TILE>
-int launch_halo(const TcPlan* plan, const TcParams& p, cudaStream_t st) {
+// Launch attribute for programmatic dependent launch (MSI_PDL=0 turns it off): the kernel may begin
+// before the previous kernel in the stream has finished; it calls griddepcontrol.wait before
+// touching anything that kernel wrote.  `first` = no kernel precedes it in the forward (memset).
+template <int N_TILE, int T>
+int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_tcgen05_kernel<N_TILE>;
+    auto kern = conv_halo_tcgen05_kernel<N_TILE, T>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(conv_halo_tcgen05_kernel<%d>, %d) failed: %s", N_TILE, kMaxDynSmem,
+            set_error("cudaFuncSetAttribute(conv_halo_tcgen05_kernel<%d,%d>, %d) failed: %s", N_TILE, T, kMaxDynSmem,
                       cudaGetErrorString(e));
             return MSI_ERR_CUDA;
         }
         attr_set = true;
     }
-    kern<<<plan->grid, kHaloThreads, plan->smem_bytes, st>>>(plan->a_map[0][0], plan->a_map[1][0], plan->w_map[0], p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(kHaloThreads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->a_map[0][0], plan->a_map[1][0], plan->w_map[0], p);
+    if (e != cudaSuccess) {
+        set_error("cudaLaunchKernelEx(conv_halo_tcgen05_kernel<%d,%d>, grid %d) failed: %s", N_TILE, T, plan->grid,
+                  cudaGetErrorString(e));
+        return MSI_ERR_CUDA;
+    }
     return MSI_OK;
 }
 
@@ -1176,12 +1310,23 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     p.a_stages = 2;
     const int ntaps = p.taps[0].n;
     p.T = (plan->n_tile == 64) ? ((ntaps % 3 == 0) ? 3 : 2) : 1;
+    {
+        const char* env = getenv("MSI_HALO_T");  // experiment: taps per W slot for the Cout = 64 layers
+        if (env && plan->n_tile == 64 && atoi(env) == 1) p.T = 1;  // measured: 667 clk per tap (issue-thread bound) vs 572 for T = 3
+    }
     if (ntaps % p.T != 0 || p.PS > 256 || p.PF > 256) return MSI_ERR_UNSUPPORTED;
     const int w_slot = p.T * 2 * plan->n_tile * kBlockK * 2;
-    p.w_stages = (kMaxDynSmem - 1024 - p.a_stages * p.a_slot_bytes) / w_slot;
+    const int budget = kMaxDynSmem - 1024 - p.a_stages * p.a_slot_bytes;
+    const int stage_bytes = kEpiWarps * 4096;  // one 32 x 32 float tile per epilogue warp
+    {
+        const char* env = getenv("MSI_CONV_STAGE");
+        const int with = (budget - stage_bytes) / w_slot;
+        p.stage_out = (!(env && atoi(env) == 0) && with >= (p.T == 1 ? 3 : 2)) ? 1 : 0;
+        p.w_stages = p.stage_out ? with : budget / w_slot;
+    }
     if (p.w_stages > 8) p.w_stages = 8;
     if (p.w_stages < 2) return MSI_ERR_UNSUPPORTED;
-    plan->smem_bytes = 1024 + p.a_stages * p.a_slot_bytes + p.w_stages * w_slot;
+    plan->smem_bytes = 1024 + p.a_stages * p.a_slot_bytes + p.w_stages * w_slot + (p.stage_out ? stage_bytes : 0);
     p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
     p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
     if (L.w_lo != L.w_hi + (size_t)L.ncls * L.cout * L.K) return MSI_ERR_UNSUPPORTED;  // one [.. hi|lo ..] buffer
@@ -1196,6 +1341,15 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
 }
 
 }  // namespace
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* env = getenv("MSI_PDL");
+        on = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
 
 int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int precision) {
     TcPlan* plan = new TcPlan();
@@ -1370,7 +1524,7 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
 
 // The caller has zeroed L.partials / L.counter on `st` before this launch (net.cu does one memset
 // for all layers per forward).  On return L.stats holds (mean, rstd) per frame.
-int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
+int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st) {
     TcPlan* plan = reinterpret_cast<TcPlan*>(L.tc_plan);
     if (!plan) {
         set_error("conv_tc_forward: layer %s has no plan", L.scope);
@@ -1394,10 +1548,19 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st) {
         return MSI_ERR_STATE;
     }
     int rc;
-    if (plan->halo)
-        rc = (plan->n_tile == 64) ? launch_halo<64>(plan, p, st) : launch_halo<128>(plan, p, st);
-    else
-        rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, st) : launch_tc_nt<128>(plan, p, st);
+    const bool pdl = after_kernel && pdl_enabled();
+    if (plan->halo) {
+        if (plan->n_tile == 128)
+            rc = launch_halo<128, 1>(plan, p, pdl, st);
+        else if (p.T == 3)
+            rc = launch_halo<64, 3>(plan, p, pdl, st);
+        else if (p.T == 1)
+            rc = launch_halo<64, 1>(plan, p, pdl, st);
+        else
+            rc = launch_halo<64, 2>(plan, p, pdl, st);
+    } else {
+        rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, pdl, st) : launch_tc_nt<128>(plan, p, pdl, st);
+    }
     if (rc != MSI_OK) return rc;
     MSI_LAUNCH_CHECK();
     return MSI_OK;

@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(256)
 ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
                 __half* __restrict__ out_lo) {
+    // programmatic dependent launch: let the next conv kernel set itself up, then wait for the conv
+    // kernel that produced `raw` and `stats` (no-ops when launched without the attribute)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.y;
     const float2 st = stats[b];
     // kLnUnroll groups of 8 elements per thread, all loads issued before the first use
@@ -130,7 +134,7 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
 
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool stats_ready, cudaStream_t st) {
+               bool stats_ready, bool pdl, cudaStream_t st) {
     MSI_CHECK_ARG(C % 8 == 0, "layer_norm: C=%d must be a multiple of 8", C);
     if (!stats_ready) {
         // stand-alone statistics (SIMT back end); the tcgen05 conv kernel produces `stats` itself
@@ -141,8 +145,16 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
         ln_finalize_kernel<<<B, 256, 0, st>>>(partials, np, n_per_sample, stats);
         MSI_LAUNCH_CHECK();
     }
-    ln_apply_kernel<<<dim3(ceil_div(n_per_sample, 256 * 8 * kLnUnroll), B), 256, 0, st>>>(raw, n_per_sample, C, stats, gamma,
-                                                                            beta, out_hi, out_lo);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(n_per_sample, 256 * 8 * kLnUnroll), B);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && stats_ready && pdl_enabled()) ? 1 : 0;
+    MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel, raw, n_per_sample, C, (const float2*)stats, gamma, beta, out_hi, out_lo));
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

@@ -442,8 +442,8 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
             if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i], st));
             if (net->conv_impl == MSI_CONV_SIMT)
                 rc = conv_simt_forward(L, srcs, B, out, st);
-            else
-                rc = conv_tc_forward(L, B, out, st);
+            else  // the first conv follows a memset / copy, every later one follows our own LayerNorm kernel
+                rc = conv_tc_forward(L, B, out, /*after_kernel=*/i > 0 || r > 0, st);
             if (rc != MSI_OK) return rc;
         }
         if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 1], st));
@@ -452,7 +452,7 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
             for (int r = 0; r < conv_runs; ++r) {
                 if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i + 2], st));
                 rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, st);
+                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc, st);
                 if (rc != MSI_OK) return rc;
             }
             if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 3], st));

@@ -106,14 +106,17 @@ int conv_simt_forward(const LayerPlan& L, const ActBuf* srcs, int B, float* out,
 
 int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int precision);
 void conv_tc_plan_destroy(LayerPlan& L);
-int conv_tc_forward(const LayerPlan& L, int B, float* out, cudaStream_t st);
+// after_kernel: the previous operation in the stream is one of this library's kernels that calls
+// griddepcontrol.wait itself, so this launch may use programmatic dependent launch
+int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st);
+bool pdl_enabled();
 int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
 
 // LayerNorm ---------------------------------------------------------------------------------
 int ln_partials_count(long long n_per_sample);
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool stats_ready, cudaStream_t st);
+               bool stats_ready, bool pdl, cudaStream_t st);
 int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st);
 int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
                      cudaStream_t st);

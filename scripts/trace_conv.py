@@ -36,3 +36,20 @@ print("slot: W-empty seen | TMA issued | MMA saw full | MMAs+commit issued | ful
 for i in range(len(full)):
     d = full[i] - full[i - 1] if i else 0
     print(f"{i:3d}: {wemp[i]:7d} {wtma[i]:7d} {full[i]:7d} {comm[i]:7d}   d={d:5d}  lat={full[i]-wtma[i]:5d}  issue={comm[i]-full[i]:4d}")
+
+# ---- launch-to-launch timeline (nanoseconds, %globaltimer) of back-to-back launches of the same layer
+from matryodshka_b200.runtime import profile_net_layers
+buf0 = buf.copy()
+profile_net_layers(eng, (hi, lo), out, reps=1)
+torch.cuda.synchronize()
+n = lib.msi_debug_conv_trace(buf.ctypes.data, buf.size)
+g = buf.reshape(NR, R)[9]
+nl = int(g[0])
+print(f"\n{nl} launches recorded; events per launch (us, relative to the entry of the first listed launch):")
+print("launch: entry | setup done | pdl_wait done | first A full | last MMA issued | epilogue loop done (CTA0) | stats done (CTA0) | CTA0 exit | grid's last CTA finalised")
+base = None
+for i in range(max(0, nl - 6), min(nl, 60)):
+    ev = g[8 + 16 * i: 8 + 16 * i + 9]
+    if base is None:
+        base = ev[0]
+    print(f"{i:3d}: " + "  ".join(f"{(int(x) - int(base)) / 1000.0:8.2f}" if x else "    -   " for x in ev))
