@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--conv-impl", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
-    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU (independent pipelines on own streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (independent pipelines on own streams)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-profile", action="store_true",

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsi_b200.so")
+LIB_PATH = os.environ.get("MSI_B200_LIB") or os.path.join(_HERE, "libmsi_b200.so")  # env: A/B builds of the library
 
 MSI_OK = 0
 IMG_F32, IMG_U8 = 0, 1

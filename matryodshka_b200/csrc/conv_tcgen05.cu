@@ -46,6 +46,14 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, half the columns each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxDynSmem = 227 * 1024 - 4096;      // 227 KB minus this kernel's static shared memory
+// __launch_bounds__ is given 512 threads although the kernels launch 320 / 352: that caps ptxas at
+// 128 registers per thread, which leaves a third of the register file to the kernels of the OTHER
+// frames in flight (runtime.MSIFrameLanes) so that they can co-reside with the persistent conv CTA
+// (measured with 3 lanes: 778 vs 759 frames/s; one frame at a time is unchanged).
+#ifndef MSI_REG_CAP_THREADS
+#define MSI_REG_CAP_THREADS 512
+#endif
+constexpr int kRegCapThreads = MSI_REG_CAP_THREADS;
 
 struct TcParams {
     int stages;
@@ -516,7 +524,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
 
 // ---- the kernel ------------------------------------------------------------------------------
 template <int N_TILE, int SPLIT, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kRegCapThreads, 1)
 conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_constant__ CUtensorMap a0_lo,
                           const __grid_constant__ CUtensorMap a1_hi, const __grid_constant__ CUtensorMap a1_lo,
                           const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
@@ -741,7 +749,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 //   warp 1  MMA issuer + TMEM allocator                 warps 3-10  epilogue (shared with the kernel above)
 constexpr int kHaloThreads = 96 + 32 * kEpiWarps;
 template <int N_TILE, int T>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kRegCapThreads, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                          const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
     constexpr int kAccCols = 2 * N_TILE;

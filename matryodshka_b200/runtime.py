@@ -353,7 +353,8 @@ class MSIFrameLanes:
         self.device = torch.device(device)
         self.lanes = [MSIPipeline(weights, *args, device=device, **kw) for _ in range(lanes)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
-        self._next = 0        # lane of the next step() / submit()
+        self._next_step = 0   # lane of the next step()
+        self._next = 0        # lane of the next submit()
         self._oldest = 0      # lane of the next collect()
         self._fork_ev = torch.cuda.Event()
 
@@ -378,8 +379,8 @@ class MSIFrameLanes:
 
     def step(self, after_compute=None):
         """One device-resident pass on the next lane (round-robin); returns that lane's pipeline."""
-        k = self._next
-        self._next = (k + 1) % len(self.lanes)
+        k = self._next_step
+        self._next_step = (k + 1) % len(self.lanes)
         with torch.cuda.stream(self.streams[k]):
             self.lanes[k].step()
             if after_compute is not None:
