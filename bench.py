@@ -318,6 +318,7 @@ def run_ours(args):
         scopes, conv_ms, ln_ms = ["-"] * n_layers, np.full(n_layers, np.nan), np.full(n_layers, np.nan)
     else:
         scopes, conv_ms, ln_ms, _ = profile_net_layers(pipe.net, (pipe.hi, pipe.lo), pipe.pred, reps=max(3, min(K, 10)))
+    stage_ms = None if args.no_layer_profile else pipe.stage_times(reps=5)
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -350,6 +351,26 @@ def run_ours(args):
             "per_layer_ms": {s: round(float(c), 4) for s, c in zip(scopes, conv_ms)},
             "layernorm_ms_per_step": float(ln_ms.sum()),
         }
+        if not args.no_layer_profile:
+            # the metric's second half: achieved HBM GB/s of the warp (K1) and composite (K5) kernels, and of
+            # the RGBA assembly (K4), on ALGORITHMIC bytes, each kernel timed alone
+            s_out = 2  # the PSV leaves K1 as fp16 hi + fp16 lo = 4 bytes per element, like float32
+            npx = Bp * H * W
+            algo = {"psv_build": 2 * npx * 3 * 4 + npx * 6 * P * 2 * s_out,
+                    "render_composite": npx * 4 * P * 4 + 2 * npx * 3 * 4,
+                    "rgba_assemble": npx * 2 * P * 4 + npx * 6 * P * 2 * s_out + npx * 4 * P * 4}
+            hbm_peak = float(peaks["hbm_gbs"])
+            roofline["hbm_kernels"] = {
+                k: {"ms": stage_ms[k], "algorithmic_bytes": algo[k], "achieved_gbs": algo[k] / (stage_ms[k] * 1e-3) / 1e9,
+                    "frac": algo[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak} for k in algo}
+            wc = (algo["psv_build"] + algo["render_composite"]) / ((stage_ms["psv_build"] + stage_ms["render_composite"]) * 1e-3) / 1e9
+            roofline["warp_plus_composite"] = {"bound": "hbm", "achieved": wc, "peak": hbm_peak, "unit": "GB/s",
+                                               "frac": wc / hbm_peak,
+                                               "note": "K1 + K5 are instruction-issue bound (82 % issue-slot utilisation, "
+                                                       "profiles/r1_v6_geom_ncu_full_summary.csv): the reference's float32 "
+                                                       "coordinate chain is evaluated op for op (IEEE div / sqrt, no FMA) so "
+                                                       "that the validity mask and the sample-index grid match it"}
+            roofline["net_ms_per_step"] = stage_ms["net"]
         if args.no_layer_profile:
             roofline = None
         cpu = None

@@ -194,23 +194,52 @@ class MSIPipeline:
         self.launches_per_step = self.net.launches_per_forward + 3
 
     # -- device-resident step ---------------------------------------------------------------
-    def _enqueue(self):
+    def _stages(self):
+        """The four stage launchers of one step, in order, as (name, callable) pairs."""
         lib = _lib.load()
         B, H, W, P = self.B, self.H, self.W, self.P
         tb = ops.erp_tables(H, W, self.device)
         dt = _lib.IMG_U8 if self.img_dtype == torch.uint8 else _lib.IMG_F32
-        st = stream_ptr()
-        check(lib.msi_psv_build(ptr(self.ref), ptr(self.src), dt, 1, ptr(self.poses), ptr(self.baselines),
-                                ptr(self.depths), *tb.ptrs(), B, H, W, P, None, ptr(self.hi), ptr(self.lo),
-                                self.net.in_c_stride, ptr(self.psv_scratch), self.psv_scratch.numel(), st),
-              "msi_psv_build")
-        self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred)
-        check(lib.msi_rgba_assemble(ptr(self.pred), None, ptr(self.hi), ptr(self.lo), self.net.in_c_stride,
-                                    B, H, W, P, ptr(self.rgba), None, None, st), "msi_rgba_assemble")
-        check(lib.msi_render_composite(ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths),
-                                       *tb.ptrs(), B, H, W, P, ptr(self.out["rgb"]), ptr(self.out["depth"]),
-                                       ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]), st),
-              "msi_render_composite")
+
+        def k1():
+            check(lib.msi_psv_build(ptr(self.ref), ptr(self.src), dt, 1, ptr(self.poses), ptr(self.baselines),
+                                    ptr(self.depths), *tb.ptrs(), B, H, W, P, None, ptr(self.hi), ptr(self.lo),
+                                    self.net.in_c_stride, ptr(self.psv_scratch), self.psv_scratch.numel(), stream_ptr()),
+                  "msi_psv_build")
+
+        def k2():
+            self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred)
+
+        def k4():
+            check(lib.msi_rgba_assemble(ptr(self.pred), None, ptr(self.hi), ptr(self.lo), self.net.in_c_stride,
+                                        B, H, W, P, ptr(self.rgba), None, None, stream_ptr()), "msi_rgba_assemble")
+
+        def k5():
+            check(lib.msi_render_composite(ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths),
+                                           *tb.ptrs(), B, H, W, P, ptr(self.out["rgb"]), ptr(self.out["depth"]),
+                                           ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]), stream_ptr()),
+                  "msi_render_composite")
+
+        return [("psv_build", k1), ("net", k2), ("rgba_assemble", k4), ("render_composite", k5)]
+
+    def _enqueue(self):
+        for _, fn in self._stages():
+            fn()
+
+    def stage_times(self, reps=5):
+        """Milliseconds per launch of each stage, timed alone on the current stream: ``reps`` back-to-back
+        launches between two CUDA events after one warm launch.  (bench.py: HBM roofline of K1 / K4 / K5.)"""
+        out = {}
+        for name, fn in self._stages():
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            out[name] = e0.elapsed_time(e1) / reps
+        return out
 
     def step(self):
         """One pass of the hot path over the resident batch (inputs already in HBM)."""
