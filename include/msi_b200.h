@@ -225,6 +225,21 @@ typedef struct msi_net msi_net;
 
 int msi_net_create(msi_net** net, int H, int W, int c_in, int c_out, int ngf, int max_batch,
                    int conv_impl, int precision);
+
+/* Net variants.
+ * MSI_NET_COORD  nets.msi_coord_train_net (matryodshka/nets.py:471-515): SAME zero padding, one
+ *                |sin(latitude)| coord channel appended to every 3x3 conv input (nets.py:260-270).
+ * MSI_NET_WRAP   nets.msi_train_net (matryodshka/nets.py:387-469): no coord channel; every conv /
+ *                deconv input goes through wrap_pad (nets.py:288-295) = circular padding along the
+ *                width (longitude) and zero padding along the height, then a VALID conv; the
+ *                stride-2 convs therefore pad (1, 1) instead of TF-SAME's (0, 1), and the deconvs
+ *                are wrap_pad(x, 2, 2) + VALID 4x4 s2 cropped [5:-5] (= the SAME deconv taps read
+ *                from the circularly extended input).  tcgen05 back end only.
+ * msi_net_create(...) == msi_net_create_ex(..., MSI_NET_COORD). */
+#define MSI_NET_COORD 0
+#define MSI_NET_WRAP 1
+int msi_net_create_ex(msi_net** net, int H, int W, int c_in, int c_out, int ngf, int max_batch,
+                      int conv_impl, int precision, int variant);
 void msi_net_destroy(msi_net* net);
 size_t msi_net_workspace_bytes(const msi_net* net);
 size_t msi_net_arena_bytes(const msi_net* net);

@@ -16,6 +16,7 @@ MSI_OK = 0
 IMG_F32, IMG_U8 = 0, 1
 CONV_TCGEN05, CONV_SIMT = 0, 1
 PREC_FP16X3, PREC_FP16 = 0, 1
+NET_COORD, NET_WRAP = 0, 1
 ACT_SCALE = 16.0
 ABI_VERSION = 1
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "msi_highres_plane": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "msi_highres_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_net_create": (c_int, [POINTER(c_void_p), _I, _I, _I, _I, _I, _I, _I, _I]),
+    "msi_net_create_ex": (c_int, [POINTER(c_void_p), _I, _I, _I, _I, _I, _I, _I, _I, _I]),
     "msi_net_destroy": (None, [_P]),
     "msi_net_workspace_bytes": (c_size_t, [_P]),
     "msi_net_arena_bytes": (c_size_t, [_P]),

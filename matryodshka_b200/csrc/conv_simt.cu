@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
 }
 
 int conv_simt_forward(const LayerPlan& L, const ActBuf* srcs, int B, float* out, cudaStream_t st) {
+    if (!L.coord || srcs[0].x_pad != 0) {
+        set_error("conv_simt: the wrap-pad net variant is not built for the SIMT back end");
+        return MSI_ERR_UNSUPPORTED;
+    }
     SimtParams p;
     p.nsrc = L.nsrc;
     for (int s = 0; s < 2; ++s) {

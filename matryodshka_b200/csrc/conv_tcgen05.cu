@@ -96,6 +96,14 @@ struct TcParams {
     int w_stages;
     int halo_x0[4], halo_y0[4];  // per class: halo origin relative to the tile origin (min dx, min dy)
     int stage_out;       // 1: the epilogue transposes its tiles through shared memory (coalesced stores)
+    int x_off;           // added to every TMA x coordinate: the wrap padding of the source rows (MSI_NET_WRAP)
+    // MSI_NET_WRAP deconvs: slim.layer_norm sees the FULL output of the VALID transposed conv over the
+    // wrap-padded input, (2H+10) x (2W+10), and only then is it cropped [5:-5] (nets.py:431-436).  The
+    // tiles therefore cover the class grid extended by 3 on every side (grid_off = -3): everything is
+    // computed and counted in the statistics (positions the reference does not have come out as exact
+    // zeros: their inputs are TMA out-of-bounds fill), only the positions inside the crop are stored.
+    int grid_off;
+    int stat_all;
     long long* trace;    // debugging: CTA 0 records clock64() of its pipeline events here (null = off)
 };
 
@@ -274,8 +282,8 @@ __device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int unit, in
     const int tx = r - ty * p.tiles_x;
     t.cls = col / p.n_tiles;
     t.n0 = (col - t.cls * p.n_tiles) * n_tile;
-    t.ox0 = tx * p.BW;
-    t.oy0 = ty * p.BH;
+    t.ox0 = tx * p.BW + p.grid_off;
+    t.oy0 = ty * p.BH + p.grid_off;
     return t;
 }
 
@@ -354,7 +362,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
             cur_b = tc.b;
         }
         const int my = tc.oy0 + ly, mx = tc.ox0 + lx;  // output position inside the class grid
-        const bool valid = (my < p.Mh) && (mx < p.Mw) && !tc.dummy;
+        const bool valid = (my >= 0) && (mx >= 0) && (my < p.Mh) && (mx < p.Mw) && !tc.dummy;  // stored
+        const bool counted = valid || (p.stat_all != 0 && !tc.dummy);                          // computed + in the statistics
         int oy = my, ox = mx;
         if (p.out_stride == 2) {
             oy = my * 2 + (tc.cls >> 1);
@@ -374,7 +383,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                     oy2 = my2 * 2 + (tc.cls >> 1);
                     ox2 = mx2 * 2 + (tc.cls & 1);
                 }
-                const bool ok = (my2 < p.Mh) && (mx2 < p.Mw) && !tc.dummy;
+                const bool ok = (my2 >= 0) && (mx2 >= 0) && (my2 < p.Mh) && (mx2 < p.Mw) && !tc.dummy;
                 tptr[k] = ok ? p.out + (((size_t)tc.b * p.Hout + oy2) * p.Wout + ox2) * p.cout + tc.n0 + t_chunk * 4 : nullptr;
             }
         }
@@ -406,7 +415,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
             }
-            if (valid) {
+            if (counted) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 v;
@@ -441,7 +450,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_w + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
                                      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                                      : "memory");
-                    else
+                    else if (valid)
                         *reinterpret_cast<float4*>(orow + c + j) = v;
                 }
             }
@@ -625,7 +634,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
             const uint32_t so = (CL == 1) ? 0u : (uint32_t)(cta_rank * kWSliceBytes);
             const int n_row = tc.n0 + ((CL == 1) ? 0 : cta_rank * kWSliceRows);
             for (int t = 0; t < ntaps; ++t) {
-                const int cx = bx + s_dx[tc.cls][t];
+                const int cx = bx + s_dx[tc.cls][t] + p.x_off;
                 const int cy = by + s_dy[tc.cls][t];
                 int kk = t * cs_total;
                 for (int ch = 0; ch < chunks_total; ++ch, kk += kBlockK) {
@@ -838,7 +847,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas) {
                 const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
-                const int hx = tc.ox0 + p.halo_x0[tc.cls], hy = tc.oy0 + p.halo_y0[tc.cls];
+                const int hx = tc.ox0 + p.halo_x0[tc.cls] + p.x_off, hy = tc.oy0 + p.halo_y0[tc.cls];
                 const int cf = (p.orient == 0) ? hx : hy, cs = (p.orient == 0) ? hy : hx;
                 for (int ch = 0; ch < chunks_total; ++ch) {
                     mbar_wait(aempty0 + 8u * stage, phase ^ 1u);
@@ -984,7 +993,7 @@ struct PackParams {
     const float* w;
     __half* hi;
     __half* lo;
-    int kind, ncls, cout, K, cs_total, cin_total;
+    int kind, ncls, cout, K, cs_total, cin_total, coord;
     int nsrc, cin[2], cstride[2];
     TapList taps[4];
 };
@@ -1011,7 +1020,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams q) {
         if (q.kind == kDeconv)
             v = q.w[((size_t)wt * q.cout + n) * q.cin_total + c];
         else if (q.kind == kConv)
-            v = q.w[((size_t)wt * (q.cin_total + 1) + c) * q.cout + n];
+            v = q.w[((size_t)wt * (q.cin_total + q.coord) + c) * q.cout + n];
         else
             v = q.w[(size_t)c * q.cout + n];
     }
@@ -1047,7 +1056,7 @@ __global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, in
         if (q.kind == kDeconv)
             v = q.w[((size_t)wt * q.cout + n) * q.cin_total + c];
         else
-            v = q.w[((size_t)wt * (q.cin_total + 1) + c) * q.cout + n];
+            v = q.w[((size_t)wt * (q.cin_total + q.coord) + c) * q.cout + n];
     }
     __half h, l;
     split_half(v * MSI_WEIGHT_SCALE, h, l);
@@ -1291,7 +1300,8 @@ int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st
 // MSI_ERR_UNSUPPORTED when the layer does not fit (the caller then uses the per-tap kernel).
 int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batch) {
     TcParams& p = plan->p;
-    const int c0 = ((p.Mw + 7) / 8) * ((p.Mh + 15) / 16), c1 = ((p.Mw + 15) / 16) * ((p.Mh + 7) / 8);
+    const int ext = -2 * p.grid_off;  // wrap deconv: tiles cover the class grid extended by 3 on every side
+    const int c0 = ((p.Mw + ext + 7) / 8) * ((p.Mh + ext + 15) / 16), c1 = ((p.Mw + ext + 15) / 16) * ((p.Mh + ext + 7) / 8);
     p.orient = (c1 < c0) ? 1 : 0;
     p.BW = p.orient == 0 ? 8 : 16;
     p.BH = p.orient == 0 ? 16 : 8;
@@ -1335,12 +1345,12 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     if (p.w_stages > 8) p.w_stages = 8;
     if (p.w_stages < 2) return MSI_ERR_UNSUPPORTED;
     plan->smem_bytes = 1024 + p.a_stages * p.a_slot_bytes + p.w_stages * w_slot + (p.stage_out ? stage_bytes : 0);
-    p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
-    p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
+    p.tiles_x = (p.Mw + ext + p.BW - 1) / p.BW;
+    p.tiles_y = (p.Mh + ext + p.BH - 1) / p.BH;
     if (L.w_lo != L.w_hi + (size_t)L.ncls * L.cout * L.K) return MSI_ERR_UNSUPPORTED;  // one [.. hi|lo ..] buffer
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s)
-        rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, srcs[s].lo, srcs[s].c_stride, srcs[s].W, srcs[s].H, max_batch,
+        rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, srcs[s].lo, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch,
                              p.orient, p.PF, p.PS);
     if (rc == MSI_OK && L.nsrc == 1) plan->a_map[1][0] = plan->a_map[0][0];
     const int nkb = L.ncls * (p.chunks[0] + p.chunks[1]) * ntaps;
@@ -1372,6 +1382,7 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     }
     p.kind = L.kind;
     p.nsrc = L.nsrc;
+    p.x_off = srcs[0].x_pad;
     p.cs_total = 0;
     for (int s = 0; s < 2; ++s) {
         p.chunks[s] = 0;
@@ -1400,9 +1411,13 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
         p.ncls = 1;
         p.taps[0] = conv_taps(L);
     }
-    pick_tile(p.Mh, p.Mw, p.BH, p.BW);
-    p.tiles_x = (p.Mw + p.BW - 1) / p.BW;
-    p.tiles_y = (p.Mh + p.BH - 1) / p.BH;
+    const bool wrap_deconv = (L.kind == kDeconv) && srcs[0].x_pad > 0;
+    p.grid_off = wrap_deconv ? -3 : 0;
+    p.stat_all = wrap_deconv ? 1 : 0;
+    const int ext = wrap_deconv ? 6 : 0;  // tiles cover [-3, M + 3)
+    pick_tile(p.Mh + ext, p.Mw + ext, p.BH, p.BW);
+    p.tiles_x = (p.Mw + ext + p.BW - 1) / p.BW;
+    p.tiles_y = (p.Mh + ext + p.BH - 1) / p.BH;
     p.n_tiles = L.cout / plan->n_tile;
     // Optional: pair CTAs along M so that each fetches half of the W tile and multicasts it to its
     // peer (MSI_CONV_CLUSTER=2).  Measured on B200 (profiles/): no gain -- 1.100 ms vs 1.087 ms per
@@ -1439,6 +1454,7 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     p.counter = L.counter;
     p.stats = L.stats;
     p.n_per_sample = (double)L.Hout * L.Wout * L.cout;
+    if (wrap_deconv) p.n_per_sample = (double)(L.Hout + 10) * (L.Wout + 10) * L.cout;  // LayerNorm before the crop
 
     {
         const char* env = getenv("MSI_CONV_HALO");
@@ -1458,10 +1474,10 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     }
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s) {
-        rc = encode_act_map(&plan->a_map[s][0], srcs[s].hi, srcs[s].c_stride, srcs[s].W, srcs[s].H, max_batch, p.BW,
+        rc = encode_act_map(&plan->a_map[s][0], srcs[s].hi, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.BW,
                             p.BH, p.in_stride);
         if (rc == MSI_OK)
-            rc = encode_act_map(&plan->a_map[s][1], srcs[s].lo, srcs[s].c_stride, srcs[s].W, srcs[s].H, max_batch,
+            rc = encode_act_map(&plan->a_map[s][1], srcs[s].lo, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch,
                                 p.BW, p.BH, p.in_stride);
     }
     if (rc == MSI_OK && L.nsrc == 1) {
@@ -1508,6 +1524,7 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
     q.cout = L.cout;
     q.K = L.K;
     q.cin_total = L.cin_total;
+    q.coord = L.coord ? 1 : 0;
     q.nsrc = L.nsrc;
     q.cs_total = 0;
     for (int s = 0; s < 2; ++s) {

@@ -83,10 +83,26 @@ ln_finalize_kernel(const double2* __restrict__ partials, int n_partials, long lo
 
 // thread = kLnUnroll x 8 consecutive channels; the raw tensor is read once (streaming load)
 static constexpr int kLnUnroll = 2;
+// Offset (in elements) of element `lin` of a dense [rows, W, C] tensor inside the wrap-padded
+// [rows, W + 2 x_pad, C] layout, and the offsets of its wrap copies (or -1): column x < x_pad is
+// repeated right of the image, column x >= W - x_pad left of it (nets.py:288-295 wrap_pad).
+__device__ __forceinline__ void wrap_offsets(long long lin, int W, int C, int x_pad, long long& main_off, long long& copy_off) {
+    const long long pix = lin / C;
+    const int c = (int)(lin - pix * C);
+    const long long row = pix / W;
+    const int x = (int)(pix - row * W);
+    const long long Wp = W + 2 * x_pad;
+    main_off = (row * Wp + x + x_pad) * C + c;
+    copy_off = -1;
+    if (x < x_pad) copy_off = (row * Wp + x + W + x_pad) * C + c;
+    if (x >= W - x_pad) copy_off = (row * Wp + x - W + x_pad) * C + c;
+}
+
+template <bool WRAP>
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
-                __half* __restrict__ out_lo) {
+                __half* __restrict__ out_lo, int W, int x_pad) {
     // programmatic dependent launch: let the next conv kernel set itself up, then wait for the conv
     // kernel that produced `raw` and `stats` (no-ops when launched without the attribute)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -127,14 +143,25 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
             y = fmaxf(y, 0.f);
             split_half(y * MSI_ACT_SCALE, hi[q], lo[q]);
         }
-        *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        if (!WRAP) {
+            *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        } else {
+            long long m, cp;
+            wrap_offsets((long long)off, W, C, x_pad, m, cp);  // `off` runs over [B * rows, W, C]
+            *reinterpret_cast<uint4*>(out_hi + m) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(out_lo + m) = *reinterpret_cast<const uint4*>(lo);
+            if (cp >= 0) {
+                *reinterpret_cast<uint4*>(out_hi + cp) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(out_lo + cp) = *reinterpret_cast<const uint4*>(lo);
+            }
+        }
     }
 }
 
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool stats_ready, bool pdl, cudaStream_t st) {
+               bool stats_ready, bool pdl, int W, int x_pad, cudaStream_t st) {
     MSI_CHECK_ARG(C % 8 == 0, "layer_norm: C=%d must be a multiple of 8", C);
     if (!stats_ready) {
         // stand-alone statistics (SIMT back end); the tcgen05 conv kernel produces `stats` itself
@@ -154,7 +181,12 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && stats_ready && pdl_enabled()) ? 1 : 0;
-    MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel, raw, n_per_sample, C, (const float2*)stats, gamma, beta, out_hi, out_lo));
+    if (x_pad > 0)
+        MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<true>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
+                                    out_hi, out_lo, W, x_pad));
+    else
+        MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<false>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
+                                    out_hi, out_lo, W, x_pad));
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
@@ -162,37 +194,75 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
 // float32 NHWC [npix, C] -> fp16 hi/lo [npix, c_stride] scaled by MSI_ACT_SCALE (pad channels = 0)
 __global__ void __launch_bounds__(256)
 split_input_kernel(const float* __restrict__ in, long long npix, int C, int c_stride, __half* __restrict__ hi,
-                   __half* __restrict__ lo) {
+                   __half* __restrict__ lo, int W, int x_pad) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= npix * c_stride) return;
     const long long pix = idx / c_stride;
     const int c = (int)(idx % c_stride);
     __half h = __float2half_rn(0.f), l = h;
     if (c < C) split_half(__ldg(in + pix * C + c) * MSI_ACT_SCALE, h, l);
-    hi[idx] = h;
-    lo[idx] = l;
+    if (x_pad == 0) {
+        hi[idx] = h;
+        lo[idx] = l;
+    } else {
+        long long m, cp;
+        wrap_offsets(idx, W, c_stride, x_pad, m, cp);
+        hi[m] = h;
+        lo[m] = l;
+        if (cp >= 0) {
+            hi[cp] = h;
+            lo[cp] = l;
+        }
+    }
 }
 
-int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st) {
-    split_input_kernel<<<ceil_div(npix * c_stride, 256), 256, 0, st>>>(in, npix, C, c_stride, hi, lo);
+int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, int W, int x_pad,
+                cudaStream_t st) {
+    split_input_kernel<<<ceil_div(npix * c_stride, 256), 256, 0, st>>>(in, npix, C, c_stride, hi, lo, W, x_pad);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+__global__ void __launch_bounds__(256)
+wrap_copy_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, long long total, int W, int c_stride,
+                 int x_pad, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    const long long idx = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;  // 8 halves = 16 bytes
+    if (idx >= total) return;
+    long long m, cp;
+    wrap_offsets(idx, W, c_stride, x_pad, m, cp);
+    const uint4 h = *reinterpret_cast<const uint4*>(in_hi + idx), l = *reinterpret_cast<const uint4*>(in_lo + idx);
+    *reinterpret_cast<uint4*>(out_hi + m) = h;
+    *reinterpret_cast<uint4*>(out_lo + m) = l;
+    if (cp >= 0) {
+        *reinterpret_cast<uint4*>(out_hi + cp) = h;
+        *reinterpret_cast<uint4*>(out_lo + cp) = l;
+    }
+}
+
+int wrap_copy(const __half* in_hi, const __half* in_lo, long long rows, int W, int c_stride, int x_pad, __half* out_hi,
+              __half* out_lo, cudaStream_t st) {
+    MSI_CHECK_ARG(c_stride % 8 == 0, "wrap_copy: c_stride=%d must be a multiple of 8", c_stride);
+    const long long total = rows * W * c_stride;
+    wrap_copy_kernel<<<ceil_div(total / 8, 256), 256, 0, st>>>(in_hi, in_lo, total, W, c_stride, x_pad, out_hi, out_lo);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
 
 __global__ void __launch_bounds__(256)
 merge_activation_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long npix, int C,
-                        int c_stride, float* __restrict__ out) {
+                        int c_stride, float* __restrict__ out, int W, int x_pad) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= npix * C) return;
     const long long pix = idx / C;
     const int c = (int)(idx % C);
-    const size_t o = (size_t)pix * c_stride + c;
+    const long long row = pix / W;
+    const size_t o = (size_t)(row * (W + 2 * x_pad) + (pix - row * W) + x_pad) * c_stride + c;
     out[idx] = (__half2float(hi[o]) + __half2float(lo[o])) * (1.0f / MSI_ACT_SCALE);
 }
 
-int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
-                     cudaStream_t st) {
-    merge_activation_kernel<<<ceil_div(npix * C, 256), 256, 0, st>>>(hi, lo, npix, C, c_stride, out);
+int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out, int W,
+                     int x_pad, cudaStream_t st) {
+    merge_activation_kernel<<<ceil_div(npix * C, 256), 256, 0, st>>>(hi, lo, npix, C, c_stride, out, W, x_pad);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

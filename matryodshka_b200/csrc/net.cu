@@ -14,6 +14,7 @@ using namespace msi;
 
 struct msi_net {
     int H, W, c_in, c_out, ngf, max_batch, conv_impl, precision;
+    int variant = MSI_NET_COORD;  // MSI_NET_WRAP: nets.msi_train_net (wrap_pad, no coord channel)
     int in_c_stride;
     std::vector<LayerPlan> layers;
     std::vector<ActBuf> acts;  // acts[0] = network input; acts[i + 1] = output of layer i
@@ -86,7 +87,17 @@ int find_act(const msi_net* net, const char* scope) {
 
 extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, int ngf, int max_batch,
                               int conv_impl, int precision) {
+    return msi_net_create_ex(out, H, W, c_in, c_out, ngf, max_batch, conv_impl, precision, MSI_NET_COORD);
+}
+
+extern "C" int msi_net_create_ex(msi_net** out, int H, int W, int c_in, int c_out, int ngf, int max_batch,
+                                 int conv_impl, int precision, int variant) {
     MSI_CHECK_ARG(out != nullptr, "net_create: null out");
+    MSI_CHECK_ARG(variant == MSI_NET_COORD || variant == MSI_NET_WRAP, "net_create: variant=%d", variant);
+    if (variant == MSI_NET_WRAP && conv_impl != MSI_CONV_TCGEN05) {
+        set_error("net_create: MSI_NET_WRAP (msi_train_net) is built for the tcgen05 back end only");
+        return MSI_ERR_UNSUPPORTED;
+    }
     MSI_CHECK_ARG(H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "net_create: H=%d W=%d must be multiples of 8", H, W);
     MSI_CHECK_ARG(c_in > 0 && c_out > 0 && c_out % 4 == 0, "net_create: bad channels c_in=%d c_out=%d", c_in, c_out);
     MSI_CHECK_ARG(ngf >= 8 && ngf % 8 == 0, "net_create: ngf=%d must be a multiple of 8", ngf);
@@ -108,13 +119,18 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
     net->max_batch = max_batch;
     net->conv_impl = conv_impl;
     net->precision = precision;
+    net->variant = variant;
     net->in_c_stride = (int)align_up((size_t)c_in, 64);
+    // wrap_pad needs 1 column for the 3x3 / deconv taps and 2 for the dilated convs: 2 everywhere
+    const int x_pad = (variant == MSI_NET_WRAP) ? 2 : 0;
 
     net->acts.resize(kNumLayers + 1);
     net->acts[0].H = H;
     net->acts[0].W = W;
     net->acts[0].C = c_in;
     net->acts[0].c_stride = net->in_c_stride;
+    net->acts[0].x_pad = x_pad;
+    net->acts[0].Wp = W + 2 * x_pad;
     net->layers.resize(kNumLayers);
     net->off.resize(kNumLayers);
     net->coord_rows_host.resize(kNumLayers);
@@ -122,9 +138,9 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
     size_t a = 0, w = 0;
     const size_t B = (size_t)max_batch;
     net->in_hi_off = w;
-    w += align_up(B * H * W * net->in_c_stride * sizeof(__half));
+    w += align_up(B * H * (W + 2 * x_pad) * net->in_c_stride * sizeof(__half));
     net->in_lo_off = w;
-    w += align_up(B * H * W * net->in_c_stride * sizeof(__half));
+    w += align_up(B * H * (W + 2 * x_pad) * net->in_c_stride * sizeof(__half));
 
     for (int i = 0; i < kNumLayers; ++i) {
         const ArchRow& r = kArch[i];
@@ -160,14 +176,23 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
             L.Wout = (L.Win + r.stride - 1) / r.stride;
             L.pad_t = same_pad_before(L.Hin, r.k, r.stride, r.rate);
             L.pad_l = same_pad_before(L.Win, r.k, r.stride, r.rate);
+            if (variant == MSI_NET_WRAP && r.kind == kConv) {
+                // wrap_pad(x, rate, rate) + VALID (nets.py:404-423): `rate` rows / columns before, whatever the stride
+                L.pad_t = L.pad_l = r.rate;
+                L.Hout = (L.Hin + 2 * r.rate - ((r.k - 1) * r.rate + 1)) / r.stride + 1;
+                L.Wout = (L.Win + 2 * r.rate - ((r.k - 1) * r.rate + 1)) / r.stride + 1;
+            }
             L.ncls = 1;
         }
+        L.coord = (variant == MSI_NET_COORD);
         L.out_act = i + 1;
         ActBuf& o = net->acts[i + 1];
         o.H = L.Hout;
         o.W = L.Wout;
         o.C = L.cout;
         o.c_stride = L.cout;
+        o.x_pad = x_pad;
+        o.Wp = L.Wout + 2 * x_pad;
 
         // packed reduction length: taps x (sum of source channel strides)
         int cs_total = 0;
@@ -178,7 +203,7 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
         msi_net::Off& f = net->off[i];
         size_t wcount;
         if (r.kind == kConv)
-            wcount = (size_t)r.k * r.k * (L.cin_total + 1) * L.cout;
+            wcount = (size_t)r.k * r.k * (L.cin_total + (L.coord ? 1 : 0)) * L.cout;
         else if (r.kind == kDeconv)
             wcount = (size_t)r.k * r.k * L.cout * L.cin_total;
         else
@@ -205,10 +230,11 @@ extern "C" int msi_net_create(msi_net** out, int H, int W, int c_in, int c_out, 
         if (r.kind != kHead) w += align_up(B * n_per * sizeof(float));
         f.stats = w;
         w += align_up(B * sizeof(float2));
+        const size_t n_act = (size_t)L.Hout * o.Wp * L.cout;  // wrap-padded rows
         f.act_hi = w;
-        if (r.kind != kHead) w += align_up(B * n_per * sizeof(__half));
+        if (r.kind != kHead) w += align_up(B * n_act * sizeof(__half));
         f.act_lo = w;
-        if (r.kind != kHead) w += align_up(B * n_per * sizeof(__half));
+        if (r.kind != kHead) w += align_up(B * n_act * sizeof(__half));
 
         if (r.kind == kConv) {
             // nets.py:262-263: |sin(linspace(-pi/2, pi/2, H))| in float64, cast to float32
@@ -271,7 +297,7 @@ extern "C" int msi_net_bind(msi_net* net, void* workspace, size_t workspace_byte
         L.gamma = (float*)(net->arena + f.gamma);
         L.beta = (float*)(net->arena + f.beta);
         L.bias = (float*)(net->arena + f.bias);
-        L.cbias = (L.kind == kConv) ? (float*)(net->arena + f.cbias) : nullptr;
+        L.cbias = (L.kind == kConv && L.coord) ? (float*)(net->arena + f.cbias) : nullptr;
         L.w_hi = (__half*)(net->arena + f.w_hi);
         L.w_lo = (__half*)(net->arena + f.w_lo);
         L.raw = (L.kind != kHead) ? (float*)(net->ws + f.raw) : nullptr;
@@ -313,7 +339,7 @@ extern "C" int msi_net_load_layer(msi_net* net, const char* scope, const float* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     size_t wcount;
     if (L.kind == kConv)
-        wcount = (size_t)L.k * L.k * (L.cin_total + 1) * L.cout;
+        wcount = (size_t)L.k * L.k * (L.cin_total + (L.coord ? 1 : 0)) * L.cout;
     else if (L.kind == kDeconv)
         wcount = (size_t)L.k * L.k * L.cout * L.cin_total;
     else
@@ -327,7 +353,7 @@ extern "C" int msi_net_load_layer(msi_net* net, const char* scope, const float* 
         MSI_CUDA(cudaMemcpyAsync(L.gamma, gamma, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         MSI_CUDA(cudaMemcpyAsync(L.beta, beta, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    if (L.kind == kConv) {
+    if (L.kind == kConv && L.coord) {
         float* rows_dev = L.cbias + (size_t)L.Hout * 8 * L.cout;
         MSI_CUDA(cudaMemcpyAsync(rows_dev, net->coord_rows_host[i].data(), L.Hin * sizeof(float),
                                  cudaMemcpyHostToDevice, st));
@@ -398,7 +424,7 @@ extern "C" const char* msi_net_layer_scope(const msi_net* net, int i) {
 extern "C" double msi_net_layer_flops(const msi_net* net, int i) {
     if (!net || i < 0 || i >= kNumLayers) return 0.0;
     const LayerPlan& L = net->layers[i];
-    if (L.kind == kConv) return 2.0 * L.Hout * L.Wout * L.cout * (double)(L.cin_total + 1) * L.k * L.k;
+    if (L.kind == kConv) return 2.0 * L.Hout * L.Wout * L.cout * (double)(L.cin_total + (L.coord ? 1 : 0)) * L.k * L.k;
     if (L.kind == kDeconv) return 2.0 * L.Hin * L.Win * (double)L.cin_total * L.cout * L.k * L.k;
     return 2.0 * L.Hout * L.Wout * (double)L.cin_total * L.cout;
 }
@@ -422,7 +448,14 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
     const size_t in_elems = (size_t)B * net->H * net->W * net->in_c_stride;
     if (in_f32) {
         rc = split_input(in_f32, (long long)B * net->H * net->W, net->c_in, net->in_c_stride, net->acts[0].hi,
-                         net->acts[0].lo, st);
+                         net->acts[0].lo, net->W, net->acts[0].x_pad, st);
+        if (rc != MSI_OK) return rc;
+    } else if (net->acts[0].x_pad > 0) {
+        // the caller's operand is dense [B,H,W,c]; the workspace copy carries the wrap columns
+        MSI_CHECK_ARG(in_hi != net->acts[0].hi, "net_forward: the wrap-padded input buffer cannot be the operand itself");
+        rc = wrap_copy(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo),
+                       (long long)B * net->H, net->W, net->in_c_stride, net->acts[0].x_pad, net->acts[0].hi,
+                       net->acts[0].lo, st);
         if (rc != MSI_OK) return rc;
     } else if (in_hi != net->acts[0].hi) {
         // keep the TMA descriptors pointing at the workspace copy of the input
@@ -452,7 +485,8 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
             for (int r = 0; r < conv_runs; ++r) {
                 if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i + 2], st));
                 rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc, st);
+                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc, L.Wout,
+                                net->acts[i + 1].x_pad, st);
                 if (rc != MSI_OK) return rc;
             }
             if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 3], st));
@@ -469,6 +503,10 @@ extern "C" int msi_net_input_buffers(msi_net* net, void** hi, void** lo) {
         set_error("net_input_buffers: call msi_net_bind first");
         return MSI_ERR_STATE;
     }
+    if (net->acts[0].x_pad > 0) {
+        set_error("net_input_buffers: the MSI_NET_WRAP input is stored wrap-padded; pass a dense operand to msi_net_forward");
+        return MSI_ERR_UNSUPPORTED;
+    }
     *hi = net->acts[0].hi;
     *lo = net->acts[0].lo;
     return MSI_OK;
@@ -479,7 +517,7 @@ extern "C" int msi_net_read_activation(msi_net* net, const char* scope, int B, f
     const int ai = find_act(net, scope);
     MSI_CHECK_ARG(ai >= 0 && ai < kNumLayers, "net_read_activation: unknown or un-normalised scope '%s'", scope);
     const ActBuf& a = net->acts[ai];
-    return merge_activation(a.hi, a.lo, (long long)B * a.H * a.W, a.C, a.c_stride, out,
+    return merge_activation(a.hi, a.lo, (long long)B * a.H * a.W, a.C, a.c_stride, out, a.W, a.x_pad,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

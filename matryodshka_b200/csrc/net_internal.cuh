@@ -18,6 +18,10 @@ struct ActBuf {
     __half* hi = nullptr;
     __half* lo = nullptr;
     int H = 0, W = 0, C = 0, c_stride = 0;
+    // MSI_NET_WRAP: rows are stored x_pad pixels wider on both sides (Wp = W + 2 * x_pad) and the pad
+    // columns hold the circular wrap of the row, so a TMA box that leaves the image along x reads the
+    // other side of the panorama while rows above / below the image are still zero-filled
+    int x_pad = 0, Wp = 0;
 };
 
 struct LayerPlan {
@@ -31,6 +35,7 @@ struct LayerPlan {
     int cout;
     int Hin, Win, Hout, Wout;
     int pad_t, pad_l;  // SAME padding before (conv)
+    bool coord = true; // the 3x3 convs take an extra |sin(latitude)| input channel (msi_coord_train_net)
     // arena (parameters)
     float* w_f32 = nullptr;   // TF layout as loaded
     float* gamma = nullptr;
@@ -116,10 +121,15 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
 int ln_partials_count(long long n_per_sample);
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
                double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
-               bool stats_ready, bool pdl, cudaStream_t st);
-int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, cudaStream_t st);
-int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out,
-                     cudaStream_t st);
+               bool stats_ready, bool pdl, int W, int x_pad, cudaStream_t st);
+// W / x_pad: row width and wrap padding of the fp16 tensor (x_pad = 0: dense rows)
+int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, int W, int x_pad,
+                cudaStream_t st);
+int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out, int W,
+                     int x_pad, cudaStream_t st);
+// dense fp16 hi/lo [rows, W, c_stride] -> wrap-padded [rows, W + 2 x_pad, c_stride]
+int wrap_copy(const __half* in_hi, const __half* in_lo, long long rows, int W, int c_stride, int x_pad, __half* out_hi,
+              __half* out_lo, cudaStream_t st);
 int coord_bias_build(const LayerPlan& L, const float* coord_rows_dev, cudaStream_t st);
 
 }  // namespace msi

@@ -137,8 +137,10 @@ class MSI(object):
         if eng is None:
             if self.weights is None:
                 raise _lib.MsiError("MSI.infer_msi needs weights (MSI(weights=...))")
+            # FLAGS.coord_net picks nets.msi_coord_train_net or nets.msi_train_net (msi.py:120-127)
             eng = NetEngine(self.weights, H, W, c_in, c_out, ngf, self.device, max_batch=max_batch,
-                            conv_impl=self.config.conv_impl, precision=self.config.precision)
+                            conv_impl=self.config.conv_impl, precision=self.config.precision,
+                            variant="coord" if self.config.coord_net else "wrap")
             self._engines[key] = eng
         return eng
 
@@ -151,8 +153,8 @@ class MSI(object):
         cfg = self.config
         if which_color_pred != 'blend_psv':
             raise NotImplementedError("only which_color_pred='blend_psv' is built (SURVEY.md 8f-4)")
-        if cfg.input_type != 'ODS' or cfg.operation != 'train' or not cfg.coord_net:
-            raise NotImplementedError("only input_type=ODS, operation=train, coord_net=True is built")
+        if cfg.input_type != 'ODS' or cfg.operation != 'train':
+            raise NotImplementedError("only input_type=ODS, operation=train is built")
         B, H, W, _ = raw_src_image.shape
         P = len(psv_planes)
         if P != num_msi_planes:
@@ -160,7 +162,11 @@ class MSI(object):
         poses = self._sweep_poses(ref_pose, src_pose, ref_pose_inv, jitter_pose_inv)
         baselines = _host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
         eng = self._engine(H, W, 6 * P, 2 * num_msi_planes, ngf, B)
-        hi, lo = eng.input_buffers(B)
+        if cfg.coord_net:
+            hi, lo = eng.input_buffers(B)   # the sweep kernel writes the net's operand in place
+        else:                               # wrap-padded input: dense operand, copied in by the forward
+            hi = torch.zeros((B, H, W, eng.in_c_stride), dtype=torch.float16, device=self.device)
+            lo = torch.zeros_like(hi)
         # preprocessing (msi.py:73-75) is fused into the sweep kernel
         net_input = ops.psv_build(raw_ref_image, raw_src_image, poses, baselines, list(psv_planes),
                                   preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride)

@@ -122,3 +122,18 @@ def msi_coord_train_net(inputs, num_outputs, ngf=64, vscope="net", reuse_weights
         B, H, W, C = inputs.shape
         engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope)
     return engine.forward(inputs)
+
+
+def msi_train_net(inputs, num_outputs, ngf=64, vscope="net", reuse_weights=False, *, weights=None, engine=None):
+    """nets.py:387-469 -- the non-coord net: every conv / deconv input goes through ``wrap_pad``
+    (nets.py:288-295: circular padding along the width, zeros along the height) and a VALID conv;
+    conv weights are ``[3,3,Cin,Cout]`` (no coord channel).  Same calling convention as
+    ``msi_coord_train_net`` above."""
+    from .runtime import NetEngine
+
+    if engine is None:
+        if weights is None:
+            raise ValueError("msi_train_net needs weights= (TF-named dict) or engine=")
+        B, H, W, C = inputs.shape
+        engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope, variant="wrap")
+    return engine.forward(inputs)

@@ -22,6 +22,7 @@ from .nets import ARCH
 
 _CONV_IMPL = {"tcgen05": _lib.CONV_TCGEN05, "simt": _lib.CONV_SIMT}
 _PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16}
+_VARIANT = {"coord": _lib.NET_COORD, "wrap": _lib.NET_WRAP}
 
 
 def _aligned_bytes(n, device):
@@ -32,7 +33,8 @@ def _aligned_bytes(n, device):
 
 
 class NetEngine:
-    """nets.msi_coord_train_net (nets.py:471-515) on the GPU.
+    """nets.msi_coord_train_net (nets.py:471-515; ``variant="coord"``) or nets.msi_train_net
+    (nets.py:387-469: no coord channel, circular-x / zero-y ``wrap_pad``; ``variant="wrap"``) on the GPU.
 
     weights: dict keyed by the TF checkpoint variable names (``net/<scope>/weights`` ...),
     NumPy arrays or tensors in the TF layouts."""
@@ -40,17 +42,19 @@ class NetEngine:
     _cache: Dict[tuple, "NetEngine"] = {}
 
     def __init__(self, weights, H, W, c_in, c_out, ngf=64, device="cuda", max_batch=1,
-                 conv_impl="tcgen05", precision="fp16x3", vscope="net"):
+                 conv_impl="tcgen05", precision="fp16x3", vscope="net", variant="coord"):
         _lib.require_cuda()
         self.lib = _lib.load()
+        self.variant = variant
         self.device = torch.device(device)
         self.H, self.W, self.c_in, self.c_out, self.ngf = H, W, c_in, c_out, ngf
         self.max_batch = max_batch
         self.conv_impl, self.precision = conv_impl, precision
         self._h = c_void_p()
         with torch.cuda.device(self.device):
-            check(self.lib.msi_net_create(ctypes.byref(self._h), H, W, c_in, c_out, ngf, max_batch,
-                                          _CONV_IMPL[conv_impl], _PRECISION[precision]), "msi_net_create")
+            check(self.lib.msi_net_create_ex(ctypes.byref(self._h), H, W, c_in, c_out, ngf, max_batch,
+                                             _CONV_IMPL[conv_impl], _PRECISION[precision], _VARIANT[variant]),
+                  "msi_net_create_ex")
             self.ws_bytes = int(self.lib.msi_net_workspace_bytes(self._h))
             self.arena_bytes = int(self.lib.msi_net_arena_bytes(self._h))
             self._ws, wo = _aligned_bytes(self.ws_bytes, self.device)

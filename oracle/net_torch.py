@@ -200,9 +200,11 @@ def msi_coord_train_net(inputs, num_outputs, weights, ngf=64, dtype=torch.float3
     return pred
 
 
-def msi_train_net(inputs, num_outputs, weights, ngf=64, dtype=torch.float32):
+def msi_train_net(inputs, num_outputs, weights, ngf=64, dtype=torch.float32, return_feats=False):
     """nets.py:387-441: the non-coord variant -- circular-x / zero-y padding
-    (wrap_pad) + VALID convs; deconvs on wrap_pad(skip, 2, 2) cropped [5:-5]."""
+    (wrap_pad) + VALID convs; deconvs on wrap_pad(skip, 2, 2) cropped [5:-5].  Note the order in the
+    reference (nets.py:431-436): slim.layer_norm runs inside conv2d_transpose on the FULL
+    (2H+10) x (2W+10) output and the crop comes after it, so the statistics include the border."""
     x = inputs.to(dtype)
 
     def conv(x, scope, stride=1, rate=1):
@@ -240,7 +242,12 @@ def msi_train_net(inputs, num_outputs, weights, ngf=64, dtype=torch.float32):
     c82 = conv(c81, "conv8_2")
     w = _t(weights, "net/color_pred/weights", dtype)
     b = _t(weights, "net/color_pred/biases", dtype)
-    return torch.tanh(conv2d_same(c82, w, bias=b))
+    pred = torch.tanh(conv2d_same(c82, w, bias=b))
+    if return_feats:
+        return pred, {"conv1_1": c11, "conv1_2": c12, "conv2_1": c21, "conv2_2": c22, "conv3_1": c31, "conv3_2": c32,
+                      "conv3_3": c33, "conv4_1": c41, "conv4_2": c42, "conv4_3": c43, "conv6_1": c61, "conv6_2": c62,
+                      "conv6_3": c63, "conv7_1": c71, "conv7_2": c72, "conv8_1": c81, "conv8_2": c82}
+    return pred
 
 
 def net_gflop(H, W, num_inputs, num_outputs, ngf=64, coord=True):

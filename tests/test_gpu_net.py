@@ -254,3 +254,52 @@ def test_streaming_submit_collect_matches_step():
     from matryodshka_b200._lib import MsiError
     with pytest.raises(MsiError):
         pipe.collect()
+
+
+@pytest.mark.parametrize("H,W,B", [(32, 64, 1), (24, 72, 2), (64, 128, 1)])
+def test_train_net_wrap_pad_matches_oracle(H, W, B):
+    """nets.msi_train_net (nets.py:387-469, MSI_NET_WRAP): no coord channel, circular-x / zero-y
+    wrap_pad + VALID convs, stride-2 convs padded (1, 1), deconvs on wrap_pad(x, 2, 2) cropped [5:-5].
+    Every layer's activation and the head against the oracle restatement; an input whose left and
+    right image borders differ strongly makes a zero-padded (SAME) evaluation fail this test."""
+    P, ngf = 32, 64
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    x[:, :, :2, :] += 1.5   # the wrap columns matter
+    x[:, :, -2:, :] -= 1.5
+    wts = synth.net_weights(6 * P, 2 * P, ngf, coord=False)
+    eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, variant="wrap")
+    pred = eng.forward(_t(x)).cpu().numpy()
+    with torch.no_grad():
+        want, feats = net_torch.msi_train_net(torch.from_numpy(x), 2 * P, wts, ngf=ngf, return_feats=True)
+    worst = {s: float(np.abs(eng.read_activation(s, B).cpu().numpy() - f.numpy()).max()) for s, f in feats.items()}
+    err = float(np.abs(pred - want.numpy()).max())
+    assert err < TOL, (err, worst)
+    assert max(worst.values()) < TOL, worst
+
+
+def test_infer_msi_with_train_net(monkeypatch):
+    """MSI.infer_msi with FLAGS.coord_net = False (msi.py:120-127 picks nets.msi_train_net) against the oracle."""
+    H, W, P, ngf = 32, 64, 32, 64
+    ref, src = synth.ods_pair(1, H, W)
+    wts = synth.net_weights(6 * P, 2 * P, ngf, coord=False)
+    m = MSI(weights=wts, config=MSIConfig(coord_net=False), device=DEV)
+    planes = m.inv_depths(1, 100, P)
+    out, net_input = m.infer_msi(_t(src), _t(ref), None, None, _t(synth.identity_poses(1)), _t(synth.identity_poses(1)),
+                                 _t(synth.intrinsics(1)), 'blend_psv', P, planes, ngf=ngf)
+    x = msi_np.format_network_input(ref * 2 - 1, src * 2 - 1, synth.identity_poses(1), synth.identity_poses(1), planes,
+                                    synth.intrinsics(1))
+    with torch.no_grad():
+        pred = net_torch.msi_train_net(torch.from_numpy(x), 2 * P, wts, ngf=ngf).numpy()
+    want = msi_np.rgba_layers_blend_psv(pred, x, P) if hasattr(msi_np, "rgba_layers_blend_psv") else None
+    assert float(np.abs(net_input.cpu().numpy() - x).max()) < TOL
+    if want is not None:
+        assert float(np.abs(out['rgba_layers'].cpu().numpy() - want).max()) < TOL
+    else:
+        bw = (pred[..., :P] + 1) / 2
+        al = (pred[..., P:] + 1) / 2
+        fg = x[..., :3 * P].reshape(1, H, W, P, 3)
+        bg = x[..., 3 * P:].reshape(1, H, W, P, 3)
+        rgb = bw[..., None] * fg + (1 - bw[..., None]) * bg
+        want = np.concatenate([rgb, al[..., None]], axis=-1)
+        assert float(np.abs(out['rgba_layers'].cpu().numpy() - want).max()) < TOL

@@ -99,7 +99,7 @@ def test_sweep_pose_composition():
 
 
 def test_infer_msi_rejects_unbuilt_modes():
-    m = MSI(weights={}, config=MSIConfig(coord_net=False))
+    m = MSI(weights={}, config=MSIConfig(input_type='PP'))  # perspective input: not built (coord_net=False is)
     with pytest.raises(NotImplementedError):
         m.infer_msi(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), None, None, np.eye(4)[None], np.eye(4)[None],
                     synth.intrinsics(1), "blend_psv", 2, [2.0, 1.0])
