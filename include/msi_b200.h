@@ -110,6 +110,21 @@ int msi_rgba_assemble(const float* pred, const float* psv_f32, const void* psv_h
                       int c_stride, int B, int H, int W, int L,
                       float* rgba, float* blend_weights, float* alphas, void* stream);
 
+/* The other colour-prediction schemes of infer_msi (matryodshka/msi.py:107-116, 166-273).  pred has
+ * n_pred channels per pixel:
+ *   MSI_COLOR_BLEND_PSV     2L     [w | alpha]                      msi.py:117-147 (= msi_rgba_assemble)
+ *   MSI_COLOR_BLEND_BG      2L+3   [w | alpha | bg rgb]             msi.py:166-190
+ *   MSI_COLOR_BLEND_BG_PSV  3L+3   [w | alpha | bg_w | bg rgb]      msi.py:209-247
+ *   MSI_COLOR_ALPHA_ONLY    L      [alpha], rgb = reference-eye PSV  msi.py:249-268
+ * blend_weights / alphas / bg_blend_weights [B,H,W,L] are optional outputs (msi.py:276-286). */
+#define MSI_COLOR_BLEND_PSV 0
+#define MSI_COLOR_BLEND_BG 1
+#define MSI_COLOR_BLEND_BG_PSV 2
+#define MSI_COLOR_ALPHA_ONLY 3
+int msi_rgba_assemble_ex(const float* pred, int n_pred, const float* psv_f32, const void* psv_hi, const void* psv_lo,
+                         int c_stride, int B, int H, int W, int L, int mode, float* rgba, float* blend_weights,
+                         float* alphas, float* bg_blend_weights, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Stage 3 -- reproject the L spheres to the target position and over-composite
  * replaces: MSI.msi_render_equirect_view (msi.py:407-429) and

@@ -17,6 +17,7 @@ IMG_F32, IMG_U8 = 0, 1
 CONV_TCGEN05, CONV_SIMT = 0, 1
 PREC_FP16X3, PREC_FP16 = 0, 1
 NET_COORD, NET_WRAP = 0, 1
+COLOR_MODES = {"blend_psv": 0, "blend_bg": 1, "blend_bg_psv": 2, "alpha_only": 3}
 ACT_SCALE = 16.0
 ABI_VERSION = 1
 
@@ -32,6 +33,7 @@ SIGNATURES = {
     "msi_psv_scratch_bytes": (c_size_t, [_I, _I, _I]),
     "msi_sweep_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_rgba_assemble": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "msi_rgba_assemble_ex": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "msi_render_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "msi_render_ods": (c_int, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_intersect_sphere_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),

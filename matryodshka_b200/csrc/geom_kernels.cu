@@ -635,6 +635,92 @@ extern "C" int msi_rgba_assemble(const float* pred, const float* psv_f32, const 
     return MSI_OK;
 }
 
+// The other `which_color_pred` schemes of infer_msi (matryodshka/msi.py:166-273).  pred has n_pred
+// channels per pixel: blend_bg [w(L) | alpha(L) | bg rgb(3)], blend_bg_psv [w(L) | alpha(L) | bg_w(L) |
+// bg rgb(3)], alpha_only [alpha(L)].  Same op order as the reference's elementwise graph (no FMA).
+__global__ void __launch_bounds__(256)
+rgba_assemble_ex_kernel(const float* __restrict__ pred, int n_pred, const float* __restrict__ psv_f32,
+                        const __half* __restrict__ psv_hi, const __half* __restrict__ psv_lo, int c_stride,
+                        long long npix, int L, int mode, float4* __restrict__ rgba, float* __restrict__ bw_out,
+                        float* __restrict__ al_out, float* __restrict__ bgw_out) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= npix * L) return;
+    const long long pix = idx / L;
+    const int l = (int)(idx % L);
+    const float* pp = pred + pix * n_pred;
+    float fg[3], bg[3];
+    if (psv_f32 != nullptr) {
+        const float* f = psv_f32 + pix * 6 * L + 3 * l;
+        const float* g = psv_f32 + pix * 6 * L + 3 * (L + l);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            fg[c] = __ldg(f + c);
+            bg[c] = __ldg(g + c);
+        }
+    } else {
+        const size_t f = (size_t)pix * c_stride + 3 * l;
+        const size_t g = (size_t)pix * c_stride + 3 * (L + l);
+        const float inv = 1.0f / MSI_ACT_SCALE;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            fg[c] = (__half2float(psv_hi[f + c]) + __half2float(psv_lo[f + c])) * inv;
+            bg[c] = (__half2float(psv_hi[g + c]) + __half2float(psv_lo[g + c])) * inv;
+        }
+    }
+    float4 o;
+    float w = 0.f, al, bgw = 0.f;
+    if (mode == MSI_COLOR_ALPHA_ONLY) {  // msi.py:251-267
+        al = (__ldg(pp + l) + 1.0f) / 2.0f;
+        o.x = fg[0];
+        o.y = fg[1];
+        o.z = fg[2];
+    } else {
+        w = (__ldg(pp + l) + 1.0f) / 2.0f;
+        al = (__ldg(pp + L + l) + 1.0f) / 2.0f;
+        const float omw = 1.0f - w;
+        if (mode == MSI_COLOR_BLEND_BG) {  // msi.py:166-190: blend the reference PSV with ONE predicted background
+            const float* b3 = pp + 2 * L;
+            o.x = w * fg[0] + omw * __ldg(b3 + 0);
+            o.y = w * fg[1] + omw * __ldg(b3 + 1);
+            o.z = w * fg[2] + omw * __ldg(b3 + 2);
+        } else {  // MSI_COLOR_BLEND_BG_PSV, msi.py:209-247: blend both PSVs, then with the predicted background
+            bgw = (__ldg(pp + 2 * L + l) + 1.0f) / 2.0f;
+            const float ombg = 1.0f - bgw;
+            const float* b3 = pp + 3 * L;
+            o.x = bgw * (w * fg[0] + omw * bg[0]) + ombg * __ldg(b3 + 0);
+            o.y = bgw * (w * fg[1] + omw * bg[1]) + ombg * __ldg(b3 + 1);
+            o.z = bgw * (w * fg[2] + omw * bg[2]) + ombg * __ldg(b3 + 2);
+        }
+    }
+    o.w = al;
+    rgba[idx] = o;
+    if (bw_out != nullptr) bw_out[idx] = w;
+    if (al_out != nullptr) al_out[idx] = al;
+    if (bgw_out != nullptr) bgw_out[idx] = bgw;
+}
+
+extern "C" int msi_rgba_assemble_ex(const float* pred, int n_pred, const float* psv_f32, const void* psv_hi,
+                                    const void* psv_lo, int c_stride, int B, int H, int W, int L, int mode, float* rgba,
+                                    float* blend_weights, float* alphas, float* bg_blend_weights, void* stream) {
+    if (mode == MSI_COLOR_BLEND_PSV) {
+        MSI_CHECK_ARG(n_pred == 2 * L, "rgba_assemble_ex: blend_psv needs n_pred == 2L (got %d, L=%d)", n_pred, L);
+        return msi_rgba_assemble(pred, psv_f32, psv_hi, psv_lo, c_stride, B, H, W, L, rgba, blend_weights, alphas, stream);
+    }
+    MSI_CHECK_ARG(B > 0 && H > 0 && W > 0 && L > 0, "rgba_assemble_ex: bad shape");
+    MSI_CHECK_ARG(pred && rgba, "rgba_assemble_ex: null pred/rgba");
+    MSI_CHECK_ARG(psv_f32 || (psv_hi && psv_lo), "rgba_assemble_ex: need psv_f32 or the hi/lo pair");
+    const int need = mode == MSI_COLOR_BLEND_BG ? 2 * L + 3 : mode == MSI_COLOR_BLEND_BG_PSV ? 3 * L + 3 : mode == MSI_COLOR_ALPHA_ONLY ? L : -1;
+    MSI_CHECK_ARG(need > 0, "rgba_assemble_ex: unknown mode %d", mode);
+    MSI_CHECK_ARG(n_pred == need, "rgba_assemble_ex: mode %d needs %d prediction channels, got %d", mode, need, n_pred);
+    if (!psv_f32) MSI_CHECK_ARG(c_stride >= 6 * L, "rgba_assemble_ex: c_stride %d < 6L", c_stride);
+    const long long npix = (long long)B * H * W;
+    rgba_assemble_ex_kernel<<<ceil_div(npix * L, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        pred, n_pred, psv_f32, reinterpret_cast<const __half*>(psv_hi), reinterpret_cast<const __half*>(psv_lo), c_stride,
+        npix, L, mode, reinterpret_cast<float4*>(rgba), blend_weights, alphas, bg_blend_weights);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
 static int fill_render_params(RenderParams& p, const float* rgba, const float* pose_rt, const float* tgt_pos,
                               const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
                               const float* sin_t, int B, int H, int W, int L) {

@@ -151,8 +151,9 @@ class MSI(object):
         with pred['rgba_layers'] [B,H,W,L,4] always and 'blend_weights' / 'alphas' / 'psv' when the
         substring is in ``extra_outputs`` (msi.py:276-288)."""
         cfg = self.config
-        if which_color_pred != 'blend_psv':
-            raise NotImplementedError("only which_color_pred='blend_psv' is built (SURVEY.md 8f-4)")
+        if which_color_pred not in ('blend_psv', 'blend_bg', 'blend_bg_psv', 'alpha_only'):
+            raise NotImplementedError("which_color_pred=%r (msi.py:107-116 has blend_psv, blend_bg, blend_bg_psv, "
+                                      "alpha_only)" % (which_color_pred,))
         if cfg.input_type != 'ODS' or cfg.operation != 'train':
             raise NotImplementedError("only input_type=ODS, operation=train is built")
         B, H, W, _ = raw_src_image.shape
@@ -161,7 +162,7 @@ class MSI(object):
             raise ValueError("blend_psv needs len(psv_planes) == num_msi_planes")
         poses = self._sweep_poses(ref_pose, src_pose, ref_pose_inv, jitter_pose_inv)
         baselines = _host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
-        eng = self._engine(H, W, 6 * P, 2 * num_msi_planes, ngf, B)
+        eng = self._engine(H, W, 6 * P, ops.color_pred_channels(which_color_pred, num_msi_planes), ngf, B)
         if cfg.coord_net:
             hi, lo = eng.input_buffers(B)   # the sweep kernel writes the net's operand in place
         else:                               # wrap-padded input: dense operand, copied in by the forward
@@ -175,10 +176,17 @@ class MSI(object):
             return None
         msi_pred = eng.forward(hi_lo=(hi, lo))
         want_w = ('blend_weights' in extra_outputs) or ('alpha' in extra_outputs)
-        rgba, bw, al = ops.rgba_assemble(msi_pred, net_input, want_weights=want_w)
+        bgw = None
+        if which_color_pred == 'blend_psv':
+            rgba, bw, al = ops.rgba_assemble(msi_pred, net_input, want_weights=want_w)
+        else:
+            rgba, bw, al, bgw = ops.rgba_assemble_ex(msi_pred, net_input, which_color_pred, num_msi_planes,
+                                                     want_weights=want_w)
         pred = {'rgba_layers': rgba}
         if 'blend_weights' in extra_outputs and 'blend' in which_color_pred:
             pred['blend_weights'] = bw
+            if bgw is not None:   # msi.py:281-282 (the reference names it for every 'bg' scheme; only blend_bg_psv defines it)
+                pred['bg_blend_weights'] = bgw
         if 'alpha' in extra_outputs:
             pred['alphas'] = al
         if 'psv' in extra_outputs:

@@ -128,6 +128,33 @@ def sweep_coords(poses, baselines, depths, B, H, W, device):
     return uv, valid
 
 
+def color_pred_channels(which_color_pred, num_msi_planes):
+    """Output channels of the net for a colour-prediction scheme (msi.py:107-116)."""
+    L = num_msi_planes
+    return {"blend_psv": 2 * L, "blend_bg": 2 * L + 3, "blend_bg_psv": 3 * L + 3, "alpha_only": L}[which_color_pred]
+
+
+def rgba_assemble_ex(pred, psv, which_color_pred, num_msi_planes, *, want_weights=False):
+    """msi_rgba_assemble_ex: RGBA layers for any `which_color_pred` (msi.py:117-268).  pred
+    [B,H,W,n_pred]; psv float32 [B,H,W,6L].  Returns (rgba, blend_weights, alphas, bg_blend_weights)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, n_pred = pred.shape
+    L = num_msi_planes
+    assert n_pred == color_pred_channels(which_color_pred, L), (n_pred, which_color_pred, L)
+    assert psv.shape[-1] == 6 * L, "the colour schemes need num_psv_planes == num_msi_planes"
+    dev = pred.device
+    mk = lambda: torch.empty((B, H, W, L), dtype=torch.float32, device=dev)
+    rgba = torch.empty((B, H, W, L, 4), dtype=torch.float32, device=dev)
+    bw = mk() if want_weights and which_color_pred != "alpha_only" else None
+    al = mk() if want_weights else None
+    bgw = mk() if want_weights and which_color_pred == "blend_bg_psv" else None
+    check(lib.msi_rgba_assemble_ex(ptr(pred.contiguous()), n_pred, ptr(psv.contiguous()), None, None, 6 * L, B, H, W, L,
+                                   _lib.COLOR_MODES[which_color_pred], ptr(rgba), ptr(bw), ptr(al), ptr(bgw),
+                                   stream_ptr()), "msi_rgba_assemble_ex")
+    return rgba, bw, al, bgw
+
+
 def rgba_assemble(pred, psv=None, *, hi_lo=None, c_stride=None, want_weights=False):
     """msi_rgba_assemble.  pred [B,H,W,2L]; psv float32 [B,H,W,6L] or the fp16 (hi, lo) pair.
     Returns (rgba [B,H,W,L,4], blend_weights | None, alphas | None)."""

@@ -48,11 +48,14 @@ class NetEngine:
         self.variant = variant
         self.device = torch.device(device)
         self.H, self.W, self.c_in, self.c_out, self.ngf = H, W, c_in, c_out, ngf
+        # the tensor-core kernels tile Cout in 64s: a head with 2L+3 / 3L+3 / L outputs (blend_bg,
+        # blend_bg_psv, alpha_only) is padded with zero weights and the extra channels are dropped
+        self.c_out_eng = -(-c_out // 64) * 64 if conv_impl == "tcgen05" else c_out
         self.max_batch = max_batch
         self.conv_impl, self.precision = conv_impl, precision
         self._h = c_void_p()
         with torch.cuda.device(self.device):
-            check(self.lib.msi_net_create_ex(ctypes.byref(self._h), H, W, c_in, c_out, ngf, max_batch,
+            check(self.lib.msi_net_create_ex(ctypes.byref(self._h), H, W, c_in, self.c_out_eng, ngf, max_batch,
                                              _CONV_IMPL[conv_impl], _PRECISION[precision], _VARIANT[variant]),
                   "msi_net_create_ex")
             self.ws_bytes = int(self.lib.msi_net_workspace_bytes(self._h))
@@ -91,6 +94,10 @@ class NetEngine:
             g = dev(f"{vscope}/{l.scope}/LayerNorm/gamma")
             b = dev(f"{vscope}/{l.scope}/LayerNorm/beta")
             bias = dev(f"{vscope}/{l.scope}/biases")
+            if l.scope == "color_pred" and self.c_out_eng != self.c_out:
+                pad = self.c_out_eng - self.c_out
+                w = torch.nn.functional.pad(w, (0, pad)).contiguous()        # [1,1,Cin,c_out] -> zero output channels
+                bias = torch.nn.functional.pad(bias, (0, pad)).contiguous()
             keep += [w, g, b, bias]
             check(self.lib.msi_net_load_layer(self._h, l.scope.encode(), ptr(w), ptr(g), ptr(b), ptr(bias),
                                               stream_ptr()), f"msi_net_load_layer({l.scope})")
@@ -115,12 +122,12 @@ class NetEngine:
             psv = psv.contiguous()
         else:
             B = hi_lo[0].shape[0]
-        if out is None:
-            out = torch.empty((B, self.H, self.W, self.c_out), dtype=torch.float32, device=self.device)
+        if out is None or out.shape[-1] != self.c_out_eng:
+            out = torch.empty((B, self.H, self.W, self.c_out_eng), dtype=torch.float32, device=self.device)
         hi, lo = hi_lo if hi_lo is not None else (None, None)
         check(self.lib.msi_net_forward(self._h, ptr(psv), ptr(hi), ptr(lo), B, ptr(out), stream_ptr()),
               "msi_net_forward")
-        return out
+        return out if self.c_out_eng == self.c_out else out[..., :self.c_out]
 
     def read_activation(self, scope, B=1):
         from .nets import layer_channels, layer_geometry

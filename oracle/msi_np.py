@@ -125,8 +125,56 @@ def assemble_rgba(msi_pred, net_input, num_msi_planes, dt=F32):
     return rgba_layers, blend_weights, alphas
 
 
+def color_pred_channels(which_color_pred, L):
+    """msi.py:107-116."""
+    return {"blend_psv": 2 * L, "blend_bg": 2 * L + 3, "blend_bg_psv": 3 * L + 3, "alpha_only": L}[which_color_pred]
+
+
+def assemble_rgba_ex(msi_pred, net_input, num_msi_planes, which_color_pred, dt=F32):
+    """msi.py:117-268: RGBA layers for every `which_color_pred`.  Returns (rgba_layers,
+    blend_weights | None, alphas, bg_blend_weights | None)."""
+    L = num_msi_planes
+    if which_color_pred == "blend_psv":
+        r, bw, al = assemble_rgba(msi_pred, net_input, L, dt)
+        return r, bw, al, None
+    msi_pred = np.asarray(msi_pred, dtype=dt)
+    net_input = np.asarray(net_input, dtype=dt)
+    one, two = dt(1.0), dt(2.0)
+    blend_weights = bg_blend_weights = None
+    layers = []
+    if which_color_pred == "blend_bg":          # msi.py:166-190
+        blend_weights = (msi_pred[..., :L] + one) / two
+        alphas = (msi_pred[..., L:2 * L] + one) / two
+        bg_rgb = msi_pred[..., -3:]
+        for i in range(L):
+            fg_rgb = net_input[..., i * 3:(1 + i) * 3]
+            w = blend_weights[..., i][..., None]
+            curr_rgb = w * fg_rgb + (one - w) * bg_rgb
+            layers.append(np.concatenate([curr_rgb, alphas[..., i][..., None]], axis=3))
+    elif which_color_pred == "blend_bg_psv":    # msi.py:209-247
+        blend_weights = (msi_pred[..., :L] + one) / two
+        bg_blend_weights = (msi_pred[..., 2 * L:3 * L] + one) / two
+        alphas = (msi_pred[..., L:2 * L] + one) / two
+        pred_bg = msi_pred[..., -3:]
+        for i in range(L):
+            fg_rgb = net_input[..., i * 3:(1 + i) * 3]
+            bg_rgb = net_input[..., (L + i) * 3:(L + 1 + i) * 3]
+            w = blend_weights[..., i][..., None]
+            curr_rgb = w * fg_rgb + (one - w) * bg_rgb
+            bg_w = bg_blend_weights[..., i][..., None]
+            curr_rgb = bg_w * curr_rgb + (one - bg_w) * pred_bg
+            layers.append(np.concatenate([curr_rgb, alphas[..., i][..., None]], axis=3))
+    elif which_color_pred == "alpha_only":      # msi.py:249-268
+        alphas = (msi_pred[..., :L] + one) / two
+        for i in range(L):
+            layers.append(np.concatenate([net_input[..., i * 3:(1 + i) * 3], alphas[..., i][..., None]], axis=3))
+    else:
+        raise ValueError(which_color_pred)
+    return np.stack(layers, axis=3).astype(dt), blend_weights, alphas, bg_blend_weights
+
+
 def infer_msi(raw_src_image, raw_ref_image, ref_pose, src_pose, intrinsics, num_msi_planes,
-              psv_planes, weights, extra_outputs="", ngf=64, coord_net=True):
+              psv_planes, weights, extra_outputs="", ngf=64, coord_net=True, which_color_pred="blend_psv"):
     """msi.py:40-289, ``blend_psv`` / ODS / operation=='train' path, one frame at
     a time (argument order src, ref as in the reference)."""
     preds = {"rgba_layers": [], "blend_weights": [], "alphas": [], "psv": []}
@@ -138,14 +186,15 @@ def infer_msi(raw_src_image, raw_ref_image, ref_pose, src_pose, intrinsics, num_
                                          psv_planes, intrinsics[b:b + 1])
         net = net_torch.msi_coord_train_net if coord_net else net_torch.msi_train_net
         with torch.no_grad():
-            pred = net(torch.from_numpy(net_input), num_msi_planes * 2, weights, ngf=ngf).numpy()
-        rgba, bw, al = assemble_rgba(pred, net_input, num_msi_planes)
+            pred = net(torch.from_numpy(net_input), color_pred_channels(which_color_pred, num_msi_planes), weights,
+                       ngf=ngf).numpy()
+        rgba, bw, al, _ = assemble_rgba_ex(pred, net_input, num_msi_planes, which_color_pred)
         preds["rgba_layers"].append(rgba)
         preds["blend_weights"].append(bw)
         preds["alphas"].append(al)
         preds["psv"].append(net_input)
     out = {"rgba_layers": np.concatenate(preds["rgba_layers"], 0)}
-    if "blend_weights" in extra_outputs:
+    if "blend_weights" in extra_outputs and "blend" in which_color_pred:
         out["blend_weights"] = np.concatenate(preds["blend_weights"], 0)
     if "alpha" in extra_outputs:
         out["alphas"] = np.concatenate(preds["alphas"], 0)

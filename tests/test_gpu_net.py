@@ -303,3 +303,33 @@ def test_infer_msi_with_train_net(monkeypatch):
         rgb = bw[..., None] * fg + (1 - bw[..., None]) * bg
         want = np.concatenate([rgb, al[..., None]], axis=-1)
         assert float(np.abs(out['rgba_layers'].cpu().numpy() - want).max()) < TOL
+
+
+@pytest.mark.parametrize("which", ["blend_bg", "blend_bg_psv", "alpha_only"])
+def test_infer_msi_other_color_schemes(which):
+    """which_color_pred != blend_psv (msi.py:166-268): net heads with 2L+3 / 3L+3 / L outputs (padded to a
+    multiple of 64 for the tensor-core kernel) and the matching RGBA assembly, against the oracle."""
+    H, W, P, ngf = 32, 64, 32, 64
+    ref, src = synth.ods_pair(1, H, W, seed=77)
+    n_out = ops.color_pred_channels(which, P)
+    wts = synth.net_weights(6 * P, n_out, ngf)
+    m = MSI(weights=wts, device=DEV)
+    planes = m.inv_depths(1, 100, P)
+    eye = synth.identity_poses(1)
+    out, net_input = m.infer_msi(_t(src), _t(ref), None, None, _t(eye), _t(eye), _t(synth.intrinsics(1)), which, P,
+                                 planes, extra_outputs='blend_weights_alphas', ngf=ngf)
+    want, _ = msi_np.infer_msi(src, ref, eye, eye, synth.intrinsics(1), P, planes, wts, extra_outputs='blend_weights_alphas',
+                               ngf=ngf, which_color_pred=which)
+    assert float(np.abs(out['rgba_layers'].cpu().numpy() - want['rgba_layers']).max()) < TOL
+    assert float(np.abs(out['alphas'].cpu().numpy() - want['alphas']).max()) < TOL
+    if 'blend' in which:
+        assert float(np.abs(out['blend_weights'].cpu().numpy() - want['blend_weights']).max()) < TOL
+    else:
+        assert 'blend_weights' not in out
+    assert ('bg_blend_weights' in out) == (which == 'blend_bg_psv')
+    # the assembly itself is bit-exact given the same prediction (separate mul / add, no FMA)
+    pred = torch.rand(1, H, W, n_out, device=DEV) * 2 - 1
+    rgba, bw, al, bgw = ops.rgba_assemble_ex(pred, net_input, which, P, want_weights=True)
+    w_rgba, w_bw, w_al, w_bgw = msi_np.assemble_rgba_ex(pred.cpu().numpy(), net_input.cpu().numpy(), P, which)
+    assert np.array_equal(rgba.cpu().numpy(), w_rgba)
+    assert np.array_equal(al.cpu().numpy(), w_al)

@@ -105,7 +105,7 @@ def test_infer_msi_rejects_unbuilt_modes():
                     synth.intrinsics(1), "blend_psv", 2, [2.0, 1.0])
     with pytest.raises(NotImplementedError):
         MSI(weights={}).infer_msi(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), None, None, np.eye(4)[None],
-                                  np.eye(4)[None], synth.intrinsics(1), "alpha_only", 2, [2.0, 1.0])
+                                  np.eye(4)[None], synth.intrinsics(1), "no_such_scheme", 2, [2.0, 1.0])
 
 
 def test_shard_frames_partition():
