@@ -12,8 +12,9 @@ ref_image_*,msi_alpha_%02d,msi_rgb_%02d,blend_weight_%03d}.png``, ``blend_weight
 ``alphas.npy`` and ``step.txt`` -- the files the reference's eval.py reads (eval.py:132-136).
 
 Differences from the reference (it needs a TF-1.14 session, this needs a B200):
-* weights come from ``<checkpoint_dir>/<experiment_name>/weights.npz`` (arrays keyed by the TF
-  checkpoint variable names); a TF checkpoint reader is not built.  ``--random_init`` uses seeded
+* weights come from the TensorFlow checkpoint ``tf.train.latest_checkpoint(<checkpoint_dir>/<experiment_name>)``
+  names (test.py:192-202; parsed by ``matryodshka_b200.tf_checkpoint``, no TensorFlow needed), or from
+  ``<checkpoint_dir>/<experiment_name>/weights.npz`` (arrays keyed by the TF variable names).  ``--random_init`` uses seeded
   random weights, ``--synthetic N`` fabricates N synthetic ODS triples (no dataset needed);
 * ``--test_type high_res`` / ``high_res_only`` (test.py:284-394) re-render at --hres_height x
   --hres_width from the saved blend_weights.npy / alphas.npy, plane by plane on the GPU, and write
@@ -144,15 +145,23 @@ def make_synthetic_dataset(root, n, height, width, seed, sub="images"):
 
 def load_weights(flags):
     from matryodshka_b200 import synth
+    from matryodshka_b200 import tf_checkpoint
+    from matryodshka_b200.ops import color_pred_channels
     if flags.random_init:
-        return synth.net_weights(6 * flags.num_psv_planes, 2 * flags.num_msi_planes, flags.ngf, flags.random_seed), 0
-    path = os.path.join(flags.checkpoint_dir, flags.experiment_name, "weights.npz")
-    if not os.path.exists(path):
-        raise SystemExit(f"{path} not found: export the TF checkpoint variables to an .npz keyed by their TF names "
-                         "(net/conv1_1/weights ...), or pass --random_init")
-    z = np.load(path)
-    step = int(z["global_step"]) if "global_step" in z.files else 0
-    return {k: z[k] for k in z.files if k != "global_step"}, step
+        n_out = color_pred_channels(flags.which_color_pred, flags.num_msi_planes)
+        return synth.net_weights(6 * flags.num_psv_planes, n_out, flags.ngf, flags.random_seed,
+                                 coord=bool(flags.coord_net)), 0
+    ckpt_dir = os.path.join(flags.checkpoint_dir, flags.experiment_name)
+    npz = os.path.join(ckpt_dir, "weights.npz")
+    if tf_checkpoint.latest_checkpoint(ckpt_dir) is not None:      # test.py:193-202
+        w = tf_checkpoint.load_weights(ckpt_dir)
+    elif os.path.exists(npz):
+        w = tf_checkpoint.load_weights(npz)
+    else:
+        raise SystemExit(f"no TensorFlow checkpoint ('checkpoint' file) and no weights.npz under {ckpt_dir}; "
+                         "pass --random_init for seeded random weights")
+    step = int(np.asarray(w["global_step"]).reshape(-1)[0]) if "global_step" in w else 0
+    return {k: v for k, v in w.items() if k.startswith("net/")}, step
 
 
 def main(argv=None):
