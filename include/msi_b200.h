@@ -158,6 +158,17 @@ int msi_render_ods(const float* rgba, const float* pose_rt, float order, const f
                    const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
                    int B, int H, int W, int L, float* out_rgb, uint8_t* out_rgb_u8, void* stream);
 
+/* MSI.msi_render_perspective_view (matryodshka/msi.py:475-500) ->
+ * projector.projective_forward_sphere_to_perspective (geometry/projector.py:64-99) ->
+ * spherical.intersect_perspective (geometry/spherical.py:367-401) + over_composite: the MSI seen
+ * through a pinhole window of oH x oW pixels.  pose_rt [B,16] = the viewing-window rotation the
+ * reference builds from viewing_window * pi / 2 about y (projector.py:80-85; the caller's pose is
+ * ignored there); tgt_pos [B,3]; s_axis [oW], t_axis [oH] = the uv_grid axes (spherical.py:46-48).
+ * out_rgb [B,oH,oW,3] float32 in [-1,1] and / or out_rgb_u8. */
+int msi_render_perspective(const float* rgba, const float* pose_rt, const float* tgt_pos, const float* depths,
+                           const float* s_axis, const float* t_axis, int B, int H, int W, int L, int oH, int oW,
+                           float* out_rgb, uint8_t* out_rgb_u8, void* stream);
+
 /* Sample coordinates only (spherical.intersect_sphere): uv [B,L,H,W,2]. */
 int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
                                 const float* cos_s, const float* sin_s, const float* cos_t,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "msi_rgba_assemble_ex": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "msi_render_composite": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "msi_render_ods": (c_int, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "msi_render_perspective": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "msi_intersect_sphere_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "msi_project_layers": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "msi_point_op": (c_int, [_I, _P, _P, _P, ctypes.c_longlong, _I, _P, _I, ctypes.c_float, ctypes.c_float, _I, _I,

@@ -168,6 +168,27 @@ __device__ __forceinline__ SphereRay sphere_ray_ods(float cs, float sn, float ct
     return q;
 }
 
+// The ray of spherical.intersect_perspective (spherical.py:367-401) + transform_ray (:70-94): pixel
+// (S, T) of uv_grid looks along (0.1 S, 0.05 T, -0.05) (hard-coded intrinsics, :385-387) from
+// (center[0], center[1], -center[2]) (:390-392); both are moved by `pos`.
+__device__ __forceinline__ SphereRay sphere_ray_perspective(float S, float T, const float* __restrict__ pos,
+                                                            const float* __restrict__ center) {
+    SphereRay q;
+    const float rx0 = S * 0.1f;
+    const float ry0 = T * 0.05f;
+    const float rz0 = -1.0f * 0.05f;
+    const float cx0 = center[0], cy0 = center[1], cz0 = -center[2];
+    q.rx = (pos[0] * rx0 + pos[1] * ry0) + pos[2] * rz0;
+    q.ry = (pos[4] * rx0 + pos[5] * ry0) + pos[6] * rz0;
+    q.rz = (pos[8] * rx0 + pos[9] * ry0) + pos[10] * rz0;
+    q.cx = ((pos[0] * cx0 + pos[1] * cy0) + pos[2] * cz0) + pos[3];
+    q.cy = ((pos[4] * cx0 + pos[5] * cy0) + pos[6] * cz0) + pos[7];
+    q.cz = ((pos[8] * cx0 + pos[9] * cy0) + pos[10] * cz0) + pos[11];
+    q.a = (q.rx * q.rx + q.ry * q.ry) + q.rz * q.rz;
+    q.b = 2.0f * ((q.rx * q.cx + q.ry * q.cy) + q.rz * q.cz);
+    return q;
+}
+
 // ... and the per-layer hit + projection (:315-326, :235-246, :54-68).  Same operations in the same
 // order as sphere_uv below, so both forms give identical bits.
 __device__ __forceinline__ void sphere_hit_uv(const SphereRay& q, float radius, const ErpConsts& k, float& u, float& v) {

@@ -307,7 +307,9 @@ struct RenderParams {
     uint8_t* out_rgb_u8;
     uint8_t* out_depth_u8;
     ErpConsts k;
-    int ods_mode;            // 0: target ERP view (intersect_sphere); 1: ODS eye view (intersect_ods)
+    int ods_mode;            // 0: target ERP view (intersect_sphere); 1: ODS eye view (intersect_ods);
+                             // 2: perspective view (intersect_perspective; cos_s / cos_t hold the uv_grid axes)
+    int oH, oW;              // output image size (= H, W except for the perspective view)
     float ods_order;         // +1 / -1
     const float* baselines;  // [B] (ODS mode)
 };
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
     float* frac = sm + 4 * 32 * ld;
     __shared__ SphereRay s_ray[32];
     __shared__ int s_b[32];
-    const long long npix = (long long)p.B * p.H * p.W;
+    const long long npix = (long long)p.B * p.oH * p.oW;
     const long long pix0 = (long long)blockIdx.x * 32;
 
     for (int l = threadIdx.x; l < L; l += 256) frac[l] = (float)((double)l / (double)L);
@@ -353,10 +355,12 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
         int b = 0;
         SphereRay ray = {};
         if (pix < npix) {
-            const int j = (int)(pix % p.W);
-            const int i = (int)((pix / p.W) % p.H);
-            b = (int)(pix / ((long long)p.W * p.H));
-            if (p.ods_mode)
+            const int j = (int)(pix % p.oW);
+            const int i = (int)((pix / p.oW) % p.oH);
+            b = (int)(pix / ((long long)p.oW * p.oH));
+            if (p.ods_mode == 2)
+                ray = sphere_ray_perspective(__ldg(p.cos_s + j), __ldg(p.cos_t + i), p.pose_rt + b * 16, p.tgt_pos + b * 3);
+            else if (p.ods_mode)
                 ray = sphere_ray_ods(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
                                      p.pose_rt + b * 16, p.ods_order, __ldg(p.baselines + b));
             else
@@ -744,6 +748,8 @@ static int fill_render_params(RenderParams& p, const float* rgba, const float* p
     p.out_depth_u8 = nullptr;
     p.k = make_erp_consts(H, W);
     p.ods_mode = 0;
+    p.oH = H;
+    p.oW = W;
     p.ods_order = 1.0f;
     p.baselines = nullptr;
     return MSI_OK;
@@ -799,6 +805,33 @@ extern "C" int msi_render_ods(const float* rgba, const float* pose_rt, float ord
         smem_opted.store(smem);
     }
     const long long npix = (long long)B * H * W;
+    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+// MSI.msi_render_perspective_view (msi.py:475-500) -> projector.projective_forward_sphere_to_perspective
+// (projector.py:64-99) -> spherical.intersect_perspective (spherical.py:367-401) + over_composite.
+// pose_rt [B,16] is the viewing-window rotation the reference builds itself (projector.py:80-85);
+// s_axis [oW] / t_axis [oH] are the uv_grid axes (spherical.py:46-48).
+extern "C" int msi_render_perspective(const float* rgba, const float* pose_rt, const float* tgt_pos, const float* depths,
+                                      const float* s_axis, const float* t_axis, int B, int H, int W, int L, int oH,
+                                      int oW, float* out_rgb, uint8_t* out_rgb_u8, void* stream) {
+    RenderParams p;
+    int rc = fill_render_params(p, rgba, pose_rt, tgt_pos, depths, s_axis, s_axis, t_axis, t_axis, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(rgba && (out_rgb || out_rgb_u8), "render_perspective: null pointer");
+    MSI_CHECK_ARG(oH > 0 && oW > 0, "render_perspective: bad output size %dx%d", oH, oW);
+    p.out_rgb = out_rgb;
+    p.out_rgb_u8 = out_rgb_u8;
+    p.ods_mode = 2;
+    p.oH = oH;
+    p.oW = oW;
+    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
+    MSI_CHECK_ARG(smem <= 200 * 1024, "render_perspective: L=%d needs %zu B of shared memory", L, smem);
+    if (smem > 48 * 1024)
+        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long npix = (long long)B * oH * oW;
     render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     MSI_LAUNCH_CHECK();
     return MSI_OK;

@@ -215,6 +215,14 @@ class MSI(object):
 
     msi_render_equirect_depth_single = msi_render_equirect_view_single
 
+    def msi_render_perspective_view(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None,
+                                    viewing_window=3, psp_height=270, psp_width=480):
+        """msi.py:475-500: pinhole view of the MSI.  As in the reference, ``tgt_pose_rt`` is accepted and
+        replaced by the viewing-window rotation (projector.py:80-85) and the intrinsics are the
+        hard-coded ones of spherical.py:385-387."""
+        return ops.render_perspective(rgba_layers, _host(tgt_pos).reshape(-1, 3), list(planes),
+                                      viewing_window=viewing_window, psp_height=psp_height, psp_width=psp_width)
+
     def msi_render_ods_view(self, rgba_layers, order, jitter_pose, tgt_pos, planes, intrinsics):
         """msi.py:502-525: the MSI seen from one ODS eye (order +1 = left / ref, -1 = right / src)
         under ``jitter_pose`` [B,4,4].  As in the reference, ``tgt_pos`` is not used by the ODS ray

@@ -228,6 +228,35 @@ def render_ods(rgba, pose_rt, order, baselines, depths, *, want_u8=False):
     return (rgb, u8) if want_u8 else rgb
 
 
+def viewing_window_pose(viewing_window, B):
+    """projector.py:80-85: rotation by viewing_window * pi / 2 about y, as a [B,4,4] float32 [R|0] pose.
+    [tensorflow_graphics 1.0.0 rotation_matrix_3d.from_euler, R = Rz Ry Rx, restated for angles (0, a, 0):
+    float32 sin / cos of the float32 angle.]"""
+    a = np.float32(viewing_window * np.pi / 2.0)
+    sy, cy = np.sin(a, dtype=np.float32), np.cos(a, dtype=np.float32)
+    m = np.array([[cy, 0, sy, 0], [0, 1, 0, 0], [-sy, 0, cy, 0], [0, 0, 0, 1]], dtype=np.float32)
+    return np.tile(m[None], (B, 1, 1))
+
+
+def render_perspective(rgba, tgt_pos, depths, *, viewing_window=3, psp_height=270, psp_width=480, want_u8=False):
+    """msi_render_perspective: pinhole view [B,psp_height,psp_width,3] of an MSI (msi.py:475-500)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    B, H, W, L, _ = rgba.shape
+    dev = rgba.device
+    pose = _dev_f32(viewing_window_pose(viewing_window, B), dev).reshape(B, 16).contiguous()
+    pos = _dev_f32(tgt_pos, dev).reshape(B, 3).contiguous()
+    d = _dev_f32(np.asarray(depths, dtype=np.float32), dev)
+    s_axis = _dev_f32(_linspace_tf(-1.0 + 1.0 / psp_width, 1.0 - 1.0 / psp_width, psp_width), dev)   # spherical.py:46-48
+    t_axis = _dev_f32(_linspace_tf(-1.0 + 1.0 / psp_height, 1.0 - 1.0 / psp_height, psp_height), dev)
+    out = torch.empty((B, psp_height, psp_width, 3), dtype=torch.float32, device=dev)
+    u8 = torch.empty((B, psp_height, psp_width, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+    check(lib.msi_render_perspective(ptr(rgba.contiguous()), ptr(pose), ptr(pos), ptr(d), ptr(s_axis), ptr(t_axis),
+                                     B, H, W, L, psp_height, psp_width, ptr(out), ptr(u8), stream_ptr()),
+          "msi_render_perspective")
+    return (out, u8) if want_u8 else out
+
+
 def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device):
     """msi_intersect_sphere_coords -> uv [B,L,H,W,2]."""
     _lib.require_cuda()

@@ -228,6 +228,53 @@ def intersect_ods(pose, center, order, intrinsics, radius, num_planes, num_batch
         return project_spherical((x, y, z), order, None, intrinsics, width, height, dt).astype(dt)
 
 
+def uv_grid(shape, dt=F32):
+    """spherical.py:46-48: pixel-centre coordinates in (-1, 1).  [TF-1.14 LinSpace]"""
+    h, w = shape
+    return np.meshgrid(linspace_tf(-1.0 + 1.0 / w, 1.0 - 1.0 / w, w, dt), linspace_tf(-1.0 + 1.0 / h, 1.0 - 1.0 / h, h, dt))
+
+
+def viewing_window_pose(viewing_window, dt=F32):
+    """projector.py:80-85: [R | 0] with R = tfg rotation_matrix_3d.from_euler([0, vw*pi/2, 0]).
+    [tensorflow_graphics 1.0.0, absent here: R = Rz Ry Rx built from float32 sines / cosines of the
+    float32 angles; for (0, a, 0) that is [[cos a, 0, sin a], [0, 1, 0], [-sin a, 0, cos a]].]"""
+    a = dt(viewing_window * np.pi / 2.0)
+    sy, cy = np.sin(a, dtype=dt), np.cos(a, dtype=dt)
+    return np.array([[cy, 0, sy, 0], [0, 1, 0, 0], [-sy, 0, cy, 0], [0, 0, 0, 1]], dtype=dt)
+
+
+def intersect_perspective(pos, center, radius, num_planes, num_batch, width, height, tgt_width, tgt_height,
+                          intrinsics=None, dt=F32):
+    """spherical.py:367-401 (+ transform_ray :70-94, get_sphere_intersections :96-111, project_spherical
+    :235-246).  pos [4,4]; center [3] (or [3,1]); radius [L].  uv [L, tgt_height, tgt_width, 2] into the
+    width x height ERP layers."""
+    pos = np.asarray(pos, dtype=dt)
+    center = np.asarray(center, dtype=dt).reshape(3)
+    radius = np.asarray(radius, dtype=dt).reshape(num_planes, 1, 1)
+    S, T = uv_grid((tgt_height, tgt_width), dt)
+    S = np.broadcast_to(S[None], (num_planes, tgt_height, tgt_width))
+    T = np.broadcast_to(T[None], (num_planes, tgt_height, tgt_width))
+    rx = S * dt(0.1)
+    ry = T * dt(0.05)
+    rz = -np.ones_like(S) * dt(0.05)
+    cx = np.full_like(S, center[0])
+    cy = np.full_like(S, center[1])
+    cz = np.full_like(S, -center[2])
+    rx, ry, rz = _matvec_rows(pos[:3, :3], [rx, ry, rz], dt)
+    pt = _matvec_rows(pos, [cx, cy, cz, np.ones_like(cx)], dt)
+    cx, cy, cz = pt[0], pt[1], pt[2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = rx * rx + ry * ry + rz * rz
+        b = dt(2) * (rx * cx + ry * cy + rz * cz)
+        c = cx * cx + cy * cy + cz * cz - radius * radius
+        disc = np.square(b) - dt(4) * a * c
+        t = (-b + np.sqrt(disc)) / (dt(2) * a)
+        x = cx + t * rx
+        y = cy + t * ry
+        z = cz + t * rz
+        return project_spherical((x, y, z), 1, None, None, width, height, dt).astype(dt)
+
+
 # --------------------------------------------------------------------------- #
 # sampling.py
 # --------------------------------------------------------------------------- #

@@ -239,6 +239,22 @@ def msi_render_ods_view(rgba_layers, order, jitter_pose, tgt_pos, planes, intrin
     return g.over_composite(proj, dt)
 
 
+def msi_render_perspective_view(rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None, viewing_window=3,
+                                psp_height=270, psp_width=480, dt=F32):
+    """msi.py:475-500 -> projector.projective_forward_sphere_to_perspective (projector.py:64-99): the
+    caller's pose is replaced by the viewing-window rotation; [B, psp_height, psp_width, 3]."""
+    rgba_layers = np.asarray(rgba_layers, dtype=dt)
+    B, H, W, L, _ = rgba_layers.shape
+    depths = np.asarray(planes, dtype=dt)
+    layers = np.transpose(rgba_layers, (3, 0, 1, 2, 4))  # [L, B, H, W, 4]
+    pose = g.viewing_window_pose(viewing_window, dt)
+    tgt_pos = np.asarray(tgt_pos, dtype=dt).reshape(B, 3)
+    coords = np.stack([g.intersect_perspective(pose, tgt_pos[i], depths, L, B, W, H, psp_width, psp_height, None, dt)
+                       for i in range(B)], axis=0).transpose(1, 0, 2, 3, 4)   # [L, B, h, w, 2]
+    proj = [g.resample(layers[l], coords[l], dt) for l in range(L)]
+    return g.over_composite(proj, dt)
+
+
 def msi_render_equirect_view_single(rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None, dt=F32):
     """msi.py:431-452: reprojected layers without compositing [L, B, H, W, 4]."""
     return _project_layers(rgba_layers, tgt_pose_rt, tgt_pos, planes, dt)

@@ -78,3 +78,19 @@ def test_jittered_inference_path():
     assert np.abs(net_input.cpu().numpy() - psv).max() < TOL
     got = m.msi_render_equirect_view(out["rgba_layers"], jitter, tp, planes).cpu().numpy()
     assert np.abs(got - want).max() < TOL
+
+
+@pytest.mark.parametrize("viewing_window,psp", [(3, (27, 48)), (1, (30, 40)), (0, (270, 480))])
+def test_render_perspective_view_matches_oracle(viewing_window, psp):
+    """MSI.msi_render_perspective_view (msi.py:475-500): pinhole window of psp_height x psp_width pixels
+    out of the ERP layers (output size differs from the layer size), two frames with different offsets."""
+    B, H, W, L = 2, 32, 64, 8
+    rgba = _smooth_layers(B, H, W, L, 33)
+    planes = msi_np.inv_depths(1, 100, L)
+    tp = np.array([[0.02, -0.01, 0.03], [0.0, 0.0, 0.0]], F32)
+    want = msi_np.msi_render_perspective_view(rgba, None, tp, planes, None, viewing_window, psp[0], psp[1])
+    got = MSI().msi_render_perspective_view(_t(rgba), None, tp, planes, None, viewing_window, psp[0], psp[1])
+    assert tuple(got.shape) == (B, psp[0], psp[1], 3)
+    assert np.abs(got.cpu().numpy() - want).max() < TOL
+    # the window looks somewhere: it is not constant, and two viewing windows differ
+    assert float(got.std()) > 1e-3
