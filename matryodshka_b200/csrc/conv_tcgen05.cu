@@ -900,19 +900,23 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         const uint64_t lo_adv = (uint64_t)(p.a_rows * 8);                       // hi halo -> lo halo
         int a_stage = 0, w_stage = 0;
         uint32_t a_phase = 0, w_phase = 0;
-        bool a_ready = false, w_ready = false;
+        bool a_ready = false, w_ready = false, t_ready = false;
         int local = 0;
         int tr_slot = 0, tr_chunk = 0;
         trace_ev(leader ? p.trace : nullptr, 7, 1);
+        const int units_per_cls = p.units_per_col * p.n_tiles;
         for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas, ++local) {
-            const int cls = (unit / p.units_per_col) / p.n_tiles;
+            const int cls = (p.ncls > 1) ? unit / units_per_cls : 0;  // (a division only for the deconv classes)
             const int slots_per_chunk = s_ntaps[cls] / T;
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
-            mbar_wait(tempty0 + 8u * acc, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+            // the epilogue has drained this accumulator (tested ahead, during the previous unit's last slot)
+            if (!t_ready) mbar_wait(tempty0 + 8u * acc, (use & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             trace_ev(leader ? p.trace : nullptr, 8, local);
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+            const uint32_t next_tempty = tempty0 + 8u * (uint32_t)(acc ^ 1);
+            const uint32_t next_tparity = ((uint32_t)((local + 1) >> 1) & 1u) ^ 1u;
             uint32_t accumulate = 0u;
             for (int ch = 0; ch < chunks_total; ++ch) {
                 if (!a_ready) mbar_wait(afull0 + 8u * a_stage, a_phase);
@@ -923,7 +927,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                     a_stage = 0;
                     a_phase ^= 1u;
                 }
-                a_ready = mbar_test_wait(afull0 + 8u * a_stage, a_phase);  // next chunk's halo, used next iteration
+                a_ready = false;
                 const uint32_t a_done_bar = aempty0 + 8u * (a_stage == 0 ? a_stages - 1 : a_stage - 1);
                 for (int sl = 0; sl < slots_per_chunk; ++sl) {
                     int off[T];
@@ -936,7 +940,16 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                         w_stage = 0;
                         w_phase ^= 1u;
                     }
-                    w_ready = mbar_test_wait(wfull0 + 8u * w_stage, w_phase);  // next slot, used next iteration
+                    // Non-blocking tests of the barriers the NEXT iteration needs, issued before this
+                    // slot's MMAs so that their latency hides behind the issue: the next W slot always,
+                    // the next chunk's halo and the next unit's accumulator during a chunk's last slot
+                    // (a blocking wait at a chunk / unit boundary drains the MMA queue: measured +400 /
+                    // +1200 clk per boundary).
+                    w_ready = mbar_test_wait(wfull0 + 8u * w_stage, w_phase);
+                    if (sl == slots_per_chunk - 1) {
+                        a_ready = mbar_test_wait(afull0 + 8u * a_stage, a_phase);
+                        t_ready = (ch == chunks_total - 1) ? mbar_test_wait(next_tempty, next_tparity) : false;
+                    }
                     if (leader) {
                         trace_ev(p.trace, 0, tr_slot);
                         uint64_t db = make_desc(w_ring + cur * w_slot_bytes);
