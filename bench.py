@@ -206,7 +206,7 @@ def run_ours(args):
     import torch.distributed as dist
     from matryodshka_b200 import _lib, synth
     from matryodshka_b200.nets import net_flops
-    from matryodshka_b200.runtime import MSIFrameLanes, all_gather_frames, profile_net_layers
+    from matryodshka_b200.runtime import FrameGather, MSIFrameLanes, all_gather_frames, profile_net_layers
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,7 +239,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    gather = (lambda lane: all_gather_frames(lane.out["rgb_u8"], world)) if world > 1 else None
+    def check_gathered():
+        """After a barrier: every rank's slot of every gathered buffer holds that rank's last frame."""
+        for lane, g in zip(lanes.lanes, gathers):
+            torch.cuda.synchronize(dev)
+            g.barrier()
+            mine = g.frames[g.first_frame:g.first_frame + Bp]
+            assert torch.equal(mine, lane.out["rgb_u8"]), "fused gather: own slot differs from the local frame"
+            per_rank = g.frames.view(world, -1).float().mean(dim=1)
+            assert bool((per_rank > 0).all()), "fused gather: a rank's slot is empty"
+            g.barrier()
+
+    # The path's only collective, the all-gather of the rendered uint8 frames (SURVEY.md 8e).  Default:
+    # FUSED into the render kernel -- it stores its frame into every rank's gathered buffer (symmetric
+    # memory; multimem.st through the NVSwitch multicast address, else peer stores), no collective kernel
+    # and no per-step rendezvous.  --gather nccl (or no symmetric memory): all_gather_into_tensor per step.
+    gather, gathers, collective = None, [], "none"
+    if world > 1:
+        if args.gather != "nccl":
+            try:
+                gathers = [FrameGather(Bp, H, W, dev, mode=args.gather) for _ in lanes.lanes]
+                for lane, g in zip(lanes.lanes, gathers):
+                    lane.attach_gather(g)
+                collective = ("fused into the render kernel: uint8 frames stored into every rank's gathered buffer, "
+                              + gathers[0].mode + " (symmetric memory); barrier at the end of the timed region")
+            except Exception as e:  # noqa: BLE001
+                log(f"fused gather unavailable ({type(e).__name__}: {e}); using NCCL all_gather")
+                gathers = []
+        if not gathers:
+            gather = lambda lane: all_gather_frames(lane.out["rgb_u8"], world)  # noqa: E731
+            collective = "NCCL all_gather_into_tensor of the rendered uint8 frames, every step"
 
     def one_step():
         lanes.step(after_compute=gather)
@@ -277,6 +306,8 @@ def run_ours(args):
         sampler.start()
     # ---- device-resident timed region: inputs already in HBM ------------------------------------
     dev_ms = timed(K, one_step)
+    if gathers:
+        check_gathered()
     # the same K steps on ONE lane (one frame at a time), reported beside the headline for reference
     single_ms = dev_ms
     if n_lanes > 1:
@@ -391,7 +422,7 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph, "frames_in_flight": n_lanes,
                        "one_frame_at_a_time": {"value": frames / (single_ms * 1e-3), "unit": UNIT,
                                                "ms_per_step": single_ms / K},
-                       "collective": "all_gather of rendered uint8 frames" if world > 1 else "none",
+                       "collective": collective,
                        "l2": f"per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "ms_per_step": e2e_ms / K,
@@ -423,6 +454,8 @@ def main():
     ap.add_argument("--conv-impl", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (independent pipelines on own streams)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
+                    help="N > 1: how the rendered frames reach every rank (default: fused into the render kernel)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-profile", action="store_true",

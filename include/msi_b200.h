@@ -149,6 +149,20 @@ int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const floa
                          float* out_rgb, float* out_depth, uint8_t* out_rgb_u8, uint8_t* out_depth_u8,
                          void* stream);
 
+/* msi_render_composite fused with the path's only collective (one all-gather of the
+ * rendered frames).  Besides the local outputs, the uint8 view of local frame b is stored into the
+ * gathered buffer [world * B, H, W, 3] of EVERY rank at frame index first_frame + b:
+ *   peer_rgb_u8       device array of n_peers base pointers of that buffer on each rank (peer-mapped
+ *                     symmetric memory; includes this rank), or NULL for no gather;
+ *   multicast_rgb_u8  the NVSwitch multicast address of the same buffer, or NULL: when given, one
+ *                     multimem.st per 32-bit word replaces the n_peers stores.
+ * No collective kernel runs afterwards; readers synchronise across ranks (a barrier) before use. */
+int msi_render_composite_gather(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
+                                const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t, int B,
+                                int H, int W, int L, float* out_rgb, float* out_depth, uint8_t* out_rgb_u8,
+                                uint8_t* out_depth_u8, uint8_t* const* peer_rgb_u8, int n_peers,
+                                uint8_t* multicast_rgb_u8, long long first_frame, void* stream);
+
 /* The MSI seen from one ODS eye: MSI.msi_render_ods_view (msi.py:502-525) ->
  * projector.projective_forward_ods (projector.py:101-127) -> spherical.intersect_ods
  * (spherical.py:328-365) + over_composite.  pose_rt [B,16] (the "jitter pose"), order = +1 (left /

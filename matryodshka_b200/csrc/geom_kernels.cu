@@ -310,6 +310,14 @@ struct RenderParams {
     int ods_mode;            // 0: target ERP view (intersect_sphere); 1: ODS eye view (intersect_ods);
                              // 2: perspective view (intersect_perspective; cos_s / cos_t hold the uv_grid axes)
     int oH, oW;              // output image size (= H, W except for the perspective view)
+    // Fused output all-gather: besides its local outputs the kernel stores the uint8
+    // view into the gathered buffer [world * B, H, W, 3] of EVERY rank -- through the NVSwitch
+    // multicast address of the symmetric buffer when there is one (one multimem.st per word), else
+    // with one peer store per rank -- so no collective kernel runs after it.
+    uint8_t* const* peer_u8;  // device array of n_peers base pointers (null: no gather)
+    int n_peers;
+    uint8_t* mc_u8;           // multicast address of the same buffer (null: per-peer stores)
+    long long gather_off;     // byte offset of this rank's first frame in the gathered buffer
     float ods_order;         // +1 / -1
     const float* baselines;  // [B] (ODS mode)
 };
@@ -344,6 +352,7 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
     float* frac = sm + 4 * 32 * ld;
     __shared__ SphereRay s_ray[32];
     __shared__ int s_b[32];
+    __shared__ __align__(16) uint8_t s_u8[96];
     const long long npix = (long long)p.B * p.oH * p.oW;
     const long long pix0 = (long long)blockIdx.x * 32;
 
@@ -430,7 +439,9 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
         if (pix < npix) {
             if (ch < 3) {
                 if (p.out_rgb != nullptr) p.out_rgb[pix * 3 + ch] = out;
-                if (p.out_rgb_u8 != nullptr) p.out_rgb_u8[pix * 3 + ch] = to_u8((out + 1.0f) / 2.0f);
+                const uint8_t q8 = to_u8((out + 1.0f) / 2.0f);
+                if (p.out_rgb_u8 != nullptr) p.out_rgb_u8[pix * 3 + ch] = q8;
+                if (p.peer_u8 != nullptr) s_u8[q * 3 + ch] = q8;
             } else {
                 if (p.out_depth != nullptr) {
                     p.out_depth[pix * 3 + 0] = out;
@@ -444,6 +455,25 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
                     p.out_depth_u8[pix * 3 + 2] = d;
                 }
             }
+        }
+    }
+    if (p.peer_u8 != nullptr) {
+        // the block's 32 pixels x 3 bytes = 24 words, contiguous in the gathered buffer
+        __syncthreads();
+        const long long dst = p.gather_off + pix0 * 3;  // multiple of 4: pix0 is a multiple of 32
+        const int nbytes = (int)min((long long)96, (npix - pix0) * 3);
+        if (nbytes == 96) {
+            if (threadIdx.x < 24) {
+                const unsigned int w = reinterpret_cast<const unsigned int*>(s_u8)[threadIdx.x];
+                if (p.mc_u8 != nullptr) {
+                    asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p.mc_u8 + dst + 4 * threadIdx.x), "r"(w) : "memory");
+                } else {
+                    for (int k = 0; k < p.n_peers; ++k)
+                        *reinterpret_cast<unsigned int*>(p.peer_u8[k] + dst + 4 * threadIdx.x) = w;
+                }
+            }
+        } else if ((int)threadIdx.x < nbytes) {  // ragged last block: byte stores to every peer
+            for (int k = 0; k < p.n_peers; ++k) p.peer_u8[k][dst + threadIdx.x] = s_u8[threadIdx.x];
         }
     }
 }
@@ -752,6 +782,10 @@ static int fill_render_params(RenderParams& p, const float* rgba, const float* p
     p.oW = W;
     p.ods_order = 1.0f;
     p.baselines = nullptr;
+    p.peer_u8 = nullptr;
+    p.n_peers = 0;
+    p.mc_u8 = nullptr;
+    p.gather_off = 0;
     return MSI_OK;
 }
 
@@ -759,11 +793,29 @@ extern "C" int msi_render_composite(const float* rgba, const float* tgt_pose_rt,
                                     const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
                                     const float* sin_t, int B, int H, int W, int L, float* out_rgb, float* out_depth,
                                     uint8_t* out_rgb_u8, uint8_t* out_depth_u8, void* stream) {
+    return msi_render_composite_gather(rgba, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L, out_rgb,
+                                       out_depth, out_rgb_u8, out_depth_u8, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int msi_render_composite_gather(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
+                                           const float* depths, const float* cos_s, const float* sin_s,
+                                           const float* cos_t, const float* sin_t, int B, int H, int W, int L,
+                                           float* out_rgb, float* out_depth, uint8_t* out_rgb_u8, uint8_t* out_depth_u8,
+                                           uint8_t* const* peer_rgb_u8, int n_peers, uint8_t* multicast_rgb_u8,
+                                           long long first_frame, void* stream) {
     RenderParams p;
     int rc = fill_render_params(p, rgba, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
     if (rc != MSI_OK) return rc;
     MSI_CHECK_ARG(rgba != nullptr, "render: null rgba");
-    MSI_CHECK_ARG(out_rgb || out_depth || out_rgb_u8 || out_depth_u8, "render: no output requested");
+    MSI_CHECK_ARG(out_rgb || out_depth || out_rgb_u8 || out_depth_u8 || peer_rgb_u8, "render: no output requested");
+    if (peer_rgb_u8 != nullptr) {
+        MSI_CHECK_ARG(n_peers >= 1 && first_frame >= 0, "render_gather: n_peers=%d first_frame=%lld", n_peers, first_frame);
+        p.peer_u8 = peer_rgb_u8;
+        p.n_peers = n_peers;
+        p.mc_u8 = multicast_rgb_u8;
+        p.gather_off = first_frame * (long long)H * W * 3;
+        MSI_CHECK_ARG(p.gather_off % 4 == 0, "render_gather: H*W*3 must be a multiple of 4");
+    }
     p.out_rgb = out_rgb;
     p.out_depth = out_depth;
     p.out_rgb_u8 = out_rgb_u8;

@@ -202,6 +202,7 @@ class MSIPipeline:
         self.h_depth_u8 = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
         self.use_graph = use_graph
         self._graph = None
+        self.gather = None   # FrameGather: the render kernel also stores its uint8 view into every rank's gathered buffer
         self.launches_per_step = self.net.launches_per_forward + 3
 
     # -- device-resident step ---------------------------------------------------------------
@@ -226,10 +227,18 @@ class MSIPipeline:
                                         B, H, W, P, ptr(self.rgba), None, None, stream_ptr()), "msi_rgba_assemble")
 
         def k5():
-            check(lib.msi_render_composite(ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths),
-                                           *tb.ptrs(), B, H, W, P, ptr(self.out["rgb"]), ptr(self.out["depth"]),
-                                           ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]), stream_ptr()),
-                  "msi_render_composite")
+            g = self.gather
+            if g is None:
+                check(lib.msi_render_composite(ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths),
+                                               *tb.ptrs(), B, H, W, P, ptr(self.out["rgb"]), ptr(self.out["depth"]),
+                                               ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]), stream_ptr()),
+                      "msi_render_composite")
+            else:   # fused with the output all-gather: peer / multicast stores from the render kernel
+                check(lib.msi_render_composite_gather(
+                    ptr(self.rgba), ptr(self.tgt_pose_rt), ptr(self.tgt_pos), ptr(self.depths), *tb.ptrs(), B, H, W, P,
+                    ptr(self.out["rgb"]), ptr(self.out["depth"]), ptr(self.out["rgb_u8"]), ptr(self.out["depth_u8"]),
+                    c_void_p(g.peers_dev), g.world, c_void_p(g.multicast_ptr) if g.multicast_ptr else None,
+                    g.first_frame, stream_ptr()), "msi_render_composite_gather")
 
         return [("psv_build", k1), ("net", k2), ("rgba_assemble", k4), ("render_composite", k5)]
 
@@ -251,6 +260,12 @@ class MSIPipeline:
             e1.synchronize()
             out[name] = e0.elapsed_time(e1) / reps
         return out
+
+    def attach_gather(self, gather):
+        """Fuse the path's collective into the render kernel (see FrameGather).  Call before the first step()."""
+        assert self._graph is None, "attach_gather() must precede the first graph-captured step()"
+        assert gather.B == self.B and gather.H == self.H and gather.W == self.W
+        self.gather = gather
 
     def step(self):
         """One pass of the hot path over the resident batch (inputs already in HBM)."""
@@ -444,6 +459,43 @@ class MSIFrameLanes:
     @property
     def in_flight_capacity(self):
         return sum(getattr(p, "_depth", 2) for p in self.lanes)
+
+
+class FrameGather:
+    """The gathered output buffer ``frames [world * B, H, W, 3]`` uint8 in symmetric memory (every rank
+    maps every rank's copy), for the fused form of the path's only collective: the render
+    kernel of rank r stores its B frames at index r * B of EVERY rank's buffer -- one ``multimem.st`` per
+    word through the NVSwitch multicast address when the fabric offers one, else one peer store per rank
+    -- so that no all-gather kernel (and no per-step rendezvous of the ranks) follows it.  Readers call
+    ``barrier()`` before they look at ``frames`` and again before the producers may overwrite it.
+
+    mode: "auto" (multicast if available, else peer stores), "peer", "multicast".  Raises if symmetric
+    memory cannot be set up (the caller then falls back to ``all_gather_frames`` = NCCL)."""
+
+    def __init__(self, B, H, W, device, group=None, mode="auto"):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.B, self.H, self.W = B, H, W
+        assert (H * W * 3) % 4 == 0
+        self.buf = symm_mem.empty(self.world * B * H * W * 3, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.peers_dev = int(self.hdl.buffer_ptrs_dev)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if mode == "multicast" and not mc:
+            raise _lib.MsiError("FrameGather: no multicast address on this fabric")
+        self.multicast_ptr = mc if mode in ("auto", "multicast") else 0
+        self.mode = "multimem.st (NVSwitch multicast)" if self.multicast_ptr else "peer stores"
+        self.frames = self.buf.view(self.world * B, H, W, 3)
+        self.first_frame = self.rank * B
+        torch.cuda.synchronize(device)
+        self.barrier()
+
+    def barrier(self):
+        """All ranks' stores issued before the barrier (on the current stream) are visible after it."""
+        self.hdl.barrier(channel=0)
 
 
 def shard_frames(num_frames: int, rank: int, world_size: int):

@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from matryodshka_b200 import synth  # noqa: E402
-from matryodshka_b200.runtime import MSIPipeline, all_gather_frames, shard_frames  # noqa: E402
+from matryodshka_b200.runtime import FrameGather, MSIPipeline, all_gather_frames, shard_frames  # noqa: E402
 
 
 def main():
@@ -40,6 +40,27 @@ def main():
         assert torch.equal(rgb, full.out["rgb"]), "N-GPU gathered frames differ from the 1-GPU run"
         assert torch.equal(rgb8, full.out["rgb_u8"])
         print(f"NCCL_OK world={world} frames={n_frames}")
+    # fused form: the render kernel stores its frames into every rank's gathered buffer (symmetric
+    # memory; multimem.st if the fabric has multicast, and plain peer stores) == the NCCL all-gather
+    for mode in ("auto", "peer"):
+        try:
+            g = FrameGather(hi - lo, H, W, dev, mode=mode)
+        except Exception as e:  # no symmetric memory on this box: the NCCL path above is the fallback
+            if rank == 0:
+                print(f"FUSED_SKIP mode={mode}: {type(e).__name__}: {e}")
+            continue
+        fused = MSIPipeline(wts, H, W, P, ngf, batch=hi - lo, device=dev)
+        fused.attach_gather(g)
+        fused.set_inputs(ref[lo:hi], src[lo:hi], tgt_pos=tp[lo:hi])
+        fused.step()
+        fused.step()   # second step = CUDA-graph replay with the peer pointers baked in
+        torch.cuda.synchronize()
+        g.barrier()
+        assert torch.equal(g.frames, rgb8), f"rank {rank}: fused gather ({g.mode}) differs from the NCCL all-gather"
+        assert torch.equal(fused.out["rgb_u8"], rgb8[lo:hi])
+        g.barrier()
+        if rank == 0:
+            print(f"FUSED_OK world={world} mode={g.mode}")
     dist.barrier()
     dist.destroy_process_group()
 

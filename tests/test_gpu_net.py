@@ -155,6 +155,9 @@ def test_multi_gpu_gather_equals_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
                         os.path.join(root, "tests", "_nccl_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # the fused gather (render kernel -> every rank's symmetric buffer) either matched NCCL or was skipped loudly
+    assert "FUSED_OK" in r.stdout or "FUSED_SKIP" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    print(r.stdout[-600:])
 
 
 def _pipeline_vs_oracle(H, W, P, B, frames_to_check, ngf=64):
