@@ -7,8 +7,11 @@
 Workload (configs[1] of BASELINE.json): 640x320 ERP, 32-sphere MSI, batch = 1 frame per GPU per
 step, synthetic ODS pairs + random-init weights of the reference architecture (ngf 64).  A step is
 one pass of the hot path over one batch: PSV build -> conv net -> RGBA assembly -> reprojection +
-over-composite (+ the all-gather of the rendered frames when N > 1).  Weak scaling: per-GPU work
-is fixed as N grows; `value` = frames all ranks processed / max-over-ranks device time.
+over-composite (+ the all-gather of the rendered frames when N > 1: fused into the render kernel
+as multimem / peer stores into every rank's symmetric buffer, `--gather nccl` for the NCCL form).
+`--lanes` frames are in flight per GPU (independent pipelines on their own streams, round-robin);
+`config.one_frame_at_a_time` reports the same steps on one lane.  Weak scaling: per-GPU work is
+fixed as N grows; `value` = frames all ranks processed / max-over-ranks device time.
 
 One JSON line on stdout from rank 0 (everything else goes to stderr).
 """
