@@ -19,7 +19,8 @@ Differences from the reference (it needs a TF-1.14 session, this needs a B200):
 * ``--test_type high_res`` / ``high_res_only`` (test.py:284-394) re-render at --hres_height x
   --hres_width from the saved blend_weights.npy / alphas.npy, plane by plane on the GPU, and write
   output_hrestgt_*.png / output_hresdepth_*.png; with --synthetic the high-res images are fabricated too;
-* on_video, psp / ODS re-renders and the GCN path are not built.
+* ``on_video`` only changes the output directory names (test.py:209-217), as in the reference; the
+  psp / ODS re-renders of ``--dry_run_inference`` and the GCN path are not built into this driver.
 """
 from __future__ import annotations
 
@@ -143,6 +144,14 @@ def make_synthetic_dataset(root, n, height, width, seed, sub="images"):
     return os.path.join(cam_dir, "*.txt"), img_dir
 
 
+def scene_dirname(flags, s):
+    """test.py:208-217 / :350-360: [video_[<prefix>_]]<scene>_<src id><ref id><tgt id>."""
+    name = s["scene_id"]
+    if "on_video" in flags.test_type:
+        name = "video_" + (flags.prefix + "_" if flags.prefix != "" else "") + name
+    return name + "_%s%s%s" % tuple(s["image_id"])
+
+
 def load_weights(flags):
     from matryodshka_b200 import synth
     from matryodshka_b200 import tf_checkpoint
@@ -167,8 +176,13 @@ def load_weights(flags):
 def main(argv=None):
     flags = parse_flags(argv)
     assert flags.batch_size == 1, "Currently, batch_size must be 1 when testing."  # test.py:89
-    if flags.gcn or flags.input_type != "ODS" or flags.test_type not in ("", "high_res", "high_res_only"):
-        raise SystemExit("only the ODS inference path is built (test_type '', high_res, high_res_only; no gcn / PP / on_video)")
+    rest = flags.test_type
+    for tok in ("high_res_only", "high_res", "on_video"):   # flags are concatenated with '_' (test.py:74-75)
+        rest = rest.replace(tok, "")
+    kinds = set() if rest.strip("_") == "" else {rest}
+    if flags.gcn or flags.input_type != "ODS" or kinds:
+        raise SystemExit("only the ODS inference path is built (test_type: on_video, high_res, high_res_only concatenated "
+                         "with _; no gcn / PP)")
     import torch
     from matryodshka_b200.msi import MSI, MSIConfig
 
@@ -200,7 +214,7 @@ def main(argv=None):
     os.makedirs(out_root, exist_ok=True)
 
     for run, s in enumerate(seqs):
-        if flags.test_type == "high_res_only":
+        if "high_res_only" in flags.test_type:
             break
         imgs = [load_image(os.path.join(flags.image_dir, f"{s['scene_id']}_pos{i}.jpeg"), flags.height, flags.width)
                 for i in s["image_id"]]
@@ -211,7 +225,7 @@ def main(argv=None):
         r = model.msi_render_equirect(outs["rgba_layers"], eye, s["tgt_pos"][None], msi_planes)
         torch.cuda.synchronize(dev)
 
-        dirname = s["scene_id"] + "_%s%s%s" % tuple(s["image_id"])  # test.py:208-217
+        dirname = scene_dirname(flags, s)  # test.py:208-217
         output_dir = os.path.join(out_root, dirname)
         os.makedirs(output_dir, exist_ok=True)
         print("Saving to %s" % output_dir)
@@ -247,7 +261,7 @@ def main(argv=None):
     if "high_res" in flags.test_type:  # test.py:284-394
         from matryodshka_b200.highres import deprocess_high_res, high_res_rerender
         for s in seqs:
-            dirname = s["scene_id"] + "_%s%s%s" % tuple(s["image_id"])
+            dirname = scene_dirname(flags, s)
             output_dir = os.path.join(out_root, dirname)
             bw = torch.from_numpy(np.load(output_dir + "/blend_weights.npy")).to(dev)
             al = torch.from_numpy(np.load(output_dir + "/alphas.npy")).to(dev)

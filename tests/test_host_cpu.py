@@ -132,3 +132,21 @@ def test_gloo_world2_all_gather_of_frames():
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+def test_driver_scene_dirname_on_video():
+    """test.py:209-217: on_video prefixes the output directory with video_[<prefix>_]."""
+    import importlib.util
+    import os
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("msi_test_driver_cpu", os.path.join(root, "test.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    s = {"scene_id": "apartment_0", "image_id": ["0001", "0002", "0003"]}
+    f = types.SimpleNamespace(test_type="", prefix="")
+    assert drv.scene_dirname(f, s) == "apartment_0_000100020003"
+    f = types.SimpleNamespace(test_type="on_video_high_res", prefix="run7")
+    assert drv.scene_dirname(f, s) == "video_run7_apartment_0_000100020003"
+    f = types.SimpleNamespace(test_type="on_video", prefix="")
+    assert drv.scene_dirname(f, s) == "video_apartment_0_000100020003"
