@@ -211,13 +211,15 @@ def test_tcgen05_cluster_multicast_path(monkeypatch):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("H,W,B", [(24, 72, 3), (40, 80, 1), (64, 128, 2)])
+@pytest.mark.parametrize("H,W,B", [(24, 72, 3), (40, 80, 1), (64, 128, 2), (8, 16, 1), (56, 104, 1), (16, 264, 2)])
 def test_halo_kernel_matches_per_tap_kernel(monkeypatch, H, W, B):
     """The halo-reuse kernel (taps read from one smem halo tile through row-shifted descriptors,
     16x8 / 8x16 pixel tiles, K-block-major weights) and the per-tap kernel compute the same
     products in a different order: outputs agree to float32 accumulation noise, and both are within
     the path's 1e-3 bar of the oracle (test_net_* above run on the default = halo kernel).  Ragged
-    sizes exercise zero-filled halos and masked tile rows in both tile orientations."""
+    sizes exercise zero-filled halos and masked tile rows in both tile orientations; 8x16 shrinks the
+    deepest layers to 1x2 pixels (a tile that is almost entirely padding), 16x264 has more tile columns
+    than rows at every level."""
     P, ngf = 32, 64
     rng = np.random.default_rng(12)
     x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
