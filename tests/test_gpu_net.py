@@ -338,3 +338,21 @@ def test_infer_msi_other_color_schemes(which):
     w_rgba, w_bw, w_al, w_bgw = msi_np.assemble_rgba_ex(pred.cpu().numpy(), net_input.cpu().numpy(), P, which)
     assert np.array_equal(rgba.cpu().numpy(), w_rgba)
     assert np.array_equal(al.cpu().numpy(), w_al)
+
+
+def test_train_net_encoder_circular_shift_equivariance_on_gpu():
+    """Size-independent property of the wrap-pad net (no oracle needed): rolling the panorama by 8 columns
+    rolls every encoder activation by 8 / 4 / 2 / 1 columns (circular padding along the width), at a size
+    where the image border falls inside tiles, between tiles and at tile edges."""
+    H, W, P, ngf, B = 64, 136, 32, 64, 1
+    rng = np.random.default_rng(41)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf, coord=False)
+    eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, variant="wrap")
+    eng.forward(_t(x))
+    a = {s: eng.read_activation(s, B).clone() for s in ("conv1_1", "conv1_2", "conv2_2", "conv3_3", "conv4_3")}
+    eng.forward(_t(np.roll(x, 8, axis=2)))
+    for s, shift in [("conv1_1", 8), ("conv1_2", 4), ("conv2_2", 2), ("conv3_3", 1), ("conv4_3", 1)]:
+        b = eng.read_activation(s, B)
+        err = float((torch.roll(a[s], shift, dims=2) - b).abs().max())
+        assert err < 1e-4, (s, err)

@@ -256,3 +256,83 @@ def test_golden_fixture_reproduces():
         assert np.abs(out[k] - z[k]).max() < 2e-5, k
     assert np.array_equal(out["render_u8"], z["render_u8"]) or \
         np.abs(out["render_u8"].astype(int) - z["render_u8"].astype(int)).max() <= 1
+
+
+# ---- row-(f) restatements -------------------------------------------------------------------------
+def test_train_net_encoder_is_equivariant_to_circular_shifts_in_x():
+    """nets.msi_train_net pads every conv input circularly along the width (wrap_pad, nets.py:288-295)
+    and normalises over the whole map, so rolling the panorama by 8 columns (three stride-2 levels)
+    rolls every encoder activation (conv1_1 .. conv4_3) by 8 / 4 / 2 / 1 columns: an analytic property
+    the zero-padded coord net does not have.  The decoder is only approximately equivariant: its
+    deconvs normalise over the un-cropped (2H+10) x (2W+10) output (nets.py:431-436), whose 10 extra
+    columns repeat a different part of the panorama after the roll."""
+    P, ngf, H, W = 4, 8, 16, 32
+    wts = synth.net_weights(6 * P, 2 * P, ngf, coord=False)
+    x = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, (1, H, W, 6 * P)).astype(F32))
+    with torch.no_grad():
+        y, f = net_torch.msi_train_net(x, 2 * P, wts, ngf=ngf, return_feats=True)
+        y8, f8 = net_torch.msi_train_net(torch.roll(x, 8, dims=2), 2 * P, wts, ngf=ngf, return_feats=True)
+        wts_c = synth.net_weights(6 * P, 2 * P, ngf, coord=True)
+        _, fc = net_torch.msi_coord_train_net(x, 2 * P, wts_c, ngf=ngf, return_feats=True)
+        _, fc8 = net_torch.msi_coord_train_net(torch.roll(x, 8, dims=2), 2 * P, wts_c, ngf=ngf, return_feats=True)
+    for scope, shift in [("conv1_1", 8), ("conv1_2", 4), ("conv2_2", 2), ("conv3_3", 1), ("conv4_3", 1)]:
+        assert float((torch.roll(f[scope], shift, dims=2) - f8[scope]).abs().max()) < 1e-5, scope
+    assert float((torch.roll(fc["conv4_3"], 1, dims=2) - fc8["conv4_3"]).abs().max()) > 1e-3   # zero padding breaks it
+    d = float((torch.roll(y, 8, dims=2) - y8).abs().max())
+    assert 0 < d < 0.2   # decoder: close, not exact (pre-crop LayerNorm)
+
+
+def test_wrap_pad_kat():
+    x = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(1, 2, 3, 4)[..., :1].repeat(1, 1, 1, 1)  # [1,2,3,1]
+    p = net_torch.wrap_pad(x, 1, 1)[0, :, :, 0].numpy()
+    row0, row1 = x[0, 0, :, 0].numpy(), x[0, 1, :, 0].numpy()
+    assert p.shape == (4, 5)
+    assert np.all(p[0] == 0) and np.all(p[-1] == 0)                       # zero rows above / below
+    assert list(p[1]) == [row0[-1], *row0, row0[0]] and list(p[2]) == [row1[-1], *row1, row1[0]]  # circular columns
+
+
+def test_color_scheme_known_answers():
+    """msi.py:166-268: blend weight +1 (w = 1) shows the reference PSV, -1 (w = 0) the background;
+    alpha_only copies the reference PSV; alphas are (pred + 1) / 2 in every scheme."""
+    L, H, W = 3, 2, 4
+    rng = np.random.default_rng(5)
+    psv = rng.uniform(-1, 1, (1, H, W, 6 * L)).astype(F32)
+    fg = psv[..., :3 * L].reshape(1, H, W, L, 3)
+    bg = psv[..., 3 * L:].reshape(1, H, W, L, 3)
+    a = rng.uniform(-1, 1, (1, H, W, L)).astype(F32)
+    bgc = rng.uniform(-1, 1, (1, H, W, 3)).astype(F32)
+    ones = np.ones((1, H, W, L), F32)
+    # blend_bg: [w | alpha | bg rgb]
+    r, bw, al, bgw = msi_np.assemble_rgba_ex(np.concatenate([ones, a, bgc], -1), psv, L, "blend_bg")
+    assert np.array_equal(r[..., :3], fg) and np.array_equal(al, (a + 1) / 2) and bgw is None and np.all(bw == 1)
+    r, *_ = msi_np.assemble_rgba_ex(np.concatenate([-ones, a, bgc], -1), psv, L, "blend_bg")
+    assert np.array_equal(r[..., :3], np.broadcast_to(bgc[:, :, :, None, :], fg.shape))
+    # blend_bg_psv: [w | alpha | bg_w | bg rgb]: bg_w = 1 reduces to blend_psv, bg_w = 0 to the background
+    w = rng.uniform(-1, 1, (1, H, W, L)).astype(F32)
+    r1, *_ = msi_np.assemble_rgba_ex(np.concatenate([w, a, ones, bgc], -1), psv, L, "blend_bg_psv")
+    r0, _, _ = msi_np.assemble_rgba(np.concatenate([w, a], -1), psv, L)
+    assert np.array_equal(r1, r0)
+    r2, _, _, bgw = msi_np.assemble_rgba_ex(np.concatenate([w, a, -ones, bgc], -1), psv, L, "blend_bg_psv")
+    assert np.array_equal(r2[..., :3], np.broadcast_to(bgc[:, :, :, None, :], fg.shape)) and np.all(bgw == 0)
+    # alpha_only: [alpha]
+    r, bw, al, _ = msi_np.assemble_rgba_ex(a, psv, L, "alpha_only")
+    assert np.array_equal(r[..., :3], fg) and np.array_equal(r[..., 3], (a + 1) / 2) and bw is None
+    assert msi_np.color_pred_channels("blend_bg_psv", 32) == 99 and msi_np.color_pred_channels("alpha_only", 32) == 32
+
+
+def test_perspective_centre_ray_known_answer():
+    """spherical.py:367-401: with no rotation and no offset the ray through the image centre is
+    (0, 0, -0.05): it hits every sphere at (0, 0, -R), i.e. theta = -atan2(-R, 0) = +pi/2, phi = 0,
+    whatever the radius: u = ((3 pi / 2 - pi / W) / (2 pi - 2 pi / W)) (W - 1), v = (H - 1) / 2."""
+    W, H, tw, th = 64, 32, 9, 5   # odd target size: the centre pixel sits at S = T = 0
+    uv = g.intersect_perspective(np.eye(4, dtype=F32), np.zeros(3, F32), np.array([1.0, 7.0, 100.0], F32), 3, 1, W, H,
+                                 tw, th)
+    assert uv.shape == (3, th, tw, 2)
+    u_want = ((1.5 * np.pi - np.pi / W) / (2 * np.pi - 2 * np.pi / W)) * (W - 1)
+    assert np.allclose(uv[:, th // 2, tw // 2, 0], u_want, atol=1e-3)
+    assert np.allclose(uv[:, th // 2, tw // 2, 1], (H - 1) / 2.0, atol=1e-3)
+    # left-right symmetric in v, and the viewing-window pose for window 0 is the identity
+    assert np.allclose(uv[..., 1], uv[:, :, ::-1, 1], atol=1e-4)
+    assert np.allclose(g.viewing_window_pose(0), np.eye(4), atol=1e-7)
+    r3 = g.viewing_window_pose(3)[:3, :3]
+    assert np.allclose(r3 @ r3.T, np.eye(3), atol=1e-6) and np.allclose(r3[0, 2], -1.0, atol=1e-6)
