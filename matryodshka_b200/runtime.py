@@ -48,9 +48,10 @@ class NetEngine:
         self.variant = variant
         self.device = torch.device(device)
         self.H, self.W, self.c_in, self.c_out, self.ngf = H, W, c_in, c_out, ngf
-        # the tensor-core kernels tile Cout in 64s: a head with 2L+3 / 3L+3 / L outputs (blend_bg,
-        # blend_bg_psv, alpha_only) is padded with zero weights and the extra channels are dropped
-        self.c_out_eng = -(-c_out // 64) * 64 if conv_impl == "tcgen05" else c_out
+        # the tensor-core kernels tile Cout in 64s (the SIMT kernel in 4s): a head with 2L+3 / 3L+3 / L outputs
+        # (blend_bg, blend_bg_psv, alpha_only) is padded with zero weights and the extra channels are dropped
+        q = 64 if conv_impl == "tcgen05" else 4
+        self.c_out_eng = -(-c_out // q) * q
         self.max_batch = max_batch
         self.conv_impl, self.precision = conv_impl, precision
         self._h = c_void_p()

@@ -8,7 +8,7 @@ elementwise kernels does [TF-1.14].  Python-float constants such as
 ``np.pi / width`` are evaluated in float64 and rounded once to ``dt`` where
 they meet an array, as ``tf.convert_to_tensor`` does.
 
-PARITY UNPINNED -- see oracle/__init__.py.
+PINNED bit for bit to the reference's own code run over a restated TF op layer (tests/golden/reference_run.npz) -- see oracle/__init__.py.
 """
 from __future__ import annotations
 

@@ -10,7 +10,9 @@ in = out_index * scale;  lower = floor(in);  upper = min(ceil(in), in_size - 1);
 top = tl + (tr - tl) * x_lerp;  bottom = bl + (br - bl) * x_lerp;  out = top + (bottom - top) * y_lerp,
 all in float32.
 
-PARITY UNPINNED -- see oracle/__init__.py.
+PARITY UNPINNED for this file: test.py:284-394 is script code inside main() and is not run by oracle/refrun; the
+sweep, reprojection and compositing functions it calls are the pinned ones (see oracle/__init__.py), the align-corners
+bilinear resize is restated [TF-1.14 tf.image.resize].
 """
 from __future__ import annotations
 

@@ -9,7 +9,7 @@ msi_render_equirect_depth (:384-405).
 The reference only works at batch 1 on this path (test.py:89; SURVEY.md 0.3);
 batches here mean B independent frames, each run through the B=1 path.
 
-PARITY UNPINNED -- see oracle/__init__.py.
+PINNED to the reference's own code run over a restated TF op layer (tests/golden/reference_run.npz) -- see oracle/__init__.py.
 """
 from __future__ import annotations
 

@@ -21,7 +21,7 @@ Tensors are NHWC at the API, as in the reference.  Variable names follow the TF
 checkpoint: ``net/<scope>/weights``, ``net/<scope>/LayerNorm/{beta,gamma}``,
 ``net/color_pred/biases``.
 
-PARITY UNPINNED -- see oracle/__init__.py.
+PINNED (1e-5) to the reference's own nets.py run over a restated slim op layer (tests/golden/reference_run.npz) -- see oracle/__init__.py.
 """
 from __future__ import annotations
 
