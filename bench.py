@@ -351,7 +351,7 @@ def run_ours(args):
         n_layers = 18
         scopes, conv_ms, ln_ms = ["-"] * n_layers, np.full(n_layers, np.nan), np.full(n_layers, np.nan)
     else:
-        scopes, conv_ms, ln_ms, _ = profile_net_layers(pipe.net, (pipe.hi, pipe.lo), pipe.pred, reps=max(3, min(K, 10)))
+        scopes, conv_ms, ln_ms, _ = profile_net_layers(pipe.net, (pipe.hi, pipe.lo), pipe.pred_buf, reps=max(3, min(K, 10)))
     stage_ms = None if args.no_layer_profile else pipe.stage_times(reps=5)
     clocks = sampler.stop() if rank == 0 else None
 

@@ -124,6 +124,11 @@ int msi_rgba_assemble(const float* pred, const float* psv_f32, const void* psv_h
 int msi_rgba_assemble_ex(const float* pred, int n_pred, const float* psv_f32, const void* psv_hi, const void* psv_lo,
                          int c_stride, int B, int H, int W, int L, int mode, float* rgba, float* blend_weights,
                          float* alphas, float* bg_blend_weights, void* stream);
+/* Same, with the prediction's pixel stride given separately (pred_stride >= n_pred floats): reads the
+ * tensor-core net's output in place when its head is padded to a multiple of 64 channels. */
+int msi_rgba_assemble_strided(const float* pred, int n_pred, int pred_stride, const float* psv_f32, const void* psv_hi,
+                              const void* psv_lo, int c_stride, int B, int H, int W, int L, int mode, float* rgba,
+                              float* blend_weights, float* alphas, float* bg_blend_weights, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Stage 3 -- reproject the L spheres to the target position and over-composite

@@ -248,14 +248,14 @@ __global__ void __launch_bounds__(256) sweep_coords_kernel(PsvParams p, float* u
 __global__ void __launch_bounds__(256)
 rgba_assemble_kernel(const float* __restrict__ pred, const float* __restrict__ psv_f32,
                      const __half* __restrict__ psv_hi, const __half* __restrict__ psv_lo, int c_stride,
-                     long long npix, int L, float4* __restrict__ rgba, float* __restrict__ bw_out,
+                     long long npix, int L, int pred_stride, float4* __restrict__ rgba, float* __restrict__ bw_out,
                      float* __restrict__ al_out) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= npix * L) return;
     const long long pix = idx / L;
     const int l = (int)(idx % L);
-    const float w = (__ldg(pred + pix * 2 * L + l) + 1.0f) / 2.0f;
-    const float al = (__ldg(pred + pix * 2 * L + L + l) + 1.0f) / 2.0f;
+    const float w = (__ldg(pred + pix * pred_stride + l) + 1.0f) / 2.0f;
+    const float al = (__ldg(pred + pix * pred_stride + L + l) + 1.0f) / 2.0f;
     float fg[3], bg[3];
     if (psv_f32 != nullptr) {
         const float* f = psv_f32 + pix * 6 * L + 3 * l;
@@ -657,23 +657,15 @@ extern "C" int msi_sweep_coords(const float* poses, const float* baselines, cons
 extern "C" int msi_rgba_assemble(const float* pred, const float* psv_f32, const void* psv_hi, const void* psv_lo,
                                  int c_stride, int B, int H, int W, int L, float* rgba, float* blend_weights,
                                  float* alphas, void* stream) {
-    MSI_CHECK_ARG(B > 0 && H > 0 && W > 0 && L > 0, "rgba_assemble: bad shape");
-    MSI_CHECK_ARG(pred && rgba, "rgba_assemble: null pred/rgba");
-    MSI_CHECK_ARG(psv_f32 || (psv_hi && psv_lo), "rgba_assemble: need psv_f32 or the hi/lo pair");
-    if (!psv_f32) MSI_CHECK_ARG(c_stride >= 6 * L, "rgba_assemble: c_stride %d < 6L", c_stride);
-    const long long npix = (long long)B * H * W;
-    rgba_assemble_kernel<<<ceil_div(npix * L, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        pred, psv_f32, reinterpret_cast<const __half*>(psv_hi), reinterpret_cast<const __half*>(psv_lo), c_stride,
-        npix, L, reinterpret_cast<float4*>(rgba), blend_weights, alphas);
-    MSI_LAUNCH_CHECK();
-    return MSI_OK;
+    return msi_rgba_assemble_strided(pred, 2 * L, 2 * L, psv_f32, psv_hi, psv_lo, c_stride, B, H, W, L, MSI_COLOR_BLEND_PSV,
+                                     rgba, blend_weights, alphas, nullptr, stream);
 }
 
 // The other `which_color_pred` schemes of infer_msi (matryodshka/msi.py:166-273).  pred has n_pred
 // channels per pixel: blend_bg [w(L) | alpha(L) | bg rgb(3)], blend_bg_psv [w(L) | alpha(L) | bg_w(L) |
 // bg rgb(3)], alpha_only [alpha(L)].  Same op order as the reference's elementwise graph (no FMA).
 __global__ void __launch_bounds__(256)
-rgba_assemble_ex_kernel(const float* __restrict__ pred, int n_pred, const float* __restrict__ psv_f32,
+rgba_assemble_ex_kernel(const float* __restrict__ pred, int pred_stride, const float* __restrict__ psv_f32,
                         const __half* __restrict__ psv_hi, const __half* __restrict__ psv_lo, int c_stride,
                         long long npix, int L, int mode, float4* __restrict__ rgba, float* __restrict__ bw_out,
                         float* __restrict__ al_out, float* __restrict__ bgw_out) {
@@ -681,7 +673,7 @@ rgba_assemble_ex_kernel(const float* __restrict__ pred, int n_pred, const float*
     if (idx >= npix * L) return;
     const long long pix = idx / L;
     const int l = (int)(idx % L);
-    const float* pp = pred + pix * n_pred;
+    const float* pp = pred + pix * pred_stride;
     float fg[3], bg[3];
     if (psv_f32 != nullptr) {
         const float* f = psv_f32 + pix * 6 * L + 3 * l;
@@ -736,21 +728,36 @@ rgba_assemble_ex_kernel(const float* __restrict__ pred, int n_pred, const float*
 extern "C" int msi_rgba_assemble_ex(const float* pred, int n_pred, const float* psv_f32, const void* psv_hi,
                                     const void* psv_lo, int c_stride, int B, int H, int W, int L, int mode, float* rgba,
                                     float* blend_weights, float* alphas, float* bg_blend_weights, void* stream) {
-    if (mode == MSI_COLOR_BLEND_PSV) {
-        MSI_CHECK_ARG(n_pred == 2 * L, "rgba_assemble_ex: blend_psv needs n_pred == 2L (got %d, L=%d)", n_pred, L);
-        return msi_rgba_assemble(pred, psv_f32, psv_hi, psv_lo, c_stride, B, H, W, L, rgba, blend_weights, alphas, stream);
-    }
-    MSI_CHECK_ARG(B > 0 && H > 0 && W > 0 && L > 0, "rgba_assemble_ex: bad shape");
-    MSI_CHECK_ARG(pred && rgba, "rgba_assemble_ex: null pred/rgba");
-    MSI_CHECK_ARG(psv_f32 || (psv_hi && psv_lo), "rgba_assemble_ex: need psv_f32 or the hi/lo pair");
-    const int need = mode == MSI_COLOR_BLEND_BG ? 2 * L + 3 : mode == MSI_COLOR_BLEND_BG_PSV ? 3 * L + 3 : mode == MSI_COLOR_ALPHA_ONLY ? L : -1;
-    MSI_CHECK_ARG(need > 0, "rgba_assemble_ex: unknown mode %d", mode);
-    MSI_CHECK_ARG(n_pred == need, "rgba_assemble_ex: mode %d needs %d prediction channels, got %d", mode, need, n_pred);
-    if (!psv_f32) MSI_CHECK_ARG(c_stride >= 6 * L, "rgba_assemble_ex: c_stride %d < 6L", c_stride);
+    return msi_rgba_assemble_strided(pred, n_pred, n_pred, psv_f32, psv_hi, psv_lo, c_stride, B, H, W, L, mode, rgba,
+                                     blend_weights, alphas, bg_blend_weights, stream);
+}
+
+// All colour schemes, with the prediction's pixel stride separate from its channel count: the tensor-core
+// net pads its head to a multiple of 64 output channels, and the pipeline reads that buffer in place.
+extern "C" int msi_rgba_assemble_strided(const float* pred, int n_pred, int pred_stride, const float* psv_f32,
+                                         const void* psv_hi, const void* psv_lo, int c_stride, int B, int H, int W, int L,
+                                         int mode, float* rgba, float* blend_weights, float* alphas,
+                                         float* bg_blend_weights, void* stream) {
+    MSI_CHECK_ARG(B > 0 && H > 0 && W > 0 && L > 0, "rgba_assemble: bad shape");
+    MSI_CHECK_ARG(pred && rgba, "rgba_assemble: null pred/rgba");
+    MSI_CHECK_ARG(psv_f32 || (psv_hi && psv_lo), "rgba_assemble: need psv_f32 or the hi/lo pair");
+    const int need = mode == MSI_COLOR_BLEND_PSV ? 2 * L : mode == MSI_COLOR_BLEND_BG ? 2 * L + 3
+                     : mode == MSI_COLOR_BLEND_BG_PSV ? 3 * L + 3 : mode == MSI_COLOR_ALPHA_ONLY ? L : -1;
+    MSI_CHECK_ARG(need > 0, "rgba_assemble: unknown mode %d", mode);
+    MSI_CHECK_ARG(n_pred == need, "rgba_assemble: mode %d needs %d prediction channels, got %d (L=%d)", mode, need, n_pred, L);
+    MSI_CHECK_ARG(pred_stride >= n_pred, "rgba_assemble: pred_stride %d < n_pred %d", pred_stride, n_pred);
+    if (!psv_f32) MSI_CHECK_ARG(c_stride >= 6 * L, "rgba_assemble: c_stride %d < 6L", c_stride);
     const long long npix = (long long)B * H * W;
-    rgba_assemble_ex_kernel<<<ceil_div(npix * L, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        pred, n_pred, psv_f32, reinterpret_cast<const __half*>(psv_hi), reinterpret_cast<const __half*>(psv_lo), c_stride,
-        npix, L, mode, reinterpret_cast<float4*>(rgba), blend_weights, alphas, bg_blend_weights);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __half* hi = reinterpret_cast<const __half*>(psv_hi);
+    const __half* lo = reinterpret_cast<const __half*>(psv_lo);
+    if (mode == MSI_COLOR_BLEND_PSV)
+        rgba_assemble_kernel<<<ceil_div(npix * L, 256), 256, 0, st>>>(pred, psv_f32, hi, lo, c_stride, npix, L, pred_stride,
+                                                                      reinterpret_cast<float4*>(rgba), blend_weights, alphas);
+    else
+        rgba_assemble_ex_kernel<<<ceil_div(npix * L, 256), 256, 0, st>>>(pred, pred_stride, psv_f32, hi, lo, c_stride, npix, L,
+                                                                         mode, reinterpret_cast<float4*>(rgba), blend_weights,
+                                                                         alphas, bg_blend_weights);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

@@ -9,6 +9,7 @@ bit-reproducible on the GPU (csrc/geom_device.cuh).
 """
 from __future__ import annotations
 
+import ctypes
 import functools
 
 import numpy as np
@@ -134,24 +135,46 @@ def color_pred_channels(which_color_pred, num_msi_planes):
     return {"blend_psv": 2 * L, "blend_bg": 2 * L + 3, "blend_bg_psv": 3 * L + 3, "alpha_only": L}[which_color_pred]
 
 
-def rgba_assemble_ex(pred, psv, which_color_pred, num_msi_planes, *, want_weights=False):
-    """msi_rgba_assemble_ex: RGBA layers for any `which_color_pred` (msi.py:117-268).  pred
-    [B,H,W,n_pred]; psv float32 [B,H,W,6L].  Returns (rgba, blend_weights, alphas, bg_blend_weights)."""
+def _pixel_stride(pred):
+    """Floats between consecutive pixels of a [B,H,W,C] prediction that may be a channel slice of a wider,
+    contiguous buffer (the tensor-core net pads its head to a multiple of 64 channels); None if it is not."""
+    B, H, W, C = pred.shape
+    st = pred.stride()
+    if st[3] == 1 and st[2] >= C and st[1] == W * st[2] and st[0] == H * st[1]:
+        return st[2]
+    return None
+
+
+def rgba_assemble_ex(pred, psv=None, which_color_pred="blend_psv", num_msi_planes=None, *, want_weights=False,
+                     hi_lo=None, c_stride=None, out=None):
+    """msi_rgba_assemble_strided: RGBA layers for any `which_color_pred` (msi.py:117-268).  pred [B,H,W,n_pred]
+    (read in place when it is a channel slice of the net's padded output); psv float32 [B,H,W,6L] or the fp16
+    (hi, lo) operand pair.  Returns (rgba, blend_weights, alphas, bg_blend_weights)."""
     _lib.require_cuda()
     lib = _lib.load()
     B, H, W, n_pred = pred.shape
     L = num_msi_planes
     assert n_pred == color_pred_channels(which_color_pred, L), (n_pred, which_color_pred, L)
-    assert psv.shape[-1] == 6 * L, "the colour schemes need num_psv_planes == num_msi_planes"
     dev = pred.device
+    stride = _pixel_stride(pred)
+    if stride is None:
+        pred, stride = pred.contiguous(), n_pred
+    hi = lo = None
+    cs = 6 * L
+    if psv is None:
+        hi, lo = hi_lo
+        cs = int(c_stride if c_stride is not None else hi.shape[-1])
+    else:
+        assert psv.shape[-1] == 6 * L, "the colour schemes need num_psv_planes == num_msi_planes"
+        psv = psv.contiguous()
     mk = lambda: torch.empty((B, H, W, L), dtype=torch.float32, device=dev)
-    rgba = torch.empty((B, H, W, L, 4), dtype=torch.float32, device=dev)
+    rgba = out if out is not None else torch.empty((B, H, W, L, 4), dtype=torch.float32, device=dev)
     bw = mk() if want_weights and which_color_pred != "alpha_only" else None
     al = mk() if want_weights else None
     bgw = mk() if want_weights and which_color_pred == "blend_bg_psv" else None
-    check(lib.msi_rgba_assemble_ex(ptr(pred.contiguous()), n_pred, ptr(psv.contiguous()), None, None, 6 * L, B, H, W, L,
-                                   _lib.COLOR_MODES[which_color_pred], ptr(rgba), ptr(bw), ptr(al), ptr(bgw),
-                                   stream_ptr()), "msi_rgba_assemble_ex")
+    check(lib.msi_rgba_assemble_strided(ctypes.c_void_p(pred.data_ptr()), n_pred, stride, ptr(psv), ptr(hi), ptr(lo), cs, B, H, W, L,
+                                        _lib.COLOR_MODES[which_color_pred], ptr(rgba), ptr(bw), ptr(al), ptr(bgw),
+                                        stream_ptr()), "msi_rgba_assemble_strided")
     return rgba, bw, al, bgw
 
 

@@ -160,21 +160,25 @@ class MSIPipeline:
 
     Stages (all kernels of libmsi_b200.so, enqueued on one stream, graph-captured per batch size):
       K1 msi_psv_build      -> PSV as the net's fp16 hi/lo operand, written straight into the net input
-      K2 msi_net_forward    -> pred [B,H,W,2L]
-      K4 msi_rgba_assemble  -> RGBA layers [B,H,W,L,4]
+      K2 msi_net_forward    -> pred [B,H,W,n_pred] (pixel stride = the engine's padded head width)
+      K4 msi_rgba_assemble_strided -> RGBA layers [B,H,W,L,4]
       K5 msi_render_composite -> rgb / depth (float32 + uint8)
+    ``coord_net`` picks nets.msi_coord_train_net / nets.msi_train_net (FLAGS.coord_net, msi.py:120-127) and
+    ``which_color_pred`` the head and assembly (msi.py:107-273), as MSI.infer_msi does.
     """
 
     def __init__(self, weights, H=320, W=640, num_planes=32, ngf=64, batch=1, device="cuda",
                  min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16x3",
-                 img_dtype=torch.float32, use_graph=True):
+                 img_dtype=torch.float32, use_graph=True, coord_net=True, which_color_pred="blend_psv"):
         _lib.require_cuda()
         from .msi import MSI
         self.device = torch.device(device)
         self.H, self.W, self.P, self.B = H, W, num_planes, batch
         self.planes = MSI().inv_depths(min_depth, max_depth, num_planes)
-        self.net = NetEngine(weights, H, W, 6 * num_planes, 2 * num_planes, ngf, self.device, max_batch=batch,
-                             conv_impl=conv_impl, precision=precision)
+        self.which_color_pred = which_color_pred
+        self.n_pred = ops.color_pred_channels(which_color_pred, num_planes)
+        self.net = NetEngine(weights, H, W, 6 * num_planes, self.n_pred, ngf, self.device, max_batch=batch,
+                             conv_impl=conv_impl, precision=precision, variant="coord" if coord_net else "wrap")
         dev = self.device
         B = batch
         self.img_dtype = img_dtype
@@ -185,9 +189,15 @@ class MSIPipeline:
         self.tgt_pose_rt = torch.eye(4, device=dev).reshape(1, 16).repeat(B, 1).contiguous()
         self.tgt_pos = torch.zeros((B, 3), device=dev)
         self.depths = torch.tensor(self.planes, dtype=torch.float32, device=dev)
-        self.hi, self.lo = self.net.input_buffers(B)
+        if coord_net:
+            self.hi, self.lo = self.net.input_buffers(B)   # the sweep kernel writes the net's operand in place
+        else:                                              # wrap-padded input: dense operand, copied in by the forward
+            self.hi = torch.zeros((B, H, W, self.net.in_c_stride), dtype=torch.float16, device=dev)
+            self.lo = torch.zeros_like(self.hi)
         self.psv_scratch = ops.psv_scratch(B, H, W, dev)
-        self.pred = torch.empty((B, H, W, 2 * num_planes), dtype=torch.float32, device=dev)
+        # the engine's head may be wider than n_pred (padded for the kernels' channel tiling): K4 reads it in place
+        self.pred_buf = torch.empty((B, H, W, self.net.c_out_eng), dtype=torch.float32, device=dev)
+        self.pred = self.pred_buf[..., :self.n_pred]
         self.rgba = torch.empty((B, H, W, num_planes, 4), dtype=torch.float32, device=dev)
         self.out = {
             "rgb": torch.empty((B, H, W, 3), dtype=torch.float32, device=dev),
@@ -221,11 +231,13 @@ class MSIPipeline:
                   "msi_psv_build")
 
         def k2():
-            self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred)
+            self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred_buf)
 
         def k4():
-            check(lib.msi_rgba_assemble(ptr(self.pred), None, ptr(self.hi), ptr(self.lo), self.net.in_c_stride,
-                                        B, H, W, P, ptr(self.rgba), None, None, stream_ptr()), "msi_rgba_assemble")
+            check(lib.msi_rgba_assemble_strided(ptr(self.pred_buf), self.n_pred, self.net.c_out_eng, None, ptr(self.hi),
+                                                ptr(self.lo), self.net.in_c_stride, B, H, W, P,
+                                                _lib.COLOR_MODES[self.which_color_pred], ptr(self.rgba), None, None, None,
+                                                stream_ptr()), "msi_rgba_assemble_strided")
 
         def k5():
             g = self.gather

@@ -356,3 +356,32 @@ def test_train_net_encoder_circular_shift_equivariance_on_gpu():
         b = eng.read_activation(s, B)
         err = float((torch.roll(a[s], shift, dims=2) - b).abs().max())
         assert err < 1e-4, (s, err)
+
+
+@pytest.mark.parametrize("coord_net,which,P", [(True, "blend_psv", 16), (False, "blend_psv", 32), (True, "blend_bg", 32),
+                                               (False, "blend_bg_psv", 32), (True, "alpha_only", 32)])
+def test_pipeline_variants_equal_the_mirror_api(coord_net, which, P):
+    """The graph-captured MSIPipeline with msi_train_net (coord_net = False), the other colour schemes and a head
+    that is padded for the tensor-core kernel (2 * 16 = 32 -> 64 channels) agrees with MSI.infer_msi +
+    msi_render_equirect to rounding (same kernels; the pipeline reads the padded prediction in place and assembles
+    from the fp16 hi + lo PSV operand, ~22 bits, where the mirror API assembles from the float32 PSV)."""
+    H, W, ngf = 32, 64, 64
+    ref, src = synth.ods_pair(1, H, W, seed=31)
+    tp = synth.target_positions(1, 31)
+    wts = synth.net_weights(6 * P, ops.color_pred_channels(which, P), ngf, coord=coord_net)
+    pipe = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, coord_net=coord_net, which_color_pred=which)
+    pipe.set_inputs(ref, src, tgt_pos=tp)
+    pipe.step()
+    pipe.step()   # second step = graph replay
+    torch.cuda.synchronize()
+    m = MSI(weights=wts, config=MSIConfig(coord_net=coord_net), device=DEV)
+    planes = m.inv_depths(1, 100, P)
+    eye = synth.identity_poses(1)
+    out, _ = m.infer_msi(_t(src), _t(ref), None, None, eye, eye, synth.intrinsics(1), which, P, planes, ngf=ngf)
+    assert float((pipe.rgba - out["rgba_layers"]).abs().max()) < 1e-5
+    res = m.msi_render_equirect(out["rgba_layers"], np.eye(4, dtype=F32)[None], tp, planes)
+    assert float((pipe.out["rgb"] - res["rgb"]).abs().max()) < 1e-5
+    assert int((pipe.out["depth_u8"].int() - res["depth_u8"].int()).abs().max()) <= 1
+    want, _ = msi_np.infer_msi(src, ref, eye, eye, synth.intrinsics(1), P, planes, wts, ngf=ngf, coord_net=coord_net,
+                               which_color_pred=which)
+    assert float(np.abs(pipe.rgba.cpu().numpy() - want["rgba_layers"]).max()) < TOL
