@@ -109,6 +109,7 @@ struct TcParams {
 
 struct TcPlan {
     TcParams p;
+    int pair;                 // 1: the halo kernel runs as CTA pairs (tcgen05 cta_group::2, W rows split between the CTAs)
     int halo;                 // 1: conv_halo_tcgen05_kernel (a_map[s][0] = 5-D hi+lo map, w_map[0] = 4-D [kb][hi|lo][cout][64])
     int n_tile, split;
     int cl;                   // cluster size along M: CTAs of a cluster multicast the W tile to each other
@@ -308,6 +309,57 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mas
         : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) forms -----------------------------------------------------------------
+// In a cluster of two CTAs the shared-window address of the peer differs in bit 24; clearing it
+// addresses the leader (even rank) CTA's copy of a barrier (CUTLASS: Sm100MmaPeerBitMask).
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;
+// TMA loads issued by BOTH CTAs of the pair; the transaction bytes count on the LEADER's barrier
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// one MMA over both CTAs: M = 256 (128 rows from each CTA's A tile), B rows split between the two
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on this offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's barrier
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kLeaderMask) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_pair(int n) {  // M = 256 across the CTA pair
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 // ---- debugging trace (MSI_TC_TRACE) ----
 constexpr int kTraceRegion = 1024, kTraceRegions = 10;
 __device__ __forceinline__ long long globaltimer_ns() {
@@ -332,7 +384,7 @@ __device__ __forceinline__ void trace_ev(long long* tr, int region, int idx) {
 // the TMA loads of the next tile).  With STAGE each warp writes its 32 rows x 32 columns into a
 // private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by the row: conflict-free) and reads it
 // back so that 8 lanes cover one row: a warp store then touches 4 full lines.
-template <int N_TILE, int SPLIT, int CL, bool STAGE = false>
+template <int N_TILE, int SPLIT, int CL, bool STAGE = false, bool PAIR = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, const int quarter, const int lane,
                                               const int lx, const int ly, const int cluster_id, const int n_clusters,
                                               const int cta_rank, const uint32_t tmem_base, const uint32_t tfull0,
@@ -406,14 +458,28 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
         for (int c = c_begin; c < c_end; c += 32) {
             uint32_t r[32];
             uint32_t r2[SPLIT ? 32 : 1];
-            tmem_ld32(taddr + (uint32_t)c, r);
-            if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
+            if (!PAIR) {
+                tmem_ld32(taddr + (uint32_t)c, r);
+                if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
+            } else {
+                // CTA-pair layout of the 2N accumulator columns (see conv_halo_tcgen05_kernel<.., PAIR>):
+                // cout c < N/2: hi.hi + lo.hi in column c, hi.lo in column 3N/2 + c;
+                // cout c >= N/2: hi.hi in column N/2 + c, hi.lo + lo.hi in column c
+                const bool low = c < N_TILE / 2;
+                tmem_ld32(taddr + (uint32_t)(low ? c : N_TILE / 2 + c), r);
+                tmem_ld32(taddr + (uint32_t)(low ? 3 * N_TILE / 2 + c : c), r2);
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c + 32 >= c_end) {
                 // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+                if (lane == 0) {
+                    if (PAIR)
+                        mbar_arrive_leader(tempty0 + 8u * acc);  // the pair's one MMA thread lives in the leader CTA
+                    else
+                        mbar_arrive(tempty0 + 8u * acc);
+                }
             }
             if (counted) {
 #pragma unroll
@@ -757,13 +823,22 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 //   warp 0  A producer (halo ring, a_stages slots)      warp 2  W producer (w_stages slots of T taps)
 //   warp 1  MMA issuer + TMEM allocator                 warps 3-10  epilogue (shared with the kernel above)
 constexpr int kHaloThreads = 96 + 32 * kEpiWarps;
-template <int N_TILE, int T>
+template <int N_TILE, int T, bool PAIR>
 __global__ void __launch_bounds__(kRegCapThreads, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                          const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
     constexpr int kAccCols = 2 * N_TILE;
     constexpr int kTmemCols = 2 * kAccCols;
-    constexpr int kWTapBytes = 2 * N_TILE * kBlockK * 2;  // [W_hi | W_lo] of one tap
+    // PAIR: two CTAs of a cluster share every weight tile (tcgen05 cta_group::2, M = 256 = both CTAs'
+    // pixel tiles): each holds HALF of the rows, arranged [W_hi rows r*N/2.. | W_lo rows (1-r)*N/2..] for
+    // rank r, so that the wide MMA (N = 2N_TILE: first half of the columns from the leader's rows,
+    // second half from the peer's) and the narrow one (A_lo x the first N/2 rows of each CTA = W_hi)
+    // put the three partial products of a cout into two accumulator columns (see epilogue_role).
+    // Halves the weight bytes per SM: a deeper W ring in the same shared memory.
+    constexpr int kWTapBytes = (PAIR ? 1 : 2) * N_TILE * kBlockK * 2;  // this CTA's W rows of one tap
+    const int cta_rank = PAIR ? (int)(blockIdx.x & 1u) : 0;
+    const int cluster_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const bool is_leader = cta_rank == 0;
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ int s_launch;  // trace only
@@ -809,7 +884,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             mbar_init(afull0 + 8u * s, 1);
             mbar_init(aempty0 + 8u * s, 1);
             mbar_init(tfull0 + 8u * s, 1);
-            mbar_init(tempty0 + 8u * s, kEpiWarps);
+            mbar_init(tempty0 + 8u * s, PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues arrive on the leader
         }
         for (int s = 0; s < 8; ++s) {
             mbar_init(wfull0 + 8u * s, 1);
@@ -822,12 +897,18 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         if (p.nsrc == 2) prefetch_tmap(&a1);
     }
     if (warp == 2 && lane == 0) prefetch_tmap(&wmap);
-    if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_smem);
+    if (warp == 1) {
+        if (PAIR)
+            tmem_alloc_pair<kTmemCols>(&tmem_base_smem);
+        else
+            tmem_alloc<kTmemCols>(&tmem_base_smem);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
-    const int n_ctas = gridDim.x;
+    const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // stride of the unit loops (clusters)
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 0);
     const int tr_launch = (p.trace != nullptr) ? s_launch : -1;
     if (threadIdx.x == 0) trace_g(p.trace, tr_launch, 1);
@@ -845,17 +926,24 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             int tr_i = 0;
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas) {
-                const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
+            for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
+                const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
                 const int hx = tc.ox0 + p.halo_x0[tc.cls] + p.x_off, hy = tc.oy0 + p.halo_y0[tc.cls];
                 const int cf = (p.orient == 0) ? hx : hy, cs = (p.orient == 0) ? hy : hx;
                 for (int ch = 0; ch < chunks_total; ++ch) {
                     mbar_wait(aempty0 + 8u * stage, phase ^ 1u);
                     trace_ev(p.trace, 4, tr_i++);
-                    mbar_expect_tx(afull0 + 8u * stage, a_tx);
                     const bool second = ch >= chunks0;
-                    tma_load_5d(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
-                                (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                    if (!PAIR) {
+                        mbar_expect_tx(afull0 + 8u * stage, a_tx);
+                        tma_load_5d(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
+                                    (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                    } else {
+                        // both CTAs' halos count on the leader's barrier, which the leader arms for both
+                        if (is_leader) mbar_expect_tx(afull0 + 8u * stage, 2u * a_tx);
+                        tma_load_5d_pair(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
+                                         (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                    }
                     if (++stage == a_stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -869,16 +957,22 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             int stage = 0;
             int tr_i = 0;
             uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas) {
-                const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
+            for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
+                const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
                 const int ntaps = s_ntaps[tc.cls];
                 int kb = tc.cls * chunks_total * ntaps;
                 const int n_slots = chunks_total * (ntaps / T);
                 for (int sl = 0; sl < n_slots; ++sl, kb += T) {
                     mbar_wait(wempty0 + 8u * stage, phase ^ 1u);
                     trace_ev(p.trace, 2, tr_i);
-                    mbar_expect_tx(wfull0 + 8u * stage, w_slot_bytes);
-                    tma_load_4d(w_ring + (uint32_t)stage * w_slot_bytes, &wmap, wfull0 + 8u * stage, 0, tc.n0, 0, kb);
+                    if (!PAIR) {
+                        mbar_expect_tx(wfull0 + 8u * stage, w_slot_bytes);
+                        tma_load_4d(w_ring + (uint32_t)stage * w_slot_bytes, &wmap, wfull0 + 8u * stage, 0, tc.n0, 0, kb);
+                    } else {  // this rank's half of the rows ([kb][rank][cout][64] packing)
+                        if (is_leader) mbar_expect_tx(wfull0 + 8u * stage, 2u * w_slot_bytes);
+                        tma_load_4d_pair(w_ring + (uint32_t)stage * w_slot_bytes, &wmap, wfull0 + 8u * stage, 0, tc.n0,
+                                         cta_rank, kb);
+                    }
                     trace_ev(p.trace, 3, tr_i++);
                     if (++stage == w_stages) {
                         stage = 0;
@@ -887,14 +981,14 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                 }
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
+    } else if (warp == 1 && (!PAIR || is_leader)) {
+        // =============================== MMA issuer (PAIR: the leader CTA issues for both) ===============================
         // The issue thread is the critical resource (measured: ~80 clk per MMA issue + ~300 clk per
         // barrier round trip), so the full barrier of the NEXT slot is tested before this slot's MMAs
         // are issued (its latency hides behind them) and the tap offsets are read before the wait.
         const bool leader = elect_one();
-        constexpr uint32_t idesc_wide = make_idesc(2 * N_TILE);
-        constexpr uint32_t idesc_n = make_idesc(N_TILE);
+        constexpr uint32_t idesc_wide = PAIR ? make_idesc_pair(2 * N_TILE) : make_idesc(2 * N_TILE);
+        constexpr uint32_t idesc_n = PAIR ? make_idesc_pair(N_TILE) : make_idesc(N_TILE);
         constexpr uint64_t kDescFlags = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         const uint64_t a_desc_hi = kDescFlags | ((uint64_t)(p.PF * 8) << 32);  // SBO = PF rows of 128 bytes (>> 4)
         const uint64_t lo_adv = (uint64_t)(p.a_rows * 8);                       // hi halo -> lo halo
@@ -905,7 +999,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         int tr_slot = 0, tr_chunk = 0;
         trace_ev(leader ? p.trace : nullptr, 7, 1);
         const int units_per_cls = p.units_per_col * p.n_tiles;
-        for (int unit = blockIdx.x; unit < p.total_units; unit += n_ctas, ++local) {
+        for (int unit = cluster_id; unit < p.total_units; unit += n_ctas, ++local) {
             const int cls = (p.ncls > 1) ? unit / units_per_cls : 0;  // (a division only for the deconv classes)
             const int slots_per_chunk = s_ntaps[cls] / T;
             const int acc = local & 1;
@@ -959,15 +1053,29 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t adv = (uint64_t)(k * 2);
-                                umma_f16(d_tmem, da + adv, db + adv, idesc_wide, accumulate);  // A_hi x [W_hi | W_lo]
-                                accumulate = 1u;
-                                umma_f16(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);    // A_lo x W_hi
+                                if (!PAIR) {
+                                    umma_f16(d_tmem, da + adv, db + adv, idesc_wide, accumulate);  // A_hi x [W_hi | W_lo]
+                                    accumulate = 1u;
+                                    umma_f16(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);    // A_lo x W_hi
+                                } else {
+                                    umma_f16_pair(d_tmem, da + adv, db + adv, idesc_wide, accumulate);
+                                    accumulate = 1u;
+                                    umma_f16_pair(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);
+                                }
                             }
                         }
-                        umma_commit(wempty0 + 8u * cur);
-                        if (sl == slots_per_chunk - 1) {
-                            umma_commit(a_done_bar);
-                            if (ch == chunks_total - 1) umma_commit(tfull0 + 8u * acc);
+                        if (!PAIR) {
+                            umma_commit(wempty0 + 8u * cur);
+                            if (sl == slots_per_chunk - 1) {
+                                umma_commit(a_done_bar);
+                                if (ch == chunks_total - 1) umma_commit(tfull0 + 8u * acc);
+                            }
+                        } else {  // the slots and the accumulators of BOTH CTAs
+                            umma_commit_pair(wempty0 + 8u * cur);
+                            if (sl == slots_per_chunk - 1) {
+                                umma_commit_pair(a_done_bar);
+                                if (ch == chunks_total - 1) umma_commit_pair(tfull0 + 8u * acc);
+                            }
                         }
                         trace_ev(p.trace, 1, tr_slot);
                     }
@@ -977,26 +1085,31 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             }
         }
         if (leader) trace_g(p.trace, tr_launch, 4);
-    } else {
+    } else if (warp >= 3) {
         // =============================== epilogue (warps 3..10) ===============================
         const int row = (warp & 3) * 32 + lane;  // M index inside the tile: 8-pixel group = row / 8
         const int lx = (p.orient == 0) ? (row & 7) : (row >> 3);
         const int ly = (p.orient == 0) ? (row >> 3) : (row & 7);
         if (p.stage_out)
-            epilogue_role<N_TILE, 1, 1, true>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base, tfull0,
-                                              tempty0, &s_is_last, s_red, tr_launch, w_ring + (uint32_t)w_stages * w_slot_bytes);
+            epilogue_role<N_TILE, 1, PAIR ? 2 : 1, true, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas, cta_rank,
+                                                               tmem_base, tfull0, tempty0, &s_is_last, s_red, tr_launch,
+                                                               w_ring + (uint32_t)w_stages * w_slot_bytes);
         else
-            epilogue_role<N_TILE, 1, 1, false>(p, warp - 3, warp & 3, lane, lx, ly, (int)blockIdx.x, n_ctas, 0, tmem_base,
-                                               tfull0, tempty0, &s_is_last, s_red, tr_launch);
+            epilogue_role<N_TILE, 1, PAIR ? 2 : 1, false, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas, cta_rank,
+                                                                tmem_base, tfull0, tempty0, &s_is_last, s_red, tr_launch);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 2);
     if (threadIdx.x == 0 && *(volatile int*)&s_is_last >= 0) trace_g(p.trace, tr_launch, 7);
+    if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch its memory / barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (PAIR)
+            tmem_dealloc_pair<kTmemCols>(tmem_base);
+        else
+            tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -1045,7 +1158,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams q) {
 
 // K-block-major packing of the halo kernel: [kb][hi|lo][cout][64] with kb = (cls * chunks + chunk) *
 // ntaps + tap, so that the [W_hi | W_lo] tiles of T consecutive taps of one chunk are ONE 4-D TMA box.
-__global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, int chunks_total, int ntaps) {
+// pair_tile > 0 (CTA-pair kernel, pair_tile = N_TILE): the second index is the CTA rank instead, and the
+// rows of every N tile are arranged [W_hi of couts r * N/2 .. | W_lo of couts (1 - r) * N/2 ..] for rank r.
+__global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, int chunks_total, int ntaps, int pair_tile) {
     const long long total = (long long)q.ncls * chunks_total * ntaps * q.cout * kBlockK;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= total) return;
@@ -1073,8 +1188,16 @@ __global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, in
     }
     __half h, l;
     split_half(v * MSI_WEIGHT_SCALE, h, l);
-    q.hi[(((size_t)kb * 2 + 0) * q.cout + n) * kBlockK + k64] = h;
-    q.hi[(((size_t)kb * 2 + 1) * q.cout + n) * kBlockK + k64] = l;
+    if (pair_tile == 0) {
+        q.hi[(((size_t)kb * 2 + 0) * q.cout + n) * kBlockK + k64] = h;
+        q.hi[(((size_t)kb * 2 + 1) * q.cout + n) * kBlockK + k64] = l;
+    } else {
+        const int half_rows = pair_tile / 2;
+        const int tile0 = (n / pair_tile) * pair_tile, in_tile = n % pair_tile;
+        const int r = in_tile / half_rows, i = in_tile % half_rows;  // W_hi of this cout lives in rank r, W_lo in rank 1 - r
+        q.hi[(((size_t)kb * 2 + r) * q.cout + tile0 + i) * kBlockK + k64] = h;
+        q.hi[(((size_t)kb * 2 + (1 - r)) * q.cout + tile0 + half_rows + i) * kBlockK + k64] = l;
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -1170,7 +1293,7 @@ int encode_act_map5(CUtensorMap* m, const __half* hi, const __half* lo, int C, i
 }
 
 // 4-D weight map of the halo kernel over [kb][hi|lo][cout][64], box {64, n_tile, 2, T}
-int encode_w_map4(CUtensorMap* m, const __half* base, int cout, int nkb, int n_tile, int T) {
+int encode_w_map4(CUtensorMap* m, const __half* base, int cout, int nkb, int n_tile, int T, int planes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -1178,7 +1301,7 @@ int encode_w_map4(CUtensorMap* m, const __half* base, int cout, int nkb, int n_t
     }
     cuuint64_t dims[4] = {(cuuint64_t)kBlockK, (cuuint64_t)cout, 2, (cuuint64_t)nkb};
     cuuint64_t strides[3] = {(cuuint64_t)kBlockK * 2, (cuuint64_t)cout * kBlockK * 2, (cuuint64_t)2 * cout * kBlockK * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile, 2, (cuuint32_t)T};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile, (cuuint32_t)planes, (cuuint32_t)T};  // planes: 2 = [hi | lo], 1 = one rank (pair)
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1277,10 +1400,10 @@ long long* trace_buffer() {
 // Launch attribute for programmatic dependent launch (MSI_PDL=0 turns it off): the kernel may begin
 // before the previous kernel in the stream has finished; it calls griddepcontrol.wait before
 // touching anything that kernel wrote.  `first` = no kernel precedes it in the forward (memset).
-template <int N_TILE, int T>
+template <int N_TILE, int T, bool PAIR>
 int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_tcgen05_kernel<N_TILE, T>;
+    auto kern = conv_halo_tcgen05_kernel<N_TILE, T, PAIR>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) {
@@ -1295,11 +1418,22 @@ int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st
     cfg.blockDim = dim3(kHaloThreads);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->a_map[0][0], plan->a_map[1][0], plan->w_map[0], p);
     if (e != cudaSuccess) {
         set_error("cudaLaunchKernelEx(conv_halo_tcgen05_kernel<%d,%d>, grid %d) failed: %s", N_TILE, T, plan->grid,
@@ -1346,7 +1480,12 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
         if (env && plan->n_tile == 64 && atoi(env) == 1) p.T = 1;  // measured: 667 clk per tap (issue-thread bound) vs 572 for T = 3
     }
     if (ntaps % p.T != 0 || p.PS > 256 || p.PF > 256) return MSI_ERR_UNSUPPORTED;
-    const int w_slot = p.T * 2 * plan->n_tile * kBlockK * 2;
+    if (plan->pair && plan->n_tile == 64 && p.T == 1) return MSI_ERR_UNSUPPORTED;  // (no such instantiation)
+    // A pair synchronises its two CTAs at every unit boundary (accumulator hand-over across the cluster): with only
+    // a few W slots per unit that costs more than the halved weight traffic wins (measured: conv8_2, 3 slots per
+    // unit, 56 us as pairs vs 51 us; every layer with >= 8 slots per unit is 10-18 % faster as pairs).
+    if (plan->pair && (p.chunks[0] + p.chunks[1]) * (ntaps / p.T) < 6) return MSI_ERR_UNSUPPORTED;
+    const int w_slot = p.T * (plan->pair ? 1 : 2) * plan->n_tile * kBlockK * 2;  // pair: this CTA's half of the rows
     const int budget = kMaxDynSmem - 1024 - p.a_stages * p.a_slot_bytes;
     const int stage_bytes = kEpiWarps * 4096;  // one 32 x 32 float tile per epilogue warp
     {
@@ -1360,6 +1499,10 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     plan->smem_bytes = 1024 + p.a_stages * p.a_slot_bytes + p.w_stages * w_slot + (p.stage_out ? stage_bytes : 0);
     p.tiles_x = (p.Mw + ext + p.BW - 1) / p.BW;
     p.tiles_y = (p.Mh + ext + p.BH - 1) / p.BH;
+    // Pairs only where ONE frame has at least two pixel tiles: the choice must not depend on the batch size, because the
+    // pair kernel sums a cout's three partial products in a different order than the single-CTA kernel and a frame's
+    // result has to be the same bits whatever batch it is part of (tests: batch of 3 == three single frames).
+    if (plan->pair && p.tiles_x * p.tiles_y < 2) return MSI_ERR_UNSUPPORTED;
     if (L.w_lo != L.w_hi + (size_t)L.ncls * L.cout * L.K) return MSI_ERR_UNSUPPORTED;  // one [.. hi|lo ..] buffer
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s)
@@ -1367,7 +1510,7 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
                              p.orient, p.PF, p.PS);
     if (rc == MSI_OK && L.nsrc == 1) plan->a_map[1][0] = plan->a_map[0][0];
     const int nkb = L.ncls * (p.chunks[0] + p.chunks[1]) * ntaps;
-    if (rc == MSI_OK) rc = encode_w_map4(&plan->w_map[0], L.w_hi, L.cout, nkb, plan->n_tile, p.T);
+    if (rc == MSI_OK) rc = encode_w_map4(&plan->w_map[0], L.w_hi, L.cout, nkb, plan->n_tile, p.T, plan->pair ? 1 : 2);
     return rc;
 }
 
@@ -1475,7 +1618,18 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
                           ((L.kind == kConv && L.stride == 1) || L.kind == kDeconv);
         if (want) {
             TcPlan saved = *plan;
-            if (plan_halo(plan, L, srcs, max_batch) == MSI_OK) {
+            // CTA pairs (tcgen05 cta_group::2): the two CTAs of a cluster take two consecutive pixel tiles of a
+            // column (cl = 2) and each holds half of the weight rows.  Default on (MSI_CONV_PAIR=0 turns it off);
+            // plan_halo declines it for layers with too little work per unit, which then run one CTA per unit.
+            const char* pe = getenv("MSI_CONV_PAIR");
+            plan->pair = !(pe && atoi(pe) == 0) ? 1 : 0;
+            if (plan->pair) plan->cl = 2;
+            int hrc = plan_halo(plan, L, srcs, max_batch);
+            if (hrc != MSI_OK && plan->pair) {
+                *plan = saved;
+                hrc = plan_halo(plan, L, srcs, max_batch);
+            }
+            if (hrc == MSI_OK) {
                 plan->halo = 1;
                 const char* tr = getenv("MSI_TC_TRACE");  // debugging: scope name of the layer to trace
                 plan->p.trace = (tr && strcmp(tr, L.scope) == 0) ? trace_buffer() : nullptr;
@@ -1553,7 +1707,7 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
     const TcPlan* plan = reinterpret_cast<const TcPlan*>(L.tc_plan);
     if (plan && plan->halo)
         pack_weights_halo_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q, plan->p.chunks[0] + plan->p.chunks[1],
-                                                                        plan->p.taps[0].n);
+                                                                        plan->p.taps[0].n, plan->pair ? plan->n_tile : 0);
     else
         pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q);
     MSI_LAUNCH_CHECK();
@@ -1587,15 +1741,22 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
     }
     int rc;
     const bool pdl = after_kernel && pdl_enabled();
-    if (plan->halo) {
+    if (plan->halo && plan->pair) {
         if (plan->n_tile == 128)
-            rc = launch_halo<128, 1>(plan, p, pdl, st);
+            rc = launch_halo<128, 1, true>(plan, p, pdl, st);
         else if (p.T == 3)
-            rc = launch_halo<64, 3>(plan, p, pdl, st);
-        else if (p.T == 1)
-            rc = launch_halo<64, 1>(plan, p, pdl, st);
+            rc = launch_halo<64, 3, true>(plan, p, pdl, st);
         else
-            rc = launch_halo<64, 2>(plan, p, pdl, st);
+            rc = launch_halo<64, 2, true>(plan, p, pdl, st);
+    } else if (plan->halo) {
+        if (plan->n_tile == 128)
+            rc = launch_halo<128, 1, false>(plan, p, pdl, st);
+        else if (p.T == 3)
+            rc = launch_halo<64, 3, false>(plan, p, pdl, st);
+        else if (p.T == 1)
+            rc = launch_halo<64, 1, false>(plan, p, pdl, st);
+        else
+            rc = launch_halo<64, 2, false>(plan, p, pdl, st);
     } else {
         rc = (plan->n_tile == 64) ? launch_tc_nt<64>(plan, p, pdl, st) : launch_tc_nt<128>(plan, p, pdl, st);
     }

@@ -385,3 +385,32 @@ def test_pipeline_variants_equal_the_mirror_api(coord_net, which, P):
     want, _ = msi_np.infer_msi(src, ref, eye, eye, synth.intrinsics(1), P, planes, wts, ngf=ngf, coord_net=coord_net,
                                which_color_pred=which)
     assert float(np.abs(pipe.rgba.cpu().numpy() - want["rgba_layers"]).max()) < TOL
+
+
+@pytest.mark.parametrize("H,W,B", [(64, 128, 1), (24, 72, 3), (8, 16, 1)])
+def test_cta_pair_kernel_matches_single_cta_kernel(monkeypatch, H, W, B):
+    """Default (MSI_CONV_PAIR unset / 1) vs MSI_CONV_PAIR=0: the halo kernel as CTA pairs (tcgen05 cta_group::2, each CTA holds half of the weight
+    rows) computes the same products as the single-CTA halo kernel; per-layer raw outputs agree to float32
+    accumulation noise.  (24, 72, 3) has odd tile counts: the surplus CTA of the last pair is masked; at (8, 16, 1)
+    the deepest layers have a single tile and fall back to one CTA per unit."""
+    P, ngf = 32, 64
+    rng = np.random.default_rng(13)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    monkeypatch.setenv("MSI_CONV_PAIR", "0")
+    ea = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B)
+    a = ea.forward(_t(x))
+    monkeypatch.setenv("MSI_CONV_PAIR", "1")
+    eb = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B)
+    b = eb.forward(_t(x))
+    torch.cuda.synchronize()
+    errs = {}
+    for scope in ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1", "conv4_2",
+                  "conv4_3", "conv6_1", "conv6_2", "conv6_3", "conv7_1", "conv7_2", "conv8_1", "conv8_2"]:
+        errs[scope] = float((ea.read_raw(scope, B) - eb.read_raw(scope, B)).abs().max())
+    errs["pred"] = float((a - b).abs().max())
+    assert max(errs.values()) < 5e-5, errs
+    if H * W >= 2 * 128:   # conv1_1 has at least two pixel tiles per frame, so it runs as pairs (different summation order)
+        assert errs["conv1_1"] > 0.0, "the pair kernel was not selected (outputs are bit-identical)"
+    else:                  # one tile per frame at every level: nothing pairs up, same kernel, same bits
+        assert max(errs.values()) == 0.0
