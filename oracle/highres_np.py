@@ -10,9 +10,11 @@ in = out_index * scale;  lower = floor(in);  upper = min(ceil(in), in_size - 1);
 top = tl + (tr - tl) * x_lerp;  bottom = bl + (br - bl) * x_lerp;  out = top + (bottom - top) * y_lerp,
 all in float32.
 
-PARITY UNPINNED for this file: test.py:284-394 is script code inside main() and is not run by oracle/refrun; the
-sweep, reprojection and compositing functions it calls are the pinned ones (see oracle/__init__.py), the align-corners
-bilinear resize is restated [TF-1.14 tf.image.resize].
+PINNED bit for bit (tests/test_reference_golden.py::test_high_res_rerender_bit_exact) to the reference run of
+oracle/refrun/run_reference.py::run_highres: the graph part of test.py:300-340 goes through the reference's own
+MSI.format_network_input (one tensor plane) and msi_render_equirect_view_single; what is restated there, as here, is
+the per-plane feed loop and host-side composite of test.py:354-383 (script code inside main()) and the align-corners
+bilinear resize [TF-1.14 tf.image.resize].
 """
 from __future__ import annotations
 

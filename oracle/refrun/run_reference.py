@@ -32,6 +32,7 @@ SEED = 8964
 SMALL = dict(H=16, W=32, P=4, NGF=8)       # same inputs as tests/golden/make_golden.py
 TC = dict(H=16, W=32, P=32, NGF=64)
 GEOM = dict(H=32, W=64, P=8)
+HIGHRES = dict(h=8, w=16, Hh=40, Wh=96, P=4)
 FULL = dict(H=320, W=640, P=32)            # BASELINE.json configs[1]: digests only
 
 
@@ -173,6 +174,52 @@ def run_tc(tf, MSI, out):
     set_test_flags(tf)
 
 
+def run_highres(tf, MSI, out):
+    """The plane-streamed high-res re-render, test.py:296-383: the graph part (:300-340) through the reference's own
+    MSI methods, the per-plane feed loop and the host-side over-composite (:354-383) restated here as test.py has
+    them (they are script code inside main())."""
+    from matryodshka_b200 import synth
+    h, w, Hh, Wh, P = HIGHRES["h"], HIGHRES["w"], HIGHRES["Hh"], HIGHRES["Wh"], HIGHRES["P"]
+    rng = np.random.default_rng(SEED + 5)
+    hres_ref, hres_src = synth.ods_pair(1, Hh, Wh, SEED + 5)
+    blend_weights = rng.uniform(0, 1, (1, h, w, P)).astype(np.float32)   # blend_weights.npy / alphas.npy of the low-res pass
+    alphas = rng.uniform(0, 1, (1, h, w, P)).astype(np.float32)
+    tgt_pos = np.array([[0.02, -0.03, 0.01]], np.float32)
+    eye, intr = synth.identity_poses(1), synth.intrinsics(1)
+    out["highres/blend_weights"], out["highres/alphas"], out["highres/tgt_pos"] = blend_weights, alphas, tgt_pos
+    set_test_flags(tf)
+    tf.set_named_tensor("ref_pose_inv:0", np.linalg.inv(eye))
+    T = lambda a: tf.convert_to_tensor(a, tf.float32)  # noqa: E731
+    model = MSI()
+    psv_planes = model.inv_depths(1, 100, P)
+    hres_ref_image = model.preprocess_image(T(hres_ref))
+    hres_src_image = model.preprocess_image(T(hres_src))
+    hres_output, hres_depth = None, 0.
+    for i in range(P):
+        curr_psv_plane = tf.slice(tf.constant(psv_planes), [i], [1])
+        hres_net_input = model.format_network_input(hres_ref_image, hres_src_image, T(eye), T(eye), curr_psv_plane, T(intr))
+        uw = tf.image.resize(T(blend_weights[:, :, :, i:i + 1]), [Hh, Wh], align_corners=True,
+                             method=tf.image.ResizeMethod.BILINEAR)
+        ucurr_alpha = tf.image.resize(T(alphas[:, :, :, i:i + 1]), [Hh, Wh], align_corners=True,
+                                      method=tf.image.ResizeMethod.BILINEAR)
+        ufg_rgb = hres_net_input[:, :, :, 0:3]
+        ubg_rgb = hres_net_input[:, :, :, 3:6]
+        ucurr_rgb = uw * ufg_rgb + (1 - uw) * ubg_rgb
+        urgba_layers = tf.reshape(tf.concat([ucurr_rgb, ucurr_alpha], axis=3), [1, Hh, Wh, 1, 4])
+        single = model.msi_render_equirect_view_single(urgba_layers, tf.expand_dims(tf.eye(4), axis=0), T(tgt_pos),
+                                                       curr_psv_plane, T(intr))
+        cur = np.asarray(single)[0].astype(np.float32)
+        rgb, alpha = cur[:, :, :, :3], cur[:, :, :, 3:]
+        alpha_as_depth = np.tile(cur[:, :, :, 3:], (1, 1, 1, 3))
+        if i == 0:
+            hres_output = rgb
+        else:
+            hres_output = hres_output * (1. - alpha) + rgb * alpha
+            hres_depth = (i / P) * alpha_as_depth + hres_depth * (1.0 - alpha_as_depth)
+    out["highres/output"] = f32(hres_output[0])
+    out["highres/depth"] = f32(hres_depth[0])
+
+
 def sweep_uv(tf, spherical, pj, H, W, depths, pose, order, baseline):
     """The coordinate half of projector.sweep_one (projector.py:138-158) for one batch item."""
     S, T = spherical.lat_long_grid([H, W])
@@ -265,9 +312,10 @@ def main():
     out, meta = {}, {}
     run_small(tf, MSI, out)
     run_tc(tf, MSI, out)
+    run_highres(tf, MSI, out)
     run_geometry(tf, spherical, pj, sampling, MSI, out)
     run_full_digests(tf, spherical, pj, MSI, meta)
-    meta.update(seed=SEED, small=SMALL, tc=TC, geom=GEOM, reference=REFERENCE, reference_revision=reference_revision(),
+    meta.update(seed=SEED, small=SMALL, tc=TC, geom=GEOM, highres=HIGHRES, reference=REFERENCE, reference_revision=reference_revision(),
                 numpy=np.__version__,
                 files=["geometry/spherical.py", "geometry/projector.py", "geometry/sampling.py", "matryodshka/msi.py",
                        "matryodshka/nets.py"],

@@ -16,6 +16,7 @@ matryodshka-gpu.yml:14,43-44), eagerly, in float32 with one rounding per op:
 * ``tf.matmul``: sum over k in index order, separately rounded products and sums;
 * ``tf.mod`` floor-mod; ``tf.add_n`` left to right; ``tf.gather_nd``; ``tf.image.convert_image_dtype``
   (uint8 -> float: ``x * (1/255)``; float -> uint8: truncating ``cast(x * 255.5)``, no saturation);
+  ``tf.image.resize`` (bilinear, align_corners=True, the 1.14 legacy scaler);
 * ``slim.conv2d`` / ``conv2d_transpose`` (SAME / VALID, stride, rate; bias only without a normalizer),
   ``slim.layer_norm`` (``nn.moments`` over axes 1..3, ``nn.batch_normalization`` with eps 1e-12),
   ``slim.arg_scope``; variables are read from ``set_variables({name: array})`` by their checkpoint names;
@@ -362,7 +363,37 @@ def _convert_image_dtype(image, dtype, saturate=False, name=None):
     raise NotImplementedError((image.dtype, dtype))
 
 
-image = types.SimpleNamespace(convert_image_dtype=_convert_image_dtype)
+def _resize_bilinear(images, size, method=0, align_corners=False, name=None):
+    """[TF-1.14 tf.image.resize / ResizeBilinear kernel, align_corners=True, legacy scaler]: scale = (in - 1) /
+    (out - 1) in float32; in = out_index * scale; lower = floor(in), upper = min(ceil(in), in - 1), lerp = in - lower;
+    top = tl + (tr - tl) * x_lerp; bottom = bl + (br - bl) * x_lerp; out = top + (bottom - top) * y_lerp."""
+    assert method == 0 and align_corners, "only BILINEAR with align_corners=True is on the path (test.py:319-325)"
+    x = np.asarray(images, np.float32)
+    B, h, w, C = x.shape
+    oh, ow = int(size[0]), int(size[1])
+
+    def axis(n_in, n_out):
+        scale = np.float32((n_in - 1) / np.float32(n_out - 1)) if n_out > 1 else np.float32(0)
+        pos = np.arange(n_out).astype(np.float32) * scale
+        lo = np.floor(pos)
+        hi = np.minimum(np.ceil(pos), n_in - 1)
+        return lo.astype(np.int64), hi.astype(np.int64), (pos - lo).astype(np.float32)
+
+    y0, y1, ly = axis(h, oh)
+    x0, x1, lx = axis(w, ow)
+    out = np.empty((B, oh, ow, C), np.float32)
+    for i in np.arange(oh):      # written row by row, independently of oracle/highres_np.py
+        tl, tr = x[:, y0[i]][:, x0], x[:, y0[i]][:, x1]
+        bl, br = x[:, y1[i]][:, x0], x[:, y1[i]][:, x1]
+        top = tl + (tr - tl) * lx[None, :, None]
+        bottom = bl + (br - bl) * lx[None, :, None]
+        out[:, i] = top + (bottom - top) * ly[i]
+    return _t(out)
+
+
+image = types.SimpleNamespace(convert_image_dtype=_convert_image_dtype, resize=_resize_bilinear,
+                              resize_images=_resize_bilinear,
+                              ResizeMethod=types.SimpleNamespace(BILINEAR=0, NEAREST_NEIGHBOR=1))
 
 
 # ---- tf.nn + tf.contrib.slim ---------------------------------------------------------------------------

@@ -137,3 +137,16 @@ def test_sweep_and_sphere_coordinates(ref):
         assert np.abs(got[0] - ref["geom/sphere_uv_%d" % k]).max() < TOL
     out = ops.resample(_t(ref["geom/resample_img"]), _t(ref["geom/resample_pix"]))
     assert _err(out, ref["geom/resample_out"]) < 1e-5
+
+
+def test_high_res_rerender(ref):
+    """test.py:296-383 on the GPU (msi_highres_plane / msi_highres_composite) against the reference run."""
+    from matryodshka_b200.highres import high_res_rerender
+    m = ref["meta"]["highres"]
+    hres_ref, hres_src = synth.ods_pair(1, m["Hh"], m["Wh"], ref["meta"]["seed"] + 5)
+    eye, intr = synth.identity_poses(1), synth.intrinsics(1)
+    planes = MSI().inv_depths(1, 100, m["P"])
+    rgb, dep = high_res_rerender(_t(hres_ref), _t(hres_src), _t(ref["highres/blend_weights"]), _t(ref["highres/alphas"]), eye,
+                                 eye, intr, ref["highres/tgt_pos"], planes)
+    assert _err(rgb, ref["highres/output"]) < TOL
+    assert _err(dep, ref["highres/depth"]) < TOL

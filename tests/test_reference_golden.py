@@ -168,6 +168,20 @@ def test_full_size_digests(ref):
     assert sha(uv) == full["sphere_uv"]["sha256"]
 
 
+def test_high_res_rerender_bit_exact(ref):
+    """test.py:296-383 (plane-streamed high-res re-render): the reference's format_network_input on ONE tensor plane
+    and msi_render_equirect_view_single, the align-corners resize of the stand-in, test.py's host-side composite."""
+    from oracle import highres_np
+    m = ref["meta"]["highres"]
+    hres_ref, hres_src = synth.ods_pair(1, m["Hh"], m["Wh"], ref["meta"]["seed"] + 5)
+    eye, intr = synth.identity_poses(1), synth.intrinsics(1)
+    planes = msi_np.inv_depths(1, 100, m["P"])
+    rgb, dep = highres_np.high_res_rerender(hres_ref, hres_src, ref["highres/blend_weights"], ref["highres/alphas"], eye, eye,
+                                            intr, ref["highres/tgt_pos"], planes)
+    assert np.array_equal(rgb, ref["highres/output"])
+    assert np.array_equal(dep, ref["highres/depth"])
+
+
 def test_fixture_names_the_reference_files(ref):
     meta = ref["meta"]
     assert set(meta["file_sha256"]) == {"geometry/spherical.py", "geometry/projector.py", "geometry/sampling.py",
