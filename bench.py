@@ -371,7 +371,8 @@ def run_ours(args):
         mma_mult = 3.0 if (args.precision == "fp16x3" and args.conv_impl == "tcgen05") else 1.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         roofline = {
-            "kernel": "conv_igemm_tcgen05 (17 conv/deconv launches + 1x1 head)" if args.conv_impl == "tcgen05"
+            "kernel": "conv_halo_tcgen05 as cta_group::2 CTA pairs (13 launches; conv8_2 single-CTA) + conv_igemm_tcgen05 "
+                      "(3 stride-2 convs + 1x1 head)" if args.conv_impl == "tcgen05"
                       else "conv_simt (fp32 CUDA-core bring-up back end)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": conv_traffic(H, W, P, Bp, args),
