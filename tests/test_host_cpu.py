@@ -150,3 +150,53 @@ def test_driver_scene_dirname_on_video():
     assert drv.scene_dirname(f, s) == "video_run7_apartment_0_000100020003"
     f = types.SimpleNamespace(test_type="on_video", prefix="")
     assert drv.scene_dirname(f, s) == "video_apartment_0_000100020003"
+
+
+def _header_prototypes():
+    """{name: [parameter type strings]} for every function include/msi_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "msi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"^\s*#.*$", "", hdr, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"\b(msi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        protos[m.group(1)] = [re.sub(r"\s+[A-Za-z_][A-Za-z0-9_]*(\[\d*\])*$", "", p).strip() if "*" not in p.split()[-1]
+                              else p.rsplit("*", 1)[0].strip() + "*" for p in params]
+    return protos
+
+
+def _type_class(c_type):
+    if "*" in c_type:
+        return "ptr"
+    if c_type in ("float",):
+        return "float"
+    if c_type in ("double",):
+        return "double"
+    if c_type in ("size_t", "long long", "unsigned long long", "uint64_t", "int64_t"):
+        return "int64"
+    return "int32"
+
+
+def _ctypes_class(t):
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+        return "ptr"
+    if t is ctypes.c_float:
+        return "float"
+    if t is ctypes.c_double:
+        return "double"
+    if t in (ctypes.c_size_t, ctypes.c_longlong, ctypes.c_uint64, ctypes.c_int64):
+        return "int64"
+    return "int32"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """A drifted argtypes list corrupts the call silently (wrong registers): every entry of _lib.SIGNATURES must have
+    the header's parameter count and, per parameter, the same class (pointer / 32-bit int / 64-bit int / float)."""
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (restype, argtypes) in _lib.SIGNATURES.items():
+        want = [_type_class(p) for p in protos[name]]
+        got = [_ctypes_class(t) for t in argtypes]
+        assert got == want, (name, protos[name], got)
