@@ -41,14 +41,20 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# Libraries (NCCL's version banner, for one) write to fd 1.  Keep the real stdout for the ONE JSON
-# line and send everything else that lands on fd 1 to stderr.
-_JSON_FD = os.dup(1)
-os.dup2(2, 1)
+# Libraries (NCCL's version banner, for one) write to fd 1.  main() keeps the real stdout for the ONE JSON
+# line and sends everything else that lands on fd 1 to stderr (not done at import: tests import this module).
+_JSON_FD = None
+
+
+def reserve_stdout_for_json():
+    global _JSON_FD
+    if _JSON_FD is None:
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: dict):
-    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def load_peaks():
@@ -140,29 +146,71 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (the reference itself needs Python 2.7 + TF 1.14)
 # ------------------------------------------------------------------------------------------------
+def _chunks(n, k):
+    """n items in at most k contiguous runs: [(start, stop), ...]."""
+    k = max(1, min(k, n))
+    base, extra = divmod(n, k)
+    out, a = [], 0
+    for i in range(k):
+        b = a + base + (1 if i < extra else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+def oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, n_threads):
+    """One frame of the oracle port with the geometry spread over the host cores: the sweep planes and the
+    reprojected layers are independent, so each thread runs the oracle's own functions on a run of planes (NumPy
+    releases the GIL inside its loops) and the pieces are reassembled in the reference's channel / layer order.
+    Same functions, same arithmetic, same bits as oracle.msi_np.infer_msi + msi_render_equirect_view / _depth
+    (checked in tests/test_host_cpu.py); the reference's TF-CPU graph would likewise use all cores."""
+    from oracle import geometry_np as g, msi_np, net_torch
+    eye_p, intr = np.eye(4, dtype=np.float32)[None], np.array([[[0.032, 0, 0], [0, 1, 0], [0, 0, 1]]], np.float32)
+    t0 = time.perf_counter()
+    ref_p, src_p = msi_np.preprocess_image(ref), msi_np.preprocess_image(src)
+    runs = _chunks(P, n_threads)
+    parts = list(pool.map(lambda ab: msi_np.format_network_input(ref_p, src_p, eye_p, eye_p, planes[ab[0]:ab[1]], intr),
+                          runs))
+    # each part is [1,H,W,6k] = [ref-eye planes | src-eye planes]; the full tensor is [all ref | all src]
+    net_input = np.concatenate([q[..., :q.shape[-1] // 2] for q in parts] + [q[..., q.shape[-1] // 2:] for q in parts], axis=3)
+    with torch.no_grad():
+        pred = net_torch.msi_coord_train_net(torch.from_numpy(net_input), 2 * P, wts, ngf=ngf).numpy()
+    rgba, _, _ = msi_np.assemble_rgba(pred, net_input, P)
+    t1 = time.perf_counter()
+    layers = np.transpose(rgba, (3, 0, 1, 2, 4))                       # [L,B,H,W,4]
+    depths = np.asarray(planes, np.float32).reshape(P, 1)
+
+    def project(ab):
+        return g.projective_forward_sphere(layers[ab[0]:ab[1]], None, eye_p, tp, depths[ab[0]:ab[1]])
+
+    # the reference reprojects twice, once for the view and once for the depth (msi.py:384-429)
+    proj_v = np.concatenate(list(pool.map(project, runs)), axis=0)
+    view = g.over_composite([proj_v[i] for i in range(P)])
+    proj_d = np.concatenate(list(pool.map(project, runs)), axis=0)
+    depth = g.over_composite_depth([proj_d[i] for i in range(P)])
+    u8 = (msi_np.deprocess_image(view), msi_np.deprocess_depth_image(depth))
+    t2 = time.perf_counter()
+    return dict(net_input=net_input, rgba=rgba, view=view, depth=depth, u8=u8), (t1 - t0, t2 - t1)
+
+
 def oracle_frame_seconds(H, W, P, ngf, n_frames, seed=8964):
-    """Times the CPU oracle on n_frames full frames (PSV + net + assemble + view + depth render).
-    Returns (seconds per frame list, per-stage seconds of the last frame)."""
+    """Times the CPU oracle on n_frames full frames (PSV + net + assemble + view + depth render) with all host
+    cores.  Returns (seconds per frame list, per-stage seconds of the last frame)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import msi_np
     from matryodshka_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     ref, src = synth.ods_pair(1, H, W, seed)
     wts = synth.net_weights(6 * P, 2 * P, ngf, seed)
     tp = synth.target_positions(1, seed)
     planes = msi_np.inv_depths(1, 100, P)
-    eye = np.eye(4, dtype=np.float32)[None]
     times, stages = [], {}
-    for _ in range(n_frames):
-        t0 = time.perf_counter()
-        out, _ = msi_np.infer_msi(src, ref, synth.identity_poses(1), synth.identity_poses(1), synth.intrinsics(1),
-                                  P, planes, wts, ngf=ngf)
-        t1 = time.perf_counter()
-        view = msi_np.msi_render_equirect_view(out["rgba_layers"], eye, tp, planes)
-        depth = msi_np.msi_render_equirect_depth(out["rgba_layers"], eye, tp, planes)
-        msi_np.deprocess_image(view), msi_np.deprocess_depth_image(depth)
-        t2 = time.perf_counter()
-        times.append(t2 - t0)
-        stages = {"infer_msi_s": t1 - t0, "render_view_and_depth_s": t2 - t1}
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        for _ in range(n_frames):
+            _, (ta, tb) = oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, cores)
+            times.append(ta + tb)
+            stages = {"infer_msi_s": ta, "render_view_and_depth_s": tb}
     return times, stages
 
 
@@ -193,8 +241,8 @@ def run_reference(args):
                    "note": "oracle port of the reference path on host cores; the reference itself needs "
                            "Python 2.7 + TensorFlow 1.14 and cannot run here"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full frame(s): NumPy float32 geometry (1 thread) + torch-CPU "
-                                   f"float32 conv net ({torch.get_num_threads()} threads); stages {stages}"},
+                         "sample": f"{len(times)} full frame(s): NumPy float32 geometry (planes / layers over {cores} threads) + "
+                                   f"torch-CPU float32 conv net ({torch.get_num_threads()} threads); stages {stages}"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -413,7 +461,8 @@ def run_ours(args):
             times, stages = oracle_frame_seconds(H, W, P, ngf, 1)
             cpu = {"value": 1.0 / times[0], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"1 full frame of the same workload through the oracle port: NumPy float32 geometry "
-                             f"(1 thread) + torch-CPU float32 net ({torch.get_num_threads()} threads); {stages}"}
+                             f"(planes / layers over {os.cpu_count() or 1} threads) + torch-CPU float32 net "
+                             f"({torch.get_num_threads()} threads); {stages}"}
         ws_gb = (pipe.net.ws_bytes + pipe.rgba.numel() * 4) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -465,6 +514,7 @@ def main():
     ap.add_argument("--no-layer-profile", action="store_true",
                     help="skip the per-kernel timing pass (roofline numbers become NaN); for ncu launch lists")
     args = ap.parse_args()
+    reserve_stdout_for_json()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

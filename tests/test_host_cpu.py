@@ -200,3 +200,26 @@ def test_ctypes_signatures_match_the_header_prototypes():
         want = [_type_class(p) for p in protos[name]]
         got = [_ctypes_class(t) for t in argtypes]
         assert got == want, (name, protos[name], got)
+
+
+def test_threaded_cpu_arm_equals_the_oracle_bit_for_bit():
+    """bench.py's CPU arm spreads the oracle's planes / layers over the host cores; the reassembled frame must be
+    the same bits as the plain oracle calls (same functions on runs of planes)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import bench
+    from oracle import msi_np
+    H, W, P, ngf, seed = 16, 32, 8, 8, 3
+    ref, src = synth.ods_pair(1, H, W, seed)
+    wts = synth.net_weights(6 * P, 2 * P, ngf, seed)
+    tp = synth.target_positions(1, seed)
+    planes = msi_np.inv_depths(1, 100, P)
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        got, _ = bench.oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, 3)
+    eye = synth.identity_poses(1)
+    out, net_input = msi_np.infer_msi(src, ref, eye, eye, synth.intrinsics(1), P, planes, wts, ngf=ngf)
+    assert np.array_equal(got["net_input"], net_input)
+    assert np.array_equal(got["rgba"], out["rgba_layers"])
+    e4 = np.eye(4, dtype=np.float32)[None]
+    assert np.array_equal(got["view"], msi_np.msi_render_equirect_view(out["rgba_layers"], e4, tp, planes))
+    assert np.array_equal(got["depth"], msi_np.msi_render_equirect_depth(out["rgba_layers"], e4, tp, planes))
+    assert bench._chunks(32, 16) == [(2 * i, 2 * i + 2) for i in range(16)] and bench._chunks(3, 8) == [(0, 1), (1, 2), (2, 3)]
