@@ -26,7 +26,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REFERENCE = os.environ.get("MSI_REFERENCE_ROOT", "/root/reference")
-OUT = os.path.join(REPO, "tests", "golden", "reference_run.npz")
+OUT = os.environ.get("MSI_REFRUN_OUT") or os.path.join(REPO, "tests", "golden", "reference_run.npz")
 
 SEED = 8964
 SMALL = dict(H=16, W=32, P=4, NGF=8)       # same inputs as tests/golden/make_golden.py
