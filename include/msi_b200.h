@@ -92,6 +92,35 @@ int msi_psv_build(const void* ref, const void* src, int img_dtype, int preproces
  * NULL it runs the single-kernel form.  Results are identical. */
 size_t msi_psv_scratch_bytes(int B, int H, int W);
 
+/* ------------------------------------------------------------------------- *
+ * Stage 1 with cached sweep coordinates (static rig).
+ * The sample coordinates of the sweep depend on (poses, baselines, depths, H, W)
+ * only -- not on the images -- and the reference's data has one rig for a whole
+ * sequence (identity eye poses, one baseline: data_loader.py:146-174), so the
+ * chain backproject_spherical -> apply_pose -> project_ods (spherical.py:116-129,
+ * projector.py:275-291, spherical.py:170-233) is evaluated ONCE into a table and
+ * every frame is a pure gather + bilinear blend (sampling.py:135-197) from it.
+ * The table is written by the same device functions as msi_psv_build, so
+ * msi_psv_gather returns the same bits as msi_psv_build (validity mask included:
+ * an invalid sample carries its (1,1)).  Rebuild the table when a pose, a
+ * baseline or the depths change; the jittered sweep (msi.py:1118-1120) keeps
+ * msi_psv_build.
+ *
+ * table   [frames][H][W][P] float4 = (u_ref, v_ref, u_src, v_src), 16-byte aligned
+ *         device memory of msi_sweep_table_bytes(frames, H, W, P) bytes; frames = 1
+ *         (one rig shared by every frame of a batch) or B (poses [frames,2,16],
+ *         baselines [frames]).
+ * msi_psv_gather: table_frames must be 1 or B; other arguments as msi_psv_build.
+ * ------------------------------------------------------------------------- */
+size_t msi_sweep_table_bytes(int frames, int H, int W, int P);
+int msi_sweep_table_build(const float* poses, const float* baselines, const float* depths,
+                          const float* cos_s, const float* sin_s, const float* cos_t, const float* sin_t,
+                          int frames, int H, int W, int P, void* table, void* stream);
+int msi_psv_gather(const void* ref, const void* src, int img_dtype, int preprocess,
+                   const void* table, int table_frames, int B, int H, int W, int P,
+                   float* out_f32, void* out_hi, void* out_lo, int c_stride,
+                   void* scratch, size_t scratch_bytes, void* stream);
+
 /* Sample coordinates only (spherical.project_ods, spherical.py:170-233, after
  * backproject + apply_pose): uv [B,2,P,H,W,2] (x=u, y=v) and valid [B,2,P,H,W]
  * (uint8, 0 where disc < 0 and the sample snaps to pixel (1,1), :226-229). */
@@ -146,6 +175,17 @@ int msi_rgba_assemble_strided(const float* pred, int n_pred, int pred_stride, co
  * out_rgb     [B,H,W,3] float32 in [-1,1]       (NULL to skip)
  * out_depth   [B,H,W,3] float32 in [0,1)        (NULL to skip)
  * out_rgb_u8 / out_depth_u8 [B,H,W,3] uint8, convert_image_dtype semantics
+ *
+ * Arithmetic contract.  The render side has no validity mask, so the fused kernel
+ * evaluates the per-sample chain (quadratic root, two atan2, pixel scaling) with
+ * approximate reciprocal / square root, FMA and a polynomial atan2 (2.5e-7 rad):
+ * sample coordinates agree with the reference's float32 chain to ~1e-4 px
+ * (contract: 1e-3 px; floor() differs only at knife-edge coordinates), the
+ * bilinear blend and the over-composite recurrence keep the reference's operation
+ * order without FMA.  msi_intersect_sphere_coords_ex(fast=1) returns exactly the
+ * coordinates this kernel samples at; msi_project_layers / msi_intersect_sphere_coords
+ * keep the strict chain.  Environment MSI_RENDER_V1=1 selects the strict-chain form
+ * of the fused kernel (A/B runs).
  * ------------------------------------------------------------------------- */
 int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
                          const float* depths,
@@ -192,6 +232,11 @@ int msi_render_perspective(const float* rgba, const float* pose_rt, const float*
 int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
                                 const float* cos_s, const float* sin_s, const float* cos_t,
                                 const float* sin_t, int B, int H, int W, int L, float* uv, void* stream);
+
+/* fast = 0: as above; fast = 1: the coordinates of the fast chain of the fused render kernel. */
+int msi_intersect_sphere_coords_ex(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
+                                   const float* cos_s, const float* sin_s, const float* cos_t,
+                                   const float* sin_t, int B, int H, int W, int L, int fast, float* uv, void* stream);
 
 /* Reprojected layers without compositing (MSI.msi_render_equirect_view_single,
  * msi.py:431-452): out [L,B,H,W,4]. */

@@ -31,6 +31,9 @@ SIGNATURES = {
     "msi_psv_build": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P,
                               c_size_t, _P]),
     "msi_psv_scratch_bytes": (c_size_t, [_I, _I, _I]),
+    "msi_sweep_table_bytes": (c_size_t, [_I, _I, _I, _I]),
+    "msi_sweep_table_build": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "msi_psv_gather": (c_int, [_P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, c_size_t, _P]),
     "msi_sweep_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_rgba_assemble": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "msi_rgba_assemble_ex": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -41,6 +44,7 @@ SIGNATURES = {
     "msi_render_ods": (c_int, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "msi_render_perspective": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "msi_intersect_sphere_coords": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "msi_intersect_sphere_coords_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "msi_project_layers": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "msi_point_op": (c_int, [_I, _P, _P, _P, ctypes.c_longlong, _I, _P, _I, ctypes.c_float, ctypes.c_float, _I, _I,
                              _P, _P, _P, _P, _P]),

@@ -23,6 +23,8 @@ struct ErpConsts {
     float half_pi_h;  // 0.5*np.pi/height
     float den_v;      // np.pi - np.pi/height
     float hm1;        // height - 1
+    float ku;         // (width - 1) / den_u   (fast render chain: one multiply instead of divide + multiply)
+    float kv;         // (height - 1) / den_v
 };
 
 inline ErpConsts make_erp_consts(int H, int W) {
@@ -36,6 +38,8 @@ inline ErpConsts make_erp_consts(int H, int W) {
     c.half_pi_h = (float)(0.5 * pi / (double)H);
     c.den_v = (float)(pi - pi / (double)H);
     c.hm1 = (float)(H - 1);
+    c.ku = (float)((double)(W - 1) / (2.0 * pi - 2.0 * pi / (double)W));
+    c.kv = (float)((double)(H - 1) / (pi - pi / (double)H));
     return c;
 }
 
@@ -291,6 +295,116 @@ __device__ __forceinline__ Bilinear bilinear_setup(float x, float y, int W, int 
 // tf.add_n of the four weighted corners: ((a + b) + c) + d
 __device__ __forceinline__ float blend4(const Bilinear& s, float pa, float pb, float pc, float pd) {
     return ((s.wa * pa + s.wb * pb) + s.wc * pc) + s.wd * pd;
+}
+
+// sampling.resample corner set-up for coordinates known to lie in [-n, 2n) (every coordinate project_ods
+// returns: u in [-0.5, W - 0.5], v in [-0.5, H - 0.5], or the (1, 1) of an invalid sample): the same
+// floor / weights / floor-mod as bilinear_setup without its general-range branch.  The final unsigned
+// clamp only matters for a corrupt table (it keeps every tap inside the image).
+struct Taps {
+    unsigned a, b, c, d;   // pixel indices of (y0,x0) (y0,x1) (y1,x0) (y1,x1), frame base `ib` included
+    float wa, wb, wc, wd;
+};
+__device__ __forceinline__ Taps taps_in_range(float x, float y, int W, int H, unsigned ib) {
+    const int x0 = __float2int_rd(x), y0 = __float2int_rd(y);
+    const float fx0 = (float)x0, fy0 = (float)y0;
+    const float dx0 = x - fx0, dy0 = y - fy0;
+    const float dx1 = (fx0 + 1.0f) - x, dy1 = (fy0 + 1.0f) - y;  // (float)(x0 + 1) == (float)x0 + 1 for |x0| < 2^24
+    int xa = x0 + (x0 < 0 ? W : 0), ya = y0 + (y0 < 0 ? H : 0);
+    xa -= (xa >= W ? W : 0);
+    ya -= (ya >= H ? H : 0);
+    int xb = xa + 1, yb = ya + 1;
+    xb -= (xb >= W ? W : 0);
+    yb -= (yb >= H ? H : 0);
+    const unsigned ux0 = min((unsigned)xa, (unsigned)(W - 1)), ux1 = min((unsigned)xb, (unsigned)(W - 1));
+    const unsigned r0 = min((unsigned)ya, (unsigned)(H - 1)) * (unsigned)W + ib;
+    const unsigned r1 = min((unsigned)yb, (unsigned)(H - 1)) * (unsigned)W + ib;
+    Taps t;
+    t.a = r0 + ux0;
+    t.b = r0 + ux1;
+    t.c = r1 + ux0;
+    t.d = r1 + ux1;
+    t.wa = dy1 * dx1;
+    t.wb = dy1 * dx0;
+    t.wc = dy0 * dx1;
+    t.wd = dy0 * dx0;
+    return t;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fast form of the render-side chain (intersect_sphere + project_spherical + theta_phi_to_pixels,
+// spherical.py:268-326, 235-246, 54-68) used by the fused render kernel.  The render side has no
+// validity mask, so nothing here needs the reference's exact bits: approximate reciprocal / square
+// root, FMA, a polynomial atan2 (max abs error 2.5e-7 rad) and the pixel scaling folded into one
+// multiply.  Coordinates agree with the strict chain (sphere_hit_uv) to ~1e-4 px; the contract
+// tested is 1e-3 px, floor() flips only at knife-edge coordinates.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_sqrtf(float x) {  // MUFU.SQRT, ~1 ulp
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcpf(float x) {  // MUFU.RCP, ~1 ulp (no scaling for denormal / huge x)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float q = mn * fast_rcpf(mx);
+    q = (mx == 0.0f) ? 0.0f : q;  // atan2(0, 0) = 0
+    const float s = q * q;
+    // atan(q) / q on [0, 1] as a degree-7 polynomial in q^2 (minimax fit: 1.3e-7 abs in float32)
+    float p = -0.004054469987750053f;
+    p = __fmaf_rn(p, s, 0.02186259813606739f);
+    p = __fmaf_rn(p, s, -0.05591179430484772f);
+    p = __fmaf_rn(p, s, 0.09642156958580017f);
+    p = __fmaf_rn(p, s, -0.13908612728118896f);
+    p = __fmaf_rn(p, s, 0.19946561753749847f);
+    p = __fmaf_rn(p, s, -0.33329859375953674f);
+    p = __fmaf_rn(p, s, 0.9999993443489075f);
+    float r = p * q;
+    r = (ay > ax) ? (1.5707963267948966f - r) : r;
+    r = (x < 0.0f) ? (3.141592653589793f - r) : r;
+    return copysignf(r, y);
+}
+
+// layer-independent part of a ray for the fast chain
+struct FastRay {
+    float rx, ry, rz, cx, cy, cz;
+    float b, b2, a4, inv2a, cc;  // b, b^2, 4a, 1/(2a), |c|^2
+    float pad;
+};
+__device__ __forceinline__ FastRay make_fast_ray(const SphereRay& q) {
+    FastRay f;
+    f.rx = q.rx;
+    f.ry = q.ry;
+    f.rz = q.rz;
+    f.cx = q.cx;
+    f.cy = q.cy;
+    f.cz = q.cz;
+    f.b = q.b;
+    f.b2 = q.b * q.b;
+    f.a4 = 4.0f * q.a;
+    f.inv2a = 1.0f / (2.0f * q.a);
+    f.cc = (q.cx * q.cx + q.cy * q.cy) + q.cz * q.cz;
+    f.pad = 0.0f;
+    return f;
+}
+__device__ __forceinline__ void sphere_hit_uv_fast(const FastRay& q, float radius2, const ErpConsts& k, float& u, float& v) {
+    const float c = q.cc - radius2;
+    const float disc = __fmaf_rn(-q.a4, c, q.b2);
+    const float t = (fast_sqrtf(disc) - q.b) * q.inv2a;
+    const float x = __fmaf_rn(t, q.rx, q.cx);
+    const float y = __fmaf_rn(t, q.ry, q.cy);
+    const float z = __fmaf_rn(t, q.rz, q.cz);
+    const float theta = -fast_atan2f(z, x);
+    const float h = fast_sqrtf(__fmaf_rn(x, x, z * z));
+    const float phi = fast_atan2f(y, h);
+    u = ((theta + k.pi) - k.pi_w) * k.ku;
+    v = ((phi + k.half_pi) - k.half_pi_h) * k.kv;
 }
 
 }  // namespace msi

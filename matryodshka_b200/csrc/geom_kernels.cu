@@ -24,6 +24,10 @@ struct PsvParams {
     __half* out_lo;
     int c_stride;
     ErpConsts k;
+    // cached sweep coordinates (msi_sweep_table_build): [table_frames][H*W][P] float4 (u_ref, v_ref, u_src, v_src),
+    // table_frames = 1 (one rig shared by every frame of the batch) or B; null = evaluate the chain
+    const float4* table;
+    int table_frames;
 };
 
 template <typename T>
@@ -40,7 +44,7 @@ __device__ __forceinline__ float load_img<uint8_t>(const uint8_t* img, size_t of
     return preprocess ? (v * 2.0f - 1.0f) : v;
 }
 
-template <typename T>
+template <typename T, bool TABLE>
 __global__ void __launch_bounds__(256) psv_build_kernel(PsvParams p) {
     __shared__ __align__(16) float stage[768];
     const long long total = (long long)p.B * p.H * p.W * 2 * p.P;
@@ -57,9 +61,16 @@ __global__ void __launch_bounds__(256) psv_build_kernel(PsvParams p) {
         const int i = (int)((pix / p.W) % p.H);
         const int b = (int)(pix / ((long long)p.W * p.H));
         float u, v;
-        sweep_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
-                 __ldg(p.depths + pl), p.poses + (b * 2 + e) * 16, e == 0 ? 1.0f : -1.0f,
-                 __ldg(p.baselines + b), p.k, u, v);
+        if (TABLE) {
+            const size_t row = (size_t)(p.table_frames == 1 ? 0 : b) * p.H * p.W + (size_t)i * p.W + j;
+            const float4 uv = __ldcs(p.table + row * p.P + pl);
+            u = e ? uv.z : uv.x;
+            v = e ? uv.w : uv.y;
+        } else {
+            sweep_uv(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                     __ldg(p.depths + pl), p.poses + (b * 2 + e) * 16, e == 0 ? 1.0f : -1.0f,
+                     __ldg(p.baselines + b), p.k, u, v);
+        }
         const Bilinear s = bilinear_setup(u, v, p.W, p.H);
         const T* img = reinterpret_cast<const T*>(p.img[e]);
         const size_t ib = (size_t)b * p.H * p.W;
@@ -220,6 +231,103 @@ __global__ void __launch_bounds__(256) psv_build_pair_kernel(PsvParams p, const 
             reinterpret_cast<uint4*>(p.out_hi + fbase)[q] = *reinterpret_cast<const uint4*>(hi);
             if (p.out_lo != nullptr) reinterpret_cast<uint4*>(p.out_lo + fbase)[q] = *reinterpret_cast<const uint4*>(lo);
         }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 with cached coordinates.  The sweep coordinates depend only on (eye poses, baseline, depths,
+// H, W) -- not on the images -- and a rig is static over a sequence (every frame of the reference's
+// data has identity eye poses and one baseline, data_loader.py:146-174), so they are evaluated ONCE
+// by sweep_table_kernel with the exact chain above (same device functions, same bits) and the
+// per-frame kernel is a pure gather: one 128-bit table load, 8 taps, 6 blends per (pixel, plane).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sweep_table_kernel(PsvParams p, float4* __restrict__ table) {
+    // thread per (frame, pixel, plane), plane fastest = the table's layout
+    const long long total = (long long)p.B * p.H * p.W * p.P;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int pl = (int)(idx % p.P);
+    const long long pix = idx / p.P;
+    const int j = (int)(pix % p.W);
+    const int i = (int)((pix / p.W) % p.H);
+    const int b = (int)(pix / ((long long)p.W * p.H));
+    const float cs = __ldg(p.cos_s + j), sn = __ldg(p.sin_s + j), ct = __ldg(p.cos_t + i), st = __ldg(p.sin_t + i);
+    const float depth = __ldg(p.depths + pl);
+    const float r = __ldg(p.baselines + b);
+    float4 o;
+    sweep_uv(cs, sn, ct, st, depth, p.poses + (size_t)b * 32, 1.0f, r, p.k, o.x, o.y);
+    sweep_uv(cs, sn, ct, st, depth, p.poses + (size_t)b * 32 + 16, -1.0f, r, p.k, o.z, o.w);
+    table[idx] = o;
+}
+
+// packed form of split_half for two values: the same two roundings per value, with the packing
+// converts (full rate) instead of four scalar ones
+__device__ __forceinline__ void split_half2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hi);
+    lo = __floats2half2_rn(a - hf.x, b - hf.y);
+}
+
+// grid (ceil(H*W / ppb), B), ppb = 256 / P pixels per block (P a power of two); thread = (pixel, plane),
+// both eyes: one 128-bit table load, all eight 128-bit taps in flight before the first blend
+__global__ void __launch_bounds__(256) psv_gather_pair_kernel(PsvParams p, const float4* __restrict__ rgbx, int log2p) {
+    __shared__ __align__(16) float stage[1536];
+    const int P = p.P;
+    const unsigned ppb = 256u >> log2p;
+    const unsigned HW = (unsigned)p.H * (unsigned)p.W;
+    const unsigned pixf0 = blockIdx.x * ppb;  // first pixel of the block inside its frame
+    const unsigned lp = threadIdx.x >> log2p;
+    const unsigned pl = threadIdx.x & (unsigned)(P - 1);
+    const unsigned pixf = pixf0 + lp;
+    const unsigned ib = blockIdx.y * HW;  // < 2^31 (checked on the host)
+    if (pixf < HW) {
+        const unsigned trow = (p.table_frames == 1 ? 0u : ib) + pixf;
+        const float4 uv = __ldcs(p.table + (((size_t)trow << log2p) + pl));
+        const Taps t0 = taps_in_range(uv.x, uv.y, p.W, p.H, ib);
+        const Taps t1 = taps_in_range(uv.z, uv.w, p.W, p.H, ib);
+        const float4* img0 = rgbx;
+        const float4* img1 = rgbx + (size_t)p.B * HW;
+        const float4 a0 = __ldg(img0 + t0.a), b0 = __ldg(img0 + t0.b), c0 = __ldg(img0 + t0.c), d0 = __ldg(img0 + t0.d);
+        const float4 a1 = __ldg(img1 + t1.a), b1 = __ldg(img1 + t1.b), c1 = __ldg(img1 + t1.c), d1 = __ldg(img1 + t1.d);
+        float* s0 = stage + (lp * 6u << log2p) + 3u * pl;
+        // tf.add_n of the four weighted corners: ((a + b) + c) + d   (blend4)
+        s0[0] = ((t0.wa * a0.x + t0.wb * b0.x) + t0.wc * c0.x) + t0.wd * d0.x;
+        s0[1] = ((t0.wa * a0.y + t0.wb * b0.y) + t0.wc * c0.y) + t0.wd * d0.y;
+        s0[2] = ((t0.wa * a0.z + t0.wb * b0.z) + t0.wc * c0.z) + t0.wd * d0.z;
+        float* s1 = s0 + 3 * P;
+        s1[0] = ((t1.wa * a1.x + t1.wb * b1.x) + t1.wc * c1.x) + t1.wd * d1.x;
+        s1[1] = ((t1.wa * a1.y + t1.wb * b1.y) + t1.wc * c1.y) + t1.wd * d1.y;
+        s1[2] = ((t1.wa * a1.z + t1.wb * b1.z) + t1.wc * c1.z) + t1.wd * d1.z;
+    }
+    __syncthreads();
+    const unsigned nvalid = (HW - pixf0 < ppb) ? (HW - pixf0) : ppb;
+    const int nfl = (int)nvalid * 6 * P;
+    const size_t fbase = ((size_t)ib + pixf0) * 6 * P;
+    if (p.out_f32 != nullptr)
+        for (int q = threadIdx.x; q < nfl / 4; q += 256)
+            reinterpret_cast<float4*>(p.out_f32 + fbase)[q] = reinterpret_cast<const float4*>(stage)[q];
+    if (p.out_hi != nullptr) {
+        const int q = threadIdx.x;  // 1536 floats = 192 groups of 8: one group per thread
+        if (q < nfl / 8) {
+            const float4 a = reinterpret_cast<const float4*>(stage)[2 * q];
+            const float4 c = reinterpret_cast<const float4*>(stage)[2 * q + 1];
+            __half2 h0, h1, h2, h3, l0, l1, l2, l3;
+            split_half2(a.x * MSI_ACT_SCALE, a.y * MSI_ACT_SCALE, h0, l0);
+            split_half2(a.z * MSI_ACT_SCALE, a.w * MSI_ACT_SCALE, h1, l1);
+            split_half2(c.x * MSI_ACT_SCALE, c.y * MSI_ACT_SCALE, h2, l2);
+            split_half2(c.z * MSI_ACT_SCALE, c.w * MSI_ACT_SCALE, h3, l3);
+            uint4 hv, lv;
+            hv.x = *reinterpret_cast<const unsigned*>(&h0);
+            hv.y = *reinterpret_cast<const unsigned*>(&h1);
+            hv.z = *reinterpret_cast<const unsigned*>(&h2);
+            hv.w = *reinterpret_cast<const unsigned*>(&h3);
+            lv.x = *reinterpret_cast<const unsigned*>(&l0);
+            lv.y = *reinterpret_cast<const unsigned*>(&l1);
+            lv.z = *reinterpret_cast<const unsigned*>(&l2);
+            lv.w = *reinterpret_cast<const unsigned*>(&l3);
+            reinterpret_cast<uint4*>(p.out_hi + fbase)[q] = hv;
+            if (p.out_lo != nullptr) reinterpret_cast<uint4*>(p.out_lo + fbase)[q] = lv;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) sweep_coords_kernel(PsvParams p, float* uv, uint8_t* valid) {
@@ -478,6 +586,192 @@ __global__ void __launch_bounds__(256) render_composite_kernel(RenderParams p) {
     }
 }
 
+// K5, second form (default): a block owns NPIX = 64 consecutive output pixels.
+//   set-up: 64 threads evaluate the layer-independent ray of their pixel once (FastRay in shared memory);
+//   phase 1 (all 8 warps): lanes = layers; per (pixel, layer) the fast chain of geom_device.cuh -- no IEEE
+//     divide / square root, polynomial atan2 -- then four 128-bit taps (a warp's taps of one texel are one
+//     512-byte run of [.., L, 4]) and the no-FMA blend of sampling.resample; samples parked in shared memory;
+//   phase 2 (all 256 threads): thread = (channel r/g/b/depth, pixel) runs over_composite /
+//     over_composite_depth in the reference's order (projector.py:225-265);
+//   epilogue: the block's 768 B of float rgb, 768 B of depth and 2 x 192 B of uint8 leave as 128-bit stores.
+template <int NPIX>
+__global__ void __launch_bounds__(256) render_composite_v2_kernel(RenderParams p) {
+    extern __shared__ float sm[];  // [4][NPIX][L+1] samples, then [L] depth fractions, then [L] radius^2
+    const int L = p.L;
+    const int ld = L + 1;
+    float* frac = sm + 4 * NPIX * ld;
+    float* rad2 = frac + L;
+    __shared__ __align__(16) FastRay s_ray[NPIX];
+    __shared__ unsigned s_ib[NPIX];
+    __shared__ __align__(16) float s_out[4][NPIX];
+    __shared__ __align__(16) uint8_t s_u8[2][NPIX * 3];
+    const long long npix = (long long)p.B * p.oH * p.oW;
+    const long long pix0 = (long long)blockIdx.x * NPIX;
+
+    for (int l = threadIdx.x; l < L; l += 256) {
+        frac[l] = (float)((double)l / (double)L);
+        const float r = __ldg(p.depths + l);
+        rad2[l] = r * r;
+    }
+    if (threadIdx.x >= 256 - NPIX) {
+        const int q = threadIdx.x - (256 - NPIX);
+        const long long pix = pix0 + q;
+        int b = 0;
+        SphereRay ray = {};
+        if (pix < npix) {
+            const int j = (int)(pix % p.oW);
+            const int i = (int)((pix / p.oW) % p.oH);
+            b = (int)(pix / ((long long)p.oW * p.oH));
+            if (p.ods_mode == 2)
+                ray = sphere_ray_perspective(__ldg(p.cos_s + j), __ldg(p.cos_t + i), p.pose_rt + b * 16, p.tgt_pos + b * 3);
+            else if (p.ods_mode)
+                ray = sphere_ray_ods(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                                     p.pose_rt + b * 16, p.ods_order, __ldg(p.baselines + b));
+            else
+                ray = sphere_ray(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                                 p.pose_rt + b * 16, p.tgt_pos + b * 3);
+        }
+        s_ray[q] = make_fast_ray(ray);
+        s_ib[q] = (unsigned)b * (unsigned)(p.H * p.W);
+    }
+    __syncthreads();
+
+    {
+        int q = threadIdx.x / L;
+        int l = threadIdx.x - q * L;
+        const int dq = 256 / L, dl = 256 - dq * L;
+        for (int s = threadIdx.x; s < NPIX * L; s += 256) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix0 + q < npix) {
+                float u, v;
+                sphere_hit_uv_fast(s_ray[q], rad2[l], p.k, u, v);
+                const Taps t = taps_in_range(u, v, p.W, p.H, s_ib[q]);
+                const float4* base = p.rgba + l;
+                const float4 pa = __ldg(base + (size_t)t.a * L);
+                const float4 pb = __ldg(base + (size_t)t.b * L);
+                const float4 pc = __ldg(base + (size_t)t.c * L);
+                const float4 pd = __ldg(base + (size_t)t.d * L);
+                o.x = ((t.wa * pa.x + t.wb * pb.x) + t.wc * pc.x) + t.wd * pd.x;
+                o.y = ((t.wa * pa.y + t.wb * pb.y) + t.wc * pc.y) + t.wd * pd.y;
+                o.z = ((t.wa * pa.z + t.wb * pb.z) + t.wc * pc.z) + t.wd * pd.z;
+                o.w = ((t.wa * pa.w + t.wb * pb.w) + t.wc * pc.w) + t.wd * pd.w;
+            }
+            sm[(0 * NPIX + q) * ld + l] = o.x;
+            sm[(1 * NPIX + q) * ld + l] = o.y;
+            sm[(2 * NPIX + q) * ld + l] = o.z;
+            sm[(3 * NPIX + q) * ld + l] = o.w;
+            q += dq;
+            l += dl;
+            if (l >= L) {
+                l -= L;
+                ++q;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 4 * NPIX) {
+        const int ch = threadIdx.x / NPIX;
+        const int q = threadIdx.x - ch * NPIX;
+        const float* col = sm + (ch * NPIX + q) * ld;
+        const float* alp = sm + (3 * NPIX + q) * ld;
+        float out;
+        if (ch < 3) {
+            out = col[0];  // alpha of the farthest layer is ignored (projector.py:257-259)
+            for (int l = 1; l < L; ++l) {
+                const float a = alp[l];
+                out = col[l] * a + out * (1.0f - a);
+            }
+            s_u8[0][q * 3 + ch] = to_u8((out + 1.0f) / 2.0f);
+        } else {
+            out = 0.0f;
+            for (int l = 1; l < L; ++l) {
+                const float a = alp[l];
+                out = frac[l] * a + out * (1.0f - a);
+            }
+            const uint8_t d = to_u8(out);
+            s_u8[1][q * 3 + 0] = d;
+            s_u8[1][q * 3 + 1] = d;
+            s_u8[1][q * 3 + 2] = d;
+        }
+        s_out[ch][q] = out;
+    }
+    __syncthreads();
+
+    const int nvalid = (int)min((long long)NPIX, npix - pix0);
+    if (nvalid == NPIX) {
+        // full block: every output run starts 16-byte aligned (pix0 is a multiple of 64)
+        const int t = threadIdx.x;
+        if (t < NPIX * 3 / 4) {  // float rgb: float4 #t = elements 4t .. 4t+3 of [NPIX][3]
+            if (p.out_rgb != nullptr) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int e = 4 * t + k;
+                    v[k] = s_out[e % 3][e / 3];
+                }
+                reinterpret_cast<float4*>(p.out_rgb + pix0 * 3)[t] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        } else if (t >= 64 && t < 64 + NPIX * 3 / 4) {
+            if (p.out_depth != nullptr) {
+                const int tt = t - 64;
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = s_out[3][(4 * tt + k) / 3];
+                reinterpret_cast<float4*>(p.out_depth + pix0 * 3)[tt] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        } else if (t >= 128 && t < 128 + NPIX * 3 / 16) {
+            if (p.out_rgb_u8 != nullptr)
+                reinterpret_cast<uint4*>(p.out_rgb_u8 + pix0 * 3)[t - 128] = reinterpret_cast<const uint4*>(s_u8[0])[t - 128];
+        } else if (t >= 160 && t < 160 + NPIX * 3 / 16) {
+            if (p.out_depth_u8 != nullptr)
+                reinterpret_cast<uint4*>(p.out_depth_u8 + pix0 * 3)[t - 160] = reinterpret_cast<const uint4*>(s_u8[1])[t - 160];
+        }
+    } else if ((int)threadIdx.x < nvalid * 3) {  // ragged last block: element-wise
+        const int e = threadIdx.x, q = e / 3, ch = e - 3 * q;
+        if (p.out_rgb != nullptr) p.out_rgb[pix0 * 3 + e] = s_out[ch][q];
+        if (p.out_depth != nullptr) p.out_depth[pix0 * 3 + e] = s_out[3][q];
+        if (p.out_rgb_u8 != nullptr) p.out_rgb_u8[pix0 * 3 + e] = s_u8[0][e];
+        if (p.out_depth_u8 != nullptr) p.out_depth_u8[pix0 * 3 + e] = s_u8[1][e];
+    }
+    if (p.peer_u8 != nullptr) {
+        // the block's NPIX pixels x 3 bytes, contiguous in the gathered buffer: multimem / peer word stores
+        const long long dst = p.gather_off + pix0 * 3;  // multiple of 4
+        if (nvalid == NPIX) {
+            if (threadIdx.x >= 192 && threadIdx.x < 192 + NPIX * 3 / 4) {
+                const int w4 = threadIdx.x - 192;
+                const unsigned int w = reinterpret_cast<const unsigned int*>(s_u8[0])[w4];
+                if (p.mc_u8 != nullptr) {
+                    asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p.mc_u8 + dst + 4 * w4), "r"(w) : "memory");
+                } else {
+                    for (int k = 0; k < p.n_peers; ++k) *reinterpret_cast<unsigned int*>(p.peer_u8[k] + dst + 4 * w4) = w;
+                }
+            }
+        } else if ((int)threadIdx.x < nvalid * 3) {
+            for (int k = 0; k < p.n_peers; ++k) p.peer_u8[k][dst + threadIdx.x] = s_u8[0][threadIdx.x];
+        }
+    }
+}
+
+// the coordinates the fused render kernel samples at (fast chain), for parity accounting
+__global__ void __launch_bounds__(256) sphere_coords_fast_kernel(RenderParams p, float* uv) {
+    // [B,L,H,W]
+    const long long total = (long long)p.B * p.L * p.H * p.W;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % p.W);
+    const int i = (int)((idx / p.W) % p.H);
+    const int l = (int)((idx / ((long long)p.W * p.H)) % p.L);
+    const int b = (int)(idx / ((long long)p.W * p.H * p.L));
+    const SphereRay ray = sphere_ray(__ldg(p.cos_s + j), __ldg(p.sin_s + j), __ldg(p.cos_t + i), __ldg(p.sin_t + i),
+                                     p.pose_rt + b * 16, p.tgt_pos + b * 3);
+    const float r = __ldg(p.depths + l);
+    float u, v;
+    sphere_hit_uv_fast(make_fast_ray(ray), r * r, p.k, u, v);
+    uv[2 * idx + 0] = u;
+    uv[2 * idx + 1] = v;
+}
+
 __global__ void __launch_bounds__(256) sphere_coords_kernel(RenderParams p, float* uv) {
     // [B,L,H,W]
     const long long total = (long long)p.B * p.L * p.H * p.W;
@@ -585,6 +879,8 @@ static int fill_psv_params(PsvParams& p, const void* ref, const void* src, int p
     p.out_lo = nullptr;
     p.c_stride = 6 * P;
     p.k = make_erp_consts(H, W);
+    p.table = nullptr;
+    p.table_frames = 0;
     return MSI_OK;
 }
 
@@ -634,9 +930,87 @@ extern "C" int msi_psv_build(const void* ref, const void* src, int img_dtype, in
     const long long total = npix * 2 * P;
     const int grid = ceil_div(total, 256);
     if (img_dtype == MSI_IMG_F32)
-        psv_build_kernel<float><<<grid, 256, 0, st>>>(p);
+        psv_build_kernel<float, false><<<grid, 256, 0, st>>>(p);
     else
-        psv_build_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
+        psv_build_kernel<uint8_t, false><<<grid, 256, 0, st>>>(p);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" size_t msi_sweep_table_bytes(int frames, int H, int W, int P) {
+    if (frames <= 0 || H <= 0 || W <= 0 || P <= 0) return 0;
+    return (size_t)frames * (size_t)H * (size_t)W * (size_t)P * sizeof(float4);
+}
+
+extern "C" int msi_sweep_table_build(const float* poses, const float* baselines, const float* depths, const float* cos_s,
+                                     const float* sin_s, const float* cos_t, const float* sin_t, int frames, int H, int W,
+                                     int P, void* table, void* stream) {
+    PsvParams p;
+    int rc = fill_psv_params(p, nullptr, nullptr, 0, poses, baselines, depths, cos_s, sin_s, cos_t, sin_t, frames, H, W, P);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(table != nullptr && ((uintptr_t)table % 16 == 0), "sweep_table_build: table must be a 16-byte aligned device pointer");
+    const long long total = (long long)frames * H * W * P;
+    sweep_table_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p, reinterpret_cast<float4*>(table));
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+extern "C" int msi_psv_gather(const void* ref, const void* src, int img_dtype, int preprocess, const void* table,
+                              int table_frames, int B, int H, int W, int P, float* out_f32, void* out_hi, void* out_lo,
+                              int c_stride, void* scratch, size_t scratch_bytes, void* stream) {
+    MSI_CHECK_ARG(B > 0 && H > 1 && W > 1 && P > 0, "psv_gather: bad shape B=%d H=%d W=%d P=%d", B, H, W, P);
+    MSI_CHECK_ARG(ref && src, "psv_gather: null image pointer");
+    MSI_CHECK_ARG(table != nullptr && ((uintptr_t)table % 16 == 0), "psv_gather: table must be a 16-byte aligned device pointer");
+    MSI_CHECK_ARG(table_frames == 1 || table_frames == B, "psv_gather: table_frames=%d must be 1 or B=%d", table_frames, B);
+    MSI_CHECK_ARG(out_f32 || out_hi, "psv_gather: no output requested");
+    MSI_CHECK_ARG(img_dtype == MSI_IMG_F32 || img_dtype == MSI_IMG_U8, "psv_gather: bad img_dtype %d", img_dtype);
+    if (out_hi) MSI_CHECK_ARG(c_stride >= 6 * P && c_stride % 8 == 0, "psv_gather: c_stride %d must be >= 6P and a multiple of 8", c_stride);
+    PsvParams p = {};
+    p.img[0] = ref;
+    p.img[1] = src;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.P = P;
+    p.preprocess = preprocess;
+    p.out_f32 = out_f32;
+    p.out_hi = reinterpret_cast<__half*>(out_hi);
+    p.out_lo = reinterpret_cast<__half*>(out_lo);
+    p.c_stride = out_hi ? c_stride : 6 * P;
+    p.table = reinterpret_cast<const float4*>(table);
+    p.table_frames = table_frames;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (out_hi && c_stride != 6 * P) {
+        const size_t bytes = (size_t)B * H * W * c_stride * sizeof(__half);
+        MSI_CUDA(cudaMemsetAsync(out_hi, 0, bytes, st));
+        if (out_lo) MSI_CUDA(cudaMemsetAsync(out_lo, 0, bytes, st));
+    }
+    const long long npix = (long long)B * H * W;
+    const bool pair = scratch != nullptr && scratch_bytes >= msi_psv_scratch_bytes(B, H, W) && (256 % P == 0) &&
+                      npix < (1LL << 31) && B <= 65535 && (P % 4 == 0) && p.c_stride == 6 * P && ((uintptr_t)scratch % 16 == 0);
+    if (pair) {
+        float4* rgbx = reinterpret_cast<float4*>(scratch);
+        if (img_dtype == MSI_IMG_F32)
+            prep_images_kernel<float><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
+                reinterpret_cast<const float*>(ref), reinterpret_cast<const float*>(src), npix, preprocess, rgbx);
+        else
+            prep_images_kernel<uint8_t><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
+                reinterpret_cast<const uint8_t*>(ref), reinterpret_cast<const uint8_t*>(src), npix, preprocess, rgbx);
+        MSI_LAUNCH_CHECK();
+        const dim3 grid((unsigned)ceil_div((long long)H * W, 256 / P), (unsigned)B);
+        int log2p = 0;
+        while ((1 << log2p) < P) ++log2p;  // 256 % P == 0: P is a power of two
+        psv_gather_pair_kernel<<<grid, 256, 0, st>>>(p, rgbx, log2p);
+        MSI_LAUNCH_CHECK();
+        return MSI_OK;
+    }
+    const long long total = npix * 2 * P;
+    const int grid = ceil_div(total, 256);
+    if (img_dtype == MSI_IMG_F32)
+        psv_build_kernel<float, true><<<grid, 256, 0, st>>>(p);
+    else
+        psv_build_kernel<uint8_t, true><<<grid, 256, 0, st>>>(p);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
@@ -796,6 +1170,48 @@ static int fill_render_params(RenderParams& p, const float* rgba, const float* p
     return MSI_OK;
 }
 
+// Launch of the fused render kernel: the 64-pixel fast-chain form by default; MSI_RENDER_V1=1 selects the
+// first form (32 pixels per block, strict IEEE chain of sphere_hit_uv) for A/B parity and timing runs.
+static int launch_render(const RenderParams& p, long long npix, int L, cudaStream_t st) {
+    static int v1 = -1;
+    if (v1 < 0) {
+        const char* env = getenv("MSI_RENDER_V1");
+        v1 = (env && atoi(env) != 0) ? 1 : 0;
+    }
+    if (v1) {
+        const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
+        MSI_CHECK_ARG(smem <= 200 * 1024, "render: L=%d needs %zu B of shared memory", L, smem);
+        static std::atomic<size_t> opted{48 * 1024};
+        if (smem > opted.load()) {
+            MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opted.store(smem);
+        }
+        render_composite_kernel<<<ceil_div(npix, 32), 256, smem, st>>>(p);
+        MSI_LAUNCH_CHECK();
+        return MSI_OK;
+    }
+    const size_t smem64 = (size_t)(4 * 64 * (L + 1) + 2 * L) * sizeof(float);
+    const size_t smem32 = (size_t)(4 * 32 * (L + 1) + 2 * L) * sizeof(float);
+    MSI_CHECK_ARG(smem32 <= 200 * 1024, "render: L=%d needs %zu B of shared memory", L, smem32);
+    if (smem64 <= 100 * 1024) {
+        static std::atomic<size_t> opted{48 * 1024};
+        if (smem64 > opted.load()) {
+            MSI_CUDA(cudaFuncSetAttribute(render_composite_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            opted.store(smem64);
+        }
+        render_composite_v2_kernel<64><<<ceil_div(npix, 64), 256, smem64, st>>>(p);
+    } else {
+        static std::atomic<size_t> opted{48 * 1024};
+        if (smem32 > opted.load()) {
+            MSI_CUDA(cudaFuncSetAttribute(render_composite_v2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            opted.store(smem32);
+        }
+        render_composite_v2_kernel<32><<<ceil_div(npix, 32), 256, smem32, st>>>(p);
+    }
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
 extern "C" int msi_render_composite(const float* rgba, const float* tgt_pose_rt, const float* tgt_pos,
                                     const float* depths, const float* cos_s, const float* sin_s, const float* cos_t,
                                     const float* sin_t, int B, int H, int W, int L, float* out_rgb, float* out_depth,
@@ -827,17 +1243,7 @@ extern "C" int msi_render_composite_gather(const float* rgba, const float* tgt_p
     p.out_depth = out_depth;
     p.out_rgb_u8 = out_rgb_u8;
     p.out_depth_u8 = out_depth_u8;
-    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
-    MSI_CHECK_ARG(smem <= 200 * 1024, "render: L=%d needs %zu B of shared memory", L, smem);
-    static std::atomic<size_t> smem_opted{48 * 1024};
-    if (smem > smem_opted.load()) {
-        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_opted.store(smem);
-    }
-    const long long npix = (long long)B * H * W;
-    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    MSI_LAUNCH_CHECK();
-    return MSI_OK;
+    return launch_render(p, (long long)B * H * W, L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // MSI.msi_render_ods_view (msi.py:502-525) -> projector.projective_forward_ods (projector.py:101-127) ->
@@ -856,17 +1262,7 @@ extern "C" int msi_render_ods(const float* rgba, const float* pose_rt, float ord
     p.ods_mode = 1;
     p.ods_order = order;
     p.baselines = baselines;
-    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
-    MSI_CHECK_ARG(smem <= 200 * 1024, "render_ods: L=%d needs %zu B of shared memory", L, smem);
-    static std::atomic<size_t> smem_opted{48 * 1024};
-    if (smem > smem_opted.load()) {
-        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_opted.store(smem);
-    }
-    const long long npix = (long long)B * H * W;
-    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    MSI_LAUNCH_CHECK();
-    return MSI_OK;
+    return launch_render(p, (long long)B * H * W, L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // MSI.msi_render_perspective_view (msi.py:475-500) -> projector.projective_forward_sphere_to_perspective
@@ -886,14 +1282,7 @@ extern "C" int msi_render_perspective(const float* rgba, const float* pose_rt, c
     p.ods_mode = 2;
     p.oH = oH;
     p.oW = oW;
-    const size_t smem = (size_t)(4 * 32 * (L + 1) + L) * sizeof(float);
-    MSI_CHECK_ARG(smem <= 200 * 1024, "render_perspective: L=%d needs %zu B of shared memory", L, smem);
-    if (smem > 48 * 1024)
-        MSI_CUDA(cudaFuncSetAttribute(render_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long npix = (long long)B * oH * oW;
-    render_composite_kernel<<<ceil_div(npix, 32), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    MSI_LAUNCH_CHECK();
-    return MSI_OK;
+    return launch_render(p, (long long)B * oH * oW, L, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
@@ -905,6 +1294,23 @@ extern "C" int msi_intersect_sphere_coords(const float* tgt_pose_rt, const float
     MSI_CHECK_ARG(uv != nullptr, "intersect_sphere_coords: null uv");
     const long long total = (long long)B * L * H * W;
     sphere_coords_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, uv);
+    MSI_LAUNCH_CHECK();
+    return MSI_OK;
+}
+
+// fast = 1: the coordinates of the fast chain the fused render kernel samples at (parity accounting);
+// fast = 0: msi_intersect_sphere_coords.
+extern "C" int msi_intersect_sphere_coords_ex(const float* tgt_pose_rt, const float* tgt_pos, const float* depths,
+                                              const float* cos_s, const float* sin_s, const float* cos_t,
+                                              const float* sin_t, int B, int H, int W, int L, int fast, float* uv,
+                                              void* stream) {
+    if (!fast) return msi_intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L, uv, stream);
+    RenderParams p;
+    int rc = fill_render_params(p, nullptr, tgt_pose_rt, tgt_pos, depths, cos_s, sin_s, cos_t, sin_t, B, H, W, L);
+    if (rc != MSI_OK) return rc;
+    MSI_CHECK_ARG(uv != nullptr, "intersect_sphere_coords_ex: null uv");
+    const long long total = (long long)B * L * H * W;
+    sphere_coords_fast_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, uv);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

@@ -169,8 +169,11 @@ class MSI(object):
             hi = torch.zeros((B, H, W, eng.in_c_stride), dtype=torch.float16, device=self.device)
             lo = torch.zeros_like(hi)
         # preprocessing (msi.py:73-75) is fused into the sweep kernel
+        # a static rig (every frame of the reference's data: identity eye poses, one baseline) gathers from the
+        # cached coordinate table; the jittered sweep evaluates the chain per call.  Same bits either way.
         net_input = ops.psv_build(raw_ref_image, raw_src_image, poses, baselines, list(psv_planes),
-                                  preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride)
+                                  preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride,
+                                  cache_coords=jitter_pose_inv is None)
         if cfg.net_only:
             eng.forward(hi_lo=(hi, lo))
             return None

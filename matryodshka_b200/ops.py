@@ -72,16 +72,98 @@ def _dev_f32(x, device, shape=None):
     return t.contiguous()
 
 
+class SweepTable:
+    """Cached sweep coordinates of one rig (msi_sweep_table_build): ``table`` [frames,H,W,P,4] float32 =
+    (u_ref, v_ref, u_src, v_src) per (pixel, plane); frames = 1 when every frame of the batch has the same
+    eye poses and baseline, else B."""
+
+    def __init__(self, table, frames, H, W, P):
+        self.table, self.frames, self.H, self.W, self.P = table, frames, H, W, P
+
+
+_SWEEP_TABLES = {}        # key -> SweepTable, insertion-ordered (oldest first)
+_SWEEP_TABLES_MAX = 4     # a table is H*W*P*16 bytes (105 MB at 320x640x32)
+
+
+def sweep_table(poses, baselines, depths, H, W, device) -> SweepTable:
+    """The coordinate table for (poses [B,2,4,4], baselines [B], depths [P]) on ``device``, built on torch's
+    current stream the first time a rig is seen and then served from a small LRU cache keyed by the VALUES
+    (float32 bits) of the rig -- any change of a pose, a baseline, the depths or the image size is a new
+    table.  Host arrays in, so the key costs no device synchronisation."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    device = torch.device(device)
+    poses = np.ascontiguousarray(np.asarray(poses, np.float32).reshape(-1, 2, 16))
+    baselines = np.ascontiguousarray(np.asarray(baselines, np.float32).reshape(-1))
+    depths = np.ascontiguousarray(np.asarray(depths, np.float32).reshape(-1))
+    B, P = poses.shape[0], depths.size
+    assert baselines.size == B
+    if B > 1 and (poses == poses[:1]).all() and (baselines == baselines[0]).all():
+        poses, baselines = poses[:1], baselines[:1]          # one rig for the whole batch
+    frames = poses.shape[0]
+    key = (poses.tobytes(), baselines.tobytes(), depths.tobytes(), int(H), int(W), str(device))
+    hit = _SWEEP_TABLES.pop(key, None)
+    if hit is None:
+        table = torch.empty((frames, H, W, P, 4), dtype=torch.float32, device=device)
+        tb = erp_tables(H, W, device)
+        d_poses, d_base, d_depths = (torch.from_numpy(a).to(device) for a in (poses, baselines, depths))
+        check(lib.msi_sweep_table_build(ptr(d_poses), ptr(d_base), ptr(d_depths), *tb.ptrs(), frames, H, W, P,
+                                        ptr(table), stream_ptr()), "msi_sweep_table_build")
+        # later users may run on other streams (frame lanes): the table is complete before it is handed out
+        torch.cuda.current_stream(device).synchronize()
+        hit = SweepTable(table, frames, H, W, P)
+        while len(_SWEEP_TABLES) >= _SWEEP_TABLES_MAX:
+            _SWEEP_TABLES.pop(next(iter(_SWEEP_TABLES)))
+    _SWEEP_TABLES[key] = hit
+    return hit
+
+
+def psv_gather(ref, src, table: SweepTable, *, preprocess=True, want_f32=True, hi_lo=None, c_stride=None,
+               use_scratch=True, scratch=None):
+    """msi_psv_gather: the plane-sweep volume from cached coordinates; same outputs (same bits) as psv_build."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    assert ref.shape == src.shape and ref.dim() == 4 and ref.shape[3] == 3
+    B, H, W, _ = ref.shape
+    assert (table.H, table.W) == (H, W) and table.frames in (1, B), "sweep table built for another shape"
+    P = table.P
+    dev = ref.device
+    if ref.dtype == torch.uint8:
+        dt = _lib.IMG_U8
+    elif ref.dtype == torch.float32:
+        dt = _lib.IMG_F32
+    else:
+        raise _lib.MsiError(f"psv_gather: unsupported image dtype {ref.dtype}")
+    out = torch.empty((B, H, W, 6 * P), dtype=torch.float32, device=dev) if want_f32 else None
+    hi = lo = None
+    cs = 6 * P
+    if hi_lo is not None:
+        hi, lo = hi_lo
+        cs = int(c_stride if c_stride is not None else hi.shape[-1])
+    if scratch is None and use_scratch:
+        scratch = psv_scratch(B, H, W, dev)
+    check(lib.msi_psv_gather(ptr(ref.contiguous()), ptr(src.contiguous()), dt, 1 if preprocess else 0, ptr(table.table),
+                             table.frames, B, H, W, P, ptr(out), ptr(hi), ptr(lo), cs, ptr(scratch),
+                             scratch.numel() if scratch is not None else 0, stream_ptr()), "msi_psv_gather")
+    return out
+
+
 def psv_build(ref, src, poses, baselines, depths, *, preprocess=True, want_f32=True, hi_lo=None, c_stride=None,
-              use_scratch=True):
+              use_scratch=True, cache_coords=False):
     """msi_psv_build.  ref/src: [B,H,W,3] float32 or uint8 CUDA tensors; poses [B,2,4,4];
     baselines [B]; depths [P].  Returns the float32 PSV [B,H,W,6P] (or None); ``hi_lo`` is an
-    optional (hi, lo) pair of fp16 [B,H,W,c_stride] tensors filled with the conv-operand copy."""
+    optional (hi, lo) pair of fp16 [B,H,W,c_stride] tensors filled with the conv-operand copy.
+    ``cache_coords``: take the sample coordinates from the per-rig table (sweep_table / psv_gather; host
+    ``poses`` / ``baselines`` only) -- same bits, a pure gather from the second frame of a rig on."""
     _lib.require_cuda()
     lib = _lib.load()
     assert ref.shape == src.shape and ref.dim() == 4 and ref.shape[3] == 3
     B, H, W, _ = ref.shape
     dev = ref.device
+    if cache_coords and not torch.is_tensor(poses) and not torch.is_tensor(baselines) and not torch.is_tensor(depths):
+        tbl = sweep_table(np.asarray(poses, np.float32).reshape(B, 2, 16), baselines, depths, H, W, dev)
+        return psv_gather(ref, src, tbl, preprocess=preprocess, want_f32=want_f32, hi_lo=hi_lo, c_stride=c_stride,
+                          use_scratch=use_scratch)
     depths = _dev_f32(depths, dev, (-1,))
     P = depths.numel()
     poses = _dev_f32(poses, dev, (B, 2, 16))
@@ -280,8 +362,8 @@ def render_perspective(rgba, tgt_pos, depths, *, viewing_window=3, psp_height=27
     return (out, u8) if want_u8 else out
 
 
-def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device):
-    """msi_intersect_sphere_coords -> uv [B,L,H,W,2]."""
+def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device, fast=False):
+    """msi_intersect_sphere_coords[_ex] -> uv [B,L,H,W,2]; ``fast``: the coordinates the fused render kernel samples at."""
     _lib.require_cuda()
     lib = _lib.load()
     depths = _dev_f32(depths, device, (-1,))
@@ -290,8 +372,8 @@ def intersect_sphere_coords(tgt_pose_rt, tgt_pos, depths, B, H, W, device):
     pos = _dev_f32(tgt_pos, device, (B, 3))
     tb = erp_tables(H, W, device)
     uv = torch.empty((B, L, H, W, 2), dtype=torch.float32, device=device)
-    check(lib.msi_intersect_sphere_coords(ptr(pose), ptr(pos), ptr(depths), *tb.ptrs(), B, H, W, L, ptr(uv),
-                                          stream_ptr()), "msi_intersect_sphere_coords")
+    check(lib.msi_intersect_sphere_coords_ex(ptr(pose), ptr(pos), ptr(depths), *tb.ptrs(), B, H, W, L, 1 if fast else 0,
+                                             ptr(uv), stream_ptr()), "msi_intersect_sphere_coords_ex")
     return uv
 
 

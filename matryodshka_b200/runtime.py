@@ -25,6 +25,10 @@ _PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16}
 _VARIANT = {"coord": _lib.NET_COORD, "wrap": _lib.NET_WRAP}
 
 
+def _host_f32(x):
+    return x.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(x) else np.asarray(x, np.float32)
+
+
 def _aligned_bytes(n, device):
     """uint8 CUDA buffer of >= n bytes whose base is 1024-byte aligned."""
     buf = torch.empty(n + 1024, dtype=torch.uint8, device=device)
@@ -159,7 +163,9 @@ class MSIPipeline:
     """End-to-end frames on one GPU: (ref, src) ODS pair -> rendered ERP view + depth.
 
     Stages (all kernels of libmsi_b200.so, enqueued on one stream, graph-captured per batch size):
-      K1 msi_psv_build      -> PSV as the net's fp16 hi/lo operand, written straight into the net input
+      K1 msi_psv_gather     -> PSV as the net's fp16 hi/lo operand, written straight into the net input; the sample
+                               coordinates come from the per-rig table (ops.sweep_table) -- ``static_rig=False``
+                               evaluates them every frame instead (msi_psv_build: same bits)
       K2 msi_net_forward    -> pred [B,H,W,n_pred] (pixel stride = the engine's padded head width)
       K4 msi_rgba_assemble_strided -> RGBA layers [B,H,W,L,4]
       K5 msi_render_composite -> rgb / depth (float32 + uint8)
@@ -169,7 +175,8 @@ class MSIPipeline:
 
     def __init__(self, weights, H=320, W=640, num_planes=32, ngf=64, batch=1, device="cuda",
                  min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16x3",
-                 img_dtype=torch.float32, use_graph=True, coord_net=True, which_color_pred="blend_psv"):
+                 img_dtype=torch.float32, use_graph=True, coord_net=True, which_color_pred="blend_psv",
+                 static_rig=True):
         _lib.require_cuda()
         from .msi import MSI
         self.device = torch.device(device)
@@ -186,6 +193,10 @@ class MSIPipeline:
         self.src = torch.empty((B, H, W, 3), dtype=img_dtype, device=dev)
         self.poses = torch.eye(4, device=dev).reshape(1, 1, 16).repeat(B, 2, 1).contiguous()
         self.baselines = torch.full((B,), 0.032, device=dev)
+        # host mirror of the rig = the key of the cached coordinate table (no device read-back to look it up)
+        self.static_rig = static_rig
+        self._rig = (np.tile(np.eye(4, dtype=np.float32).reshape(1, 1, 16), (B, 2, 1)), np.full((B,), 0.032, np.float32))
+        self._table = None
         self.tgt_pose_rt = torch.eye(4, device=dev).reshape(1, 16).repeat(B, 1).contiguous()
         self.tgt_pos = torch.zeros((B, 3), device=dev)
         self.depths = torch.tensor(self.planes, dtype=torch.float32, device=dev)
@@ -225,6 +236,12 @@ class MSIPipeline:
         dt = _lib.IMG_U8 if self.img_dtype == torch.uint8 else _lib.IMG_F32
 
         def k1():
+            if self.static_rig:
+                t = self.sweep_table()
+                check(lib.msi_psv_gather(ptr(self.ref), ptr(self.src), dt, 1, ptr(t.table), t.frames, B, H, W, P, None,
+                                         ptr(self.hi), ptr(self.lo), self.net.in_c_stride, ptr(self.psv_scratch),
+                                         self.psv_scratch.numel(), stream_ptr()), "msi_psv_gather")
+                return
             check(lib.msi_psv_build(ptr(self.ref), ptr(self.src), dt, 1, ptr(self.poses), ptr(self.baselines),
                                     ptr(self.depths), *tb.ptrs(), B, H, W, P, None, ptr(self.hi), ptr(self.lo),
                                     self.net.in_c_stride, ptr(self.psv_scratch), self.psv_scratch.numel(), stream_ptr()),
@@ -255,6 +272,28 @@ class MSIPipeline:
 
         return [("psv_build", k1), ("net", k2), ("rgba_assemble", k4), ("render_composite", k5)]
 
+    def sweep_table(self):
+        """The cached sweep coordinates of the current rig (built on first use, shared between pipelines of the
+        same rig through the ops-level cache)."""
+        if self._table is None:
+            self._table = ops.sweep_table(self._rig[0], self._rig[1], self.planes, self.H, self.W, self.device)
+        return self._table
+
+    def set_rig(self, poses=None, baselines=None):
+        """Change the eye poses ([B,2,4,4] = pose_eye . ref_pose_inv, msi.py:1113-1127) and / or the ODS baselines
+        ([B]).  Drops the coordinate table and the captured graph (the next step rebuilds both)."""
+        B = self.B
+        if poses is not None:
+            p = np.ascontiguousarray(np.asarray(poses, np.float32).reshape(B, 2, 16))
+            self.poses.copy_(torch.from_numpy(p))
+            self._rig = (p, self._rig[1])
+        if baselines is not None:
+            b = np.ascontiguousarray(np.broadcast_to(np.asarray(baselines, np.float32).reshape(-1), (B,)))
+            self.baselines.copy_(torch.from_numpy(b))
+            self._rig = (self._rig[0], b)
+        self._table = None
+        self._graph = None
+
     def _enqueue(self):
         for _, fn in self._stages():
             fn()
@@ -282,6 +321,8 @@ class MSIPipeline:
 
     def step(self):
         """One pass of the hot path over the resident batch (inputs already in HBM)."""
+        if self.static_rig:
+            self.sweep_table()   # (outside any capture: building it synchronises)
         if not self.use_graph:
             self._enqueue()
             return
@@ -305,7 +346,7 @@ class MSIPipeline:
         if tgt_pos is not None:
             self.tgt_pos.copy_(torch.as_tensor(tgt_pos, dtype=torch.float32))
         if baselines is not None:
-            self.baselines.copy_(torch.as_tensor(baselines, dtype=torch.float32))
+            self.set_rig(baselines=_host_f32(baselines))
 
     # -- end-to-end step: host buffers in, host buffers out --------------------------------
     def step_e2e(self, ref_host=None, src_host=None):

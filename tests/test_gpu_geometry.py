@@ -159,6 +159,16 @@ def test_render_composite_matches_oracle(H, W, L, tp):
     for k in range(2):
         n_bad, n_far = _index_parity(uv[..., k], ref_uv[..., k], W if k == 0 else H)
         assert n_far == 0 and n_bad <= 2e-3 * uv[..., k].size
+    # ... and of the fast chain the fused kernel actually samples at (no IEEE divide / sqrt, polynomial atan2):
+    # same contract -- within 1e-3 px of the oracle, floor() flips only at knife-edge coordinates
+    uvf = ops.intersect_sphere_coords(eye, tp, d, 1, H, W, DEV, fast=True).cpu().numpy()[0]
+    assert np.abs(uvf - ref_uv).max() < 1e-3, np.abs(uvf - ref_uv).max()
+    flips = 0
+    for k in range(2):
+        n_bad, n_far = _index_parity(uvf[..., k], ref_uv[..., k], W if k == 0 else H)
+        assert n_far == 0 and n_bad <= 2e-3 * uvf[..., k].size
+        flips += n_bad
+    print(f"render fast chain {H}x{W}x{L}: max |duv| = {np.abs(uvf - ref_uv).max():.2e} px, floor flips = {flips} of {uvf.size}")
 
 
 def test_render_batch_and_pose_rotation():
@@ -274,3 +284,55 @@ def test_stage_level_spherical_functions():
     ph = np.linspace(-1.5, 1.5, 50).astype(F32)
     tp = sp.theta_phi_to_pixels(_t(th), _t(ph), W, H).cpu().numpy()
     assert np.array_equal(tp, g.theta_phi_to_pixels(th, ph, W, H))
+
+
+# ---- K1 with cached coordinates (msi_sweep_table_build + msi_psv_gather) -------------------------------
+@pytest.mark.parametrize("B,H,W,P,shared", [(1, 320, 640, 32, True), (2, 32, 64, 32, True), (2, 32, 64, 8, False),
+                                            (1, 10, 12, 4, True), (1, 16, 32, 6, True), (3, 24, 40, 64, False)])
+def test_psv_gather_equals_psv_build_bit_for_bit(B, H, W, P, shared):
+    """The table is written by the same device functions as the per-frame chain, so the gathered PSV -- float32 and
+    the fp16 hi/lo operand, disc < 0 samples included -- is the SAME BITS as msi_psv_build's.  Cases: the full bench
+    size; a batch sharing one rig (table_frames = 1) and one with a rig per frame (general poses, two baselines);
+    a ragged last block (120 pixels, 64 per block); P = 6 (generic kernel); P = 64 (config 3)."""
+    ref, src = synth.ods_pair(B, H, W, seed=5)
+    d = msi_np.inv_depths(1, 100, P)
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (B, 2, 1))
+    base = np.full((B,), 0.032, F32)
+    if not shared:
+        for b in range(B):
+            a = 0.01 * (b + 1)
+            m = np.array([[np.cos(a), 0, np.sin(a), 0.004 * b], [0, 1, 0, -0.003], [-np.sin(a), 0, np.cos(a), 0.002],
+                          [0, 0, 0, 1]], F32)
+            poses[b, 1] = m.reshape(16)
+            base[b] = 0.032 + 0.004 * b
+    cs = -(-6 * P // 64) * 64
+    mk = lambda: (torch.zeros((B, H, W, cs), dtype=torch.float16, device=DEV), torch.zeros((B, H, W, cs), dtype=torch.float16, device=DEV))  # noqa: E731
+    hl_a, hl_b = mk(), mk()
+    want = ops.psv_build(_t(ref), _t(src), poses, base, d, preprocess=True, hi_lo=hl_a, c_stride=cs)
+    tbl = ops.sweep_table(poses, base, d, H, W, DEV)
+    assert tbl.frames == (1 if shared else B)
+    got = ops.psv_gather(_t(ref), _t(src), tbl, preprocess=True, hi_lo=hl_b, c_stride=cs)
+    assert torch.equal(got, want)
+    assert torch.equal(hl_a[0], hl_b[0]) and torch.equal(hl_a[1], hl_b[1])
+    # the table itself == msi_sweep_coords (which the mask / index-grid tests above hold to the oracle)
+    uv, valid = ops.sweep_coords(poses[:tbl.frames], base[:tbl.frames], d, tbl.frames, H, W, DEV)   # [F,2,P,H,W,2]
+    t = tbl.table.view(tbl.frames, H, W, P, 2, 2).permute(0, 4, 3, 1, 2, 5)
+    assert torch.equal(t, uv)
+    if (B, H, W, P) == (1, 320, 640, 32):
+        assert int((valid[0, 0] == 0).sum()) == 68409 and bool((uv[0, 0][valid[0, 0] == 0] == 1.0).all())
+    # uint8 images and the cache_coords switch of the tensor-level API
+    ref8, src8 = _t((ref * 255).astype(np.uint8)), _t((src * 255).astype(np.uint8))
+    assert torch.equal(ops.psv_build(ref8, src8, poses, base, d, cache_coords=True), ops.psv_build(ref8, src8, poses, base, d))
+
+
+def test_sweep_table_cache_keyed_by_rig_values():
+    H, W, P = 16, 32, 4
+    d = msi_np.inv_depths(1, 100, P)
+    poses = np.tile(np.eye(4, dtype=F32).reshape(1, 1, 16), (1, 2, 1))
+    a = ops.sweep_table(poses, [0.032], d, H, W, DEV)
+    assert ops.sweep_table(poses.copy(), [0.032], list(d), H, W, DEV) is a            # same values -> same table
+    assert ops.sweep_table(poses, [0.033], d, H, W, DEV) is not a                    # another baseline
+    p2 = poses.copy()
+    p2[0, 1, 3] = 1e-4
+    assert ops.sweep_table(p2, [0.032], d, H, W, DEV) is not a                       # another pose
+    assert ops.sweep_table(poses, [0.032], msi_np.inv_depths(1, 50, P), H, W, DEV) is not a
