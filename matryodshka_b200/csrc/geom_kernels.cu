@@ -138,16 +138,17 @@ __global__ void __launch_bounds__(256) psv_build_kernel(PsvParams p) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 prep_images_kernel(const T* __restrict__ ref, const T* __restrict__ src, long long npix, int preprocess,
-                   float4* __restrict__ out) {
+                   float4* __restrict__ out, float scale = 1.0f) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= 2 * npix) return;
     const int e = idx >= npix;
     const long long pix = idx - (e ? npix : 0);
     const T* img = e ? src : ref;
     float4 o;
-    o.x = load_img<T>(img, (size_t)pix * 3 + 0, preprocess);
-    o.y = load_img<T>(img, (size_t)pix * 3 + 1, preprocess);
-    o.z = load_img<T>(img, (size_t)pix * 3 + 2, preprocess);
+    // scale is 1 or MSI_ACT_SCALE (a power of two: exact, and it commutes with the bilinear blend bit for bit)
+    o.x = load_img<T>(img, (size_t)pix * 3 + 0, preprocess) * scale;
+    o.y = load_img<T>(img, (size_t)pix * 3 + 1, preprocess) * scale;
+    o.z = load_img<T>(img, (size_t)pix * 3 + 2, preprocess) * scale;
     o.w = 0.f;
     out[idx] = o;
 }
@@ -267,65 +268,130 @@ __device__ __forceinline__ void split_half2(float a, float b, __half2& hi, __hal
     lo = __floats2half2_rn(a - hf.x, b - hf.y);
 }
 
-// grid (ceil(H*W / ppb), B), ppb = 256 / P pixels per block (P a power of two); thread = (pixel, plane),
-// both eyes: one 128-bit table load, all eight 128-bit taps in flight before the first blend
+// One bilinear sample of an RGBX image (taps a, b, c, d already loaded): tf.add_n order, no FMA (blend4).
+#define MSI_BLEND3(dst, t, a, b, c, d)                                              \
+    do {                                                                            \
+        (dst)[0] = (((t).wa * (a).x + (t).wb * (b).x) + (t).wc * (c).x) + (t).wd * (d).x; \
+        (dst)[1] = (((t).wa * (a).y + (t).wb * (b).y) + (t).wc * (c).y) + (t).wd * (d).y; \
+        (dst)[2] = (((t).wa * (a).z + (t).wb * (b).z) + (t).wc * (c).z) + (t).wd * (d).z; \
+    } while (0)
+
+// The gather kernel.  grid (ceil(groups / kGatherGroups), B); a group = ppb = 256 / P consecutive pixels
+// (P a power of two), thread = (pixel of the group, plane), both eyes.  A block walks kGatherGroups
+// consecutive groups and loads the NEXT group's table entry before it works on the current one, so the
+// table's DRAM latency hides behind the taps and blends (measured: the one-group form stalled 9 of 12
+// warps on the table -> taps dependency).  Per group and thread: one 128-bit table load, eight 128-bit
+// taps, six blends.  When the 2 x 2 footprints of a whole warp lie inside the image (all but the seam
+// columns and the pole rows) the four taps are base, +1, +W, +W+1 of one address; otherwise the
+// floor-mod wrap of sampling.resample (taps_in_range).  rgbx holds the images pre-scaled by
+// MSI_ACT_SCALE (exact: a power of two), so the staged values are the conv operand before the split.
+constexpr int kGatherGroups = 4;
 __global__ void __launch_bounds__(256) psv_gather_pair_kernel(PsvParams p, const float4* __restrict__ rgbx, int log2p) {
-    __shared__ __align__(16) float stage[1536];
-    const int P = p.P;
+    __shared__ __align__(16) float stage[2][1536];
+    const int P = p.P, W = p.W, H = p.H;
     const unsigned ppb = 256u >> log2p;
-    const unsigned HW = (unsigned)p.H * (unsigned)p.W;
-    const unsigned pixf0 = blockIdx.x * ppb;  // first pixel of the block inside its frame
+    const unsigned HW = (unsigned)H * (unsigned)W;
     const unsigned lp = threadIdx.x >> log2p;
     const unsigned pl = threadIdx.x & (unsigned)(P - 1);
-    const unsigned pixf = pixf0 + lp;
     const unsigned ib = blockIdx.y * HW;  // < 2^31 (checked on the host)
-    if (pixf < HW) {
-        const unsigned trow = (p.table_frames == 1 ? 0u : ib) + pixf;
-        const float4 uv = __ldcs(p.table + (((size_t)trow << log2p) + pl));
-        const Taps t0 = taps_in_range(uv.x, uv.y, p.W, p.H, ib);
-        const Taps t1 = taps_in_range(uv.z, uv.w, p.W, p.H, ib);
-        const float4* img0 = rgbx;
-        const float4* img1 = rgbx + (size_t)p.B * HW;
-        const float4 a0 = __ldg(img0 + t0.a), b0 = __ldg(img0 + t0.b), c0 = __ldg(img0 + t0.c), d0 = __ldg(img0 + t0.d);
-        const float4 a1 = __ldg(img1 + t1.a), b1 = __ldg(img1 + t1.b), c1 = __ldg(img1 + t1.c), d1 = __ldg(img1 + t1.d);
-        float* s0 = stage + (lp * 6u << log2p) + 3u * pl;
-        // tf.add_n of the four weighted corners: ((a + b) + c) + d   (blend4)
-        s0[0] = ((t0.wa * a0.x + t0.wb * b0.x) + t0.wc * c0.x) + t0.wd * d0.x;
-        s0[1] = ((t0.wa * a0.y + t0.wb * b0.y) + t0.wc * c0.y) + t0.wd * d0.y;
-        s0[2] = ((t0.wa * a0.z + t0.wb * b0.z) + t0.wc * c0.z) + t0.wd * d0.z;
-        float* s1 = s0 + 3 * P;
-        s1[0] = ((t1.wa * a1.x + t1.wb * b1.x) + t1.wc * c1.x) + t1.wd * d1.x;
-        s1[1] = ((t1.wa * a1.y + t1.wb * b1.y) + t1.wc * c1.y) + t1.wd * d1.y;
-        s1[2] = ((t1.wa * a1.z + t1.wb * b1.z) + t1.wc * c1.z) + t1.wd * d1.z;
+    const unsigned tb = (p.table_frames == 1 ? 0u : ib);
+    const float4* img0 = rgbx + ib;
+    const float4* img1 = img0 + (size_t)p.B * HW;
+    const unsigned g0 = blockIdx.x * kGatherGroups;
+    const float4 dummy = make_float4(1.f, 1.f, 1.f, 1.f);  // lanes past the frame sample pixel (1, 1); nothing is stored for them
+    float4 uv_next = dummy;
+    {
+        const unsigned pixf = g0 * ppb + lp;
+        if (pixf < HW) uv_next = __ldcs(p.table + (((size_t)(tb + pixf) << log2p) + pl));
     }
-    __syncthreads();
-    const unsigned nvalid = (HW - pixf0 < ppb) ? (HW - pixf0) : ppb;
-    const int nfl = (int)nvalid * 6 * P;
-    const size_t fbase = ((size_t)ib + pixf0) * 6 * P;
-    if (p.out_f32 != nullptr)
-        for (int q = threadIdx.x; q < nfl / 4; q += 256)
-            reinterpret_cast<float4*>(p.out_f32 + fbase)[q] = reinterpret_cast<const float4*>(stage)[q];
-    if (p.out_hi != nullptr) {
-        const int q = threadIdx.x;  // 1536 floats = 192 groups of 8: one group per thread
-        if (q < nfl / 8) {
-            const float4 a = reinterpret_cast<const float4*>(stage)[2 * q];
-            const float4 c = reinterpret_cast<const float4*>(stage)[2 * q + 1];
-            __half2 h0, h1, h2, h3, l0, l1, l2, l3;
-            split_half2(a.x * MSI_ACT_SCALE, a.y * MSI_ACT_SCALE, h0, l0);
-            split_half2(a.z * MSI_ACT_SCALE, a.w * MSI_ACT_SCALE, h1, l1);
-            split_half2(c.x * MSI_ACT_SCALE, c.y * MSI_ACT_SCALE, h2, l2);
-            split_half2(c.z * MSI_ACT_SCALE, c.w * MSI_ACT_SCALE, h3, l3);
-            uint4 hv, lv;
-            hv.x = *reinterpret_cast<const unsigned*>(&h0);
-            hv.y = *reinterpret_cast<const unsigned*>(&h1);
-            hv.z = *reinterpret_cast<const unsigned*>(&h2);
-            hv.w = *reinterpret_cast<const unsigned*>(&h3);
-            lv.x = *reinterpret_cast<const unsigned*>(&l0);
-            lv.y = *reinterpret_cast<const unsigned*>(&l1);
-            lv.z = *reinterpret_cast<const unsigned*>(&l2);
-            lv.w = *reinterpret_cast<const unsigned*>(&l3);
-            reinterpret_cast<uint4*>(p.out_hi + fbase)[q] = hv;
-            if (p.out_lo != nullptr) reinterpret_cast<uint4*>(p.out_lo + fbase)[q] = lv;
+#pragma unroll 1
+    for (int it = 0; it < kGatherGroups; ++it) {
+        const unsigned pixf0 = (g0 + it) * ppb;
+        if (pixf0 >= HW) break;
+        const float4 uv = uv_next;
+        uv_next = dummy;
+        if (it + 1 < kGatherGroups) {
+            const unsigned pixn = pixf0 + ppb + lp;
+            if (pixn < HW) uv_next = __ldcs(p.table + (((size_t)(tb + pixn) << log2p) + pl));
+        }
+        float* s0 = stage[it & 1] + (lp * 6u << log2p) + 3u * pl;
+        float* s1 = s0 + 3 * P;
+        const int x0 = __float2int_rd(uv.x), y0 = __float2int_rd(uv.y), x1 = __float2int_rd(uv.z), y1 = __float2int_rd(uv.w);
+        const bool inside = ((unsigned)x0 < (unsigned)(W - 1)) & ((unsigned)y0 < (unsigned)(H - 1)) &
+                            ((unsigned)x1 < (unsigned)(W - 1)) & ((unsigned)y1 < (unsigned)(H - 1));
+        if (__all_sync(0xffffffffu, inside)) {
+            const float4* q0 = img0 + (unsigned)(y0 * W + x0);
+            const float4* q1 = img1 + (unsigned)(y1 * W + x1);
+            float4 a0 = __ldg(q0), b0 = __ldg(q0 + 1), c0 = __ldg(q0 + W), d0 = __ldg(q0 + W + 1);
+            float4 a1 = __ldg(q1), b1 = __ldg(q1 + 1), c1 = __ldg(q1 + W), d1 = __ldg(q1 + W + 1);
+            // all eight taps are issued before the first one is consumed (the compiler otherwise pairs them up to save
+            // registers, and the kernel is bound by load latency, not by occupancy)
+            asm volatile("" : "+f"(a0.x), "+f"(b0.x), "+f"(c0.x), "+f"(d0.x), "+f"(a1.x), "+f"(b1.x), "+f"(c1.x), "+f"(d1.x));
+            Taps t0, t1;
+            {
+                const float fx = (float)x0, fy = (float)y0;
+                const float dx0 = uv.x - fx, dy0 = uv.y - fy, dx1 = (fx + 1.0f) - uv.x, dy1 = (fy + 1.0f) - uv.y;
+                t0.wa = dy1 * dx1;
+                t0.wb = dy1 * dx0;
+                t0.wc = dy0 * dx1;
+                t0.wd = dy0 * dx0;
+            }
+            {
+                const float fx = (float)x1, fy = (float)y1;
+                const float dx0 = uv.z - fx, dy0 = uv.w - fy, dx1 = (fx + 1.0f) - uv.z, dy1 = (fy + 1.0f) - uv.w;
+                t1.wa = dy1 * dx1;
+                t1.wb = dy1 * dx0;
+                t1.wc = dy0 * dx1;
+                t1.wd = dy0 * dx0;
+            }
+            MSI_BLEND3(s0, t0, a0, b0, c0, d0);
+            MSI_BLEND3(s1, t1, a1, b1, c1, d1);
+        } else {
+            const Taps t0 = taps_in_range(uv.x, uv.y, W, H, 0u);
+            const Taps t1 = taps_in_range(uv.z, uv.w, W, H, 0u);
+            const float4 a0 = __ldg(img0 + t0.a), b0 = __ldg(img0 + t0.b), c0 = __ldg(img0 + t0.c), d0 = __ldg(img0 + t0.d);
+            const float4 a1 = __ldg(img1 + t1.a), b1 = __ldg(img1 + t1.b), c1 = __ldg(img1 + t1.c), d1 = __ldg(img1 + t1.d);
+            MSI_BLEND3(s0, t0, a0, b0, c0, d0);
+            MSI_BLEND3(s1, t1, a1, b1, c1, d1);
+        }
+        __syncthreads();
+        // (two stage buffers: the next iteration's writers cannot overtake this iteration's readers by more
+        // than one barrier)
+        const float* st = stage[it & 1];
+        const unsigned nvalid = (HW - pixf0 < ppb) ? (HW - pixf0) : ppb;
+        const int nfl = (int)nvalid * 6 * P;
+        const size_t fbase = ((size_t)ib + pixf0) * 6 * P;
+        if (p.out_f32 != nullptr)
+            for (int q = threadIdx.x; q < nfl / 4; q += 256) {
+                float4 v = reinterpret_cast<const float4*>(st)[q];
+                v.x *= 1.0f / MSI_ACT_SCALE;
+                v.y *= 1.0f / MSI_ACT_SCALE;
+                v.z *= 1.0f / MSI_ACT_SCALE;
+                v.w *= 1.0f / MSI_ACT_SCALE;
+                reinterpret_cast<float4*>(p.out_f32 + fbase)[q] = v;
+            }
+        if (p.out_hi != nullptr) {
+            const int q = threadIdx.x;  // 1536 floats = 192 groups of 8: one group per thread
+            if (q < nfl / 8) {
+                const float4 a = reinterpret_cast<const float4*>(st)[2 * q];
+                const float4 c = reinterpret_cast<const float4*>(st)[2 * q + 1];
+                __half2 h0, h1, h2, h3, l0, l1, l2, l3;
+                split_half2(a.x, a.y, h0, l0);
+                split_half2(a.z, a.w, h1, l1);
+                split_half2(c.x, c.y, h2, l2);
+                split_half2(c.z, c.w, h3, l3);
+                uint4 hv, lv;
+                hv.x = *reinterpret_cast<const unsigned*>(&h0);
+                hv.y = *reinterpret_cast<const unsigned*>(&h1);
+                hv.z = *reinterpret_cast<const unsigned*>(&h2);
+                hv.w = *reinterpret_cast<const unsigned*>(&h3);
+                lv.x = *reinterpret_cast<const unsigned*>(&l0);
+                lv.y = *reinterpret_cast<const unsigned*>(&l1);
+                lv.z = *reinterpret_cast<const unsigned*>(&l2);
+                lv.w = *reinterpret_cast<const unsigned*>(&l3);
+                reinterpret_cast<uint4*>(p.out_hi + fbase)[q] = hv;
+                if (p.out_lo != nullptr) reinterpret_cast<uint4*>(p.out_lo + fbase)[q] = lv;
+            }
         }
     }
 }
@@ -637,29 +703,60 @@ __global__ void __launch_bounds__(256) render_composite_v2_kernel(RenderParams p
     __syncthreads();
 
     {
+        // every thread runs the same number of iterations (warp votes inside); lanes past the work sample pixel (1, 1)
         int q = threadIdx.x / L;
         int l = threadIdx.x - q * L;
         const int dq = 256 / L, dl = 256 - dq * L;
-        for (int s = threadIdx.x; s < NPIX * L; s += 256) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pix0 + q < npix) {
-                float u, v;
+        const int W = p.W, H = p.H;
+        const int iters = (NPIX * L + 255) / 256;
+        int s = threadIdx.x;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it, s += 256) {
+            const bool live = (s < NPIX * L) && (pix0 + q < npix);
+            float u = 1.0f, v = 1.0f;
+            unsigned ib = 0;
+            if (live) {
                 sphere_hit_uv_fast(s_ray[q], rad2[l], p.k, u, v);
-                const Taps t = taps_in_range(u, v, p.W, p.H, s_ib[q]);
-                const float4* base = p.rgba + l;
-                const float4 pa = __ldg(base + (size_t)t.a * L);
-                const float4 pb = __ldg(base + (size_t)t.b * L);
-                const float4 pc = __ldg(base + (size_t)t.c * L);
-                const float4 pd = __ldg(base + (size_t)t.d * L);
-                o.x = ((t.wa * pa.x + t.wb * pb.x) + t.wc * pc.x) + t.wd * pd.x;
-                o.y = ((t.wa * pa.y + t.wb * pb.y) + t.wc * pc.y) + t.wd * pd.y;
-                o.z = ((t.wa * pa.z + t.wb * pb.z) + t.wc * pc.z) + t.wd * pd.z;
-                o.w = ((t.wa * pa.w + t.wb * pb.w) + t.wc * pc.w) + t.wd * pd.w;
+                ib = s_ib[q];
             }
-            sm[(0 * NPIX + q) * ld + l] = o.x;
-            sm[(1 * NPIX + q) * ld + l] = o.y;
-            sm[(2 * NPIX + q) * ld + l] = o.z;
-            sm[(3 * NPIX + q) * ld + l] = o.w;
+            const float4* base = p.rgba + (live ? l : 0);
+            const int x0 = __float2int_rd(u), y0 = __float2int_rd(v);
+            const bool inside = ((unsigned)x0 < (unsigned)(W - 1)) & ((unsigned)y0 < (unsigned)(H - 1));
+            float4 pa, pb, pc, pd;
+            Taps t;
+            if (__all_sync(0xffffffffu, inside)) {
+                // 2 x 2 footprint inside the image for the whole warp: one address, offsets 1, W, W + 1 texels
+                const float4* q0 = base + (size_t)(ib + (unsigned)(y0 * W + x0)) * L;
+                pa = __ldg(q0);
+                pb = __ldg(q0 + L);
+                pc = __ldg(q0 + (size_t)W * L);
+                pd = __ldg(q0 + (size_t)W * L + L);
+                const float fx = (float)x0, fy = (float)y0;
+                const float dx0 = u - fx, dy0 = v - fy, dx1 = (fx + 1.0f) - u, dy1 = (fy + 1.0f) - v;
+                t.wa = dy1 * dx1;
+                t.wb = dy1 * dx0;
+                t.wc = dy0 * dx1;
+                t.wd = dy0 * dx0;
+            } else {
+                t = taps_in_range(u, v, W, H, ib);
+                pa = __ldg(base + (size_t)t.a * L);
+                pb = __ldg(base + (size_t)t.b * L);
+                pc = __ldg(base + (size_t)t.c * L);
+                pd = __ldg(base + (size_t)t.d * L);
+            }
+            if (s < NPIX * L) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    o.x = ((t.wa * pa.x + t.wb * pb.x) + t.wc * pc.x) + t.wd * pd.x;
+                    o.y = ((t.wa * pa.y + t.wb * pb.y) + t.wc * pc.y) + t.wd * pd.y;
+                    o.z = ((t.wa * pa.z + t.wb * pb.z) + t.wc * pc.z) + t.wd * pd.z;
+                    o.w = ((t.wa * pa.w + t.wb * pb.w) + t.wc * pc.w) + t.wd * pd.w;
+                }
+                sm[(0 * NPIX + q) * ld + l] = o.x;
+                sm[(1 * NPIX + q) * ld + l] = o.y;
+                sm[(2 * NPIX + q) * ld + l] = o.z;
+                sm[(3 * NPIX + q) * ld + l] = o.w;
+            }
             q += dq;
             l += dl;
             if (l >= L) {
@@ -993,12 +1090,12 @@ extern "C" int msi_psv_gather(const void* ref, const void* src, int img_dtype, i
         float4* rgbx = reinterpret_cast<float4*>(scratch);
         if (img_dtype == MSI_IMG_F32)
             prep_images_kernel<float><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
-                reinterpret_cast<const float*>(ref), reinterpret_cast<const float*>(src), npix, preprocess, rgbx);
+                reinterpret_cast<const float*>(ref), reinterpret_cast<const float*>(src), npix, preprocess, rgbx, MSI_ACT_SCALE);
         else
             prep_images_kernel<uint8_t><<<ceil_div(2 * npix, 256), 256, 0, st>>>(
-                reinterpret_cast<const uint8_t*>(ref), reinterpret_cast<const uint8_t*>(src), npix, preprocess, rgbx);
+                reinterpret_cast<const uint8_t*>(ref), reinterpret_cast<const uint8_t*>(src), npix, preprocess, rgbx, MSI_ACT_SCALE);
         MSI_LAUNCH_CHECK();
-        const dim3 grid((unsigned)ceil_div((long long)H * W, 256 / P), (unsigned)B);
+        const dim3 grid((unsigned)ceil_div(ceil_div((long long)H * W, 256 / P), kGatherGroups), (unsigned)B);
         int log2p = 0;
         while ((1 << log2p) < P) ++log2p;  // 256 % P == 0: P is a power of two
         psv_gather_pair_kernel<<<grid, 256, 0, st>>>(p, rgbx, log2p);

@@ -159,16 +159,24 @@ def test_render_composite_matches_oracle(H, W, L, tp):
     for k in range(2):
         n_bad, n_far = _index_parity(uv[..., k], ref_uv[..., k], W if k == 0 else H)
         assert n_far == 0 and n_bad <= 2e-3 * uv[..., k].size
-    # ... and of the fast chain the fused kernel actually samples at (no IEEE divide / sqrt, polynomial atan2):
-    # same contract -- within 1e-3 px of the oracle, floor() flips only at knife-edge coordinates
+    # ... and of the fast chain the fused kernel actually samples at (no IEEE divide / sqrt, polynomial atan2).
+    # Contract: within 1e-3 px of the oracle wherever the longitude is well conditioned, floor() flips only at
+    # knife-edge coordinates.  Where the hit point lies within 1e-3 R of the vertical axis (a handful of samples
+    # around the two poles of the source sphere) one ulp of x or z already moves u by more than that -- for any
+    # evaluation order, the strict chain included (2e-3 above) -- and the bound there is 5e-3 px.
     uvf = ops.intersect_sphere_coords(eye, tp, d, 1, H, W, DEV, fast=True).cpu().numpy()[0]
-    assert np.abs(uvf - ref_uv).max() < 1e-3, np.abs(uvf - ref_uv).max()
+    phi_src = ref_uv[..., 1] / F32(H - 1) * F32(np.pi - np.pi / H) - F32(np.pi / 2 - np.pi / (2 * H))
+    well = np.cos(phi_src) > 1e-3
+    duv = np.abs(uvf - ref_uv)
+    assert duv[well].max() < 1e-3 and duv.max() < 5e-3, (duv[well].max(), duv.max())
+    assert (~well).sum() <= max(4, 1e-5 * well.size)
     flips = 0
     for k in range(2):
         n_bad, n_far = _index_parity(uvf[..., k], ref_uv[..., k], W if k == 0 else H)
         assert n_far == 0 and n_bad <= 2e-3 * uvf[..., k].size
         flips += n_bad
-    print(f"render fast chain {H}x{W}x{L}: max |duv| = {np.abs(uvf - ref_uv).max():.2e} px, floor flips = {flips} of {uvf.size}")
+    print(f"render fast chain {H}x{W}x{L}: max |duv| = {duv[well].max():.2e} px ({duv.max():.2e} incl. {int((~well).sum())} "
+          f"ill-conditioned samples), floor flips = {flips} of {uvf.size}")
 
 
 def test_render_batch_and_pose_rotation():
