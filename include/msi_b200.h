@@ -348,6 +348,17 @@ int msi_net_load_layer(msi_net* net, const char* scope, const float* weights, co
 int msi_net_forward(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
                     float* pred, void* stream);
 
+/* msi_net_forward with the RGBA assembly of `blend_psv` (MSI.infer_msi layer_prediction block,
+ * matryodshka/msi.py:130-147) fused into the head's epilogue: the 1x1 conv + bias + tanh of
+ * nets.py:509-515 never leaves the SM as `pred`; the epilogue turns a pixel's L blend weights and L
+ * alphas into rgba [B,H,W,L,4], reading the pixel's two PSV eyes from the net's own input operand
+ * (fp16 hi + lo).  Same arithmetic, in the same order, as msi_net_forward + msi_rgba_assemble on
+ * that operand (bit for bit).  Available when msi_net_can_fuse_rgba() returns 1: tcgen05 back
+ * end, MSI_PREC_FP16X3, c_in = 6P and c_out = 2L with L = P = 32 or 64. */
+int msi_net_can_fuse_rgba(const msi_net* net);
+int msi_net_forward_rgba(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                         float* rgba, void* stream);
+
 /* The workspace copy of the network input (fp16 hi/lo, channel stride
  * msi_net_input_c_stride()): let msi_psv_build write the PSV there and pass the
  * same pointers to msi_net_forward to skip the copy. */

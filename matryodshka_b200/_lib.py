@@ -61,6 +61,8 @@ SIGNATURES = {
     "msi_net_bind": (c_int, [_P, _P, c_size_t, _P, c_size_t]),
     "msi_net_load_layer": (c_int, [_P, c_char_p, _P, _P, _P, _P, _P]),
     "msi_net_forward": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
+    "msi_net_can_fuse_rgba": (c_int, [_P]),
+    "msi_net_forward_rgba": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "msi_net_input_buffers": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p)]),
     "msi_net_read_activation": (c_int, [_P, c_char_p, _I, _P, _P]),
     "msi_net_read_raw": (c_int, [_P, c_char_p, _I, _P, _P]),

@@ -105,6 +105,13 @@ struct TcParams {
     int grid_off;
     int stat_all;
     long long* trace;    // debugging: CTA 0 records clock64() of its pipeline events here (null = off)
+    // Head fused with the RGBA assembly (MSI.infer_msi `blend_psv`, msi.py:130-147): the epilogue turns a pixel's
+    // L blend weights and L alphas into its L RGBA layers, reading the two PSV eyes of that pixel from the net's
+    // own input operand (fp16 hi + lo).  rgba == null: the plain head (tanh -> pred).
+    float4* rgba;            // [B,Hout,Wout,L] float4
+    const __half* psv_hi;    // [B,H,Wp,psv_cstride], pixel x at column x + psv_xpad
+    const __half* psv_lo;
+    int psv_cstride, psv_Wp, psv_xpad;
 };
 
 struct TcPlan {
@@ -485,16 +492,17 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 v;
+                    // (explicit roundings: the fused RGBA epilogue of the head repeats this arithmetic bit for bit)
                     if (SPLIT) {
-                        v.x = (__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0])) * p.unscale;
-                        v.y = (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) * p.unscale;
-                        v.z = (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) * p.unscale;
-                        v.w = (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) * p.unscale;
+                        v.x = __fmul_rn(__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0]), p.unscale);
+                        v.y = __fmul_rn(__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]), p.unscale);
+                        v.z = __fmul_rn(__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), p.unscale);
+                        v.w = __fmul_rn(__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]), p.unscale);
                     } else {
-                        v.x = __uint_as_float(r[j + 0]) * p.unscale;
-                        v.y = __uint_as_float(r[j + 1]) * p.unscale;
-                        v.z = __uint_as_float(r[j + 2]) * p.unscale;
-                        v.w = __uint_as_float(r[j + 3]) * p.unscale;
+                        v.x = __fmul_rn(__uint_as_float(r[j + 0]), p.unscale);
+                        v.y = __fmul_rn(__uint_as_float(r[j + 1]), p.unscale);
+                        v.z = __fmul_rn(__uint_as_float(r[j + 2]), p.unscale);
+                        v.w = __fmul_rn(__uint_as_float(r[j + 3]), p.unscale);
                     }
                     if (cb != nullptr) {
                         const float4 q = __ldg(reinterpret_cast<const float4*>(cb + c + j));
@@ -505,10 +513,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
                     }
                     if (p.kind == kHead) {
                         const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + tc.n0 + c + j));
-                        v.x = fast_tanh(v.x + q.x);
-                        v.y = fast_tanh(v.y + q.y);
-                        v.z = fast_tanh(v.z + q.z);
-                        v.w = fast_tanh(v.w + q.w);
+                        v.x = fast_tanh(__fadd_rn(v.x, q.x));
+                        v.y = fast_tanh(__fadd_rn(v.y, q.y));
+                        v.z = fast_tanh(__fadd_rn(v.z, q.z));
+                        v.w = fast_tanh(__fadd_rn(v.w, q.w));
                     }
                     s_sum += (v.x + v.y) + (v.z + v.w);
                     s_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
@@ -594,6 +602,127 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
             }
         }
         if (ew == 0 && lane == 0) trace_g(p.trace, tr_launch, 6);
+    }
+}
+
+// Epilogue of the head fused with the RGBA assembly (replaces the `pred` round trip through HBM and the separate
+// rgba_assemble launch).  N_TILE = 2L: accumulator columns [0, L) are a pixel's blend weights, [L, 2L) its alphas.
+//   1. the two warps of a TMEM lane quarter (ew and ew + 4) read the weight / alpha halves of their 32 pixels,
+//      apply bias + tanh and (x + 1) / 2 (msi.py:131-133) and park them in a shared-memory tile, 16-byte chunks
+//      XOR-swizzled by the row so that both the row-wise writes and the layer-wise reads are conflict-free;
+//   2. named barrier of the pair; then each warp assembles 16 of the 32 pixels with lanes = layer pairs: the PSV
+//      taps of a pixel (fg = reference eye, bg = source eye; 3L halves each, hi and lo) are contiguous 4-byte loads
+//      across the lanes, rgb = w * fg + (1 - w) * bg without FMA (the arithmetic of rgba_assemble_kernel, bit for
+//      bit), and the L float4 of a pixel leave as one contiguous run.
+template <int N_TILE>
+__device__ __forceinline__ void epilogue_head_rgba(const TcParams& p, const int ew, const int quarter, const int lane,
+                                                   const int cluster_id, const int n_clusters, const uint32_t tmem_base,
+                                                   const uint32_t tfull0, const uint32_t tempty0, const uint32_t stage_base) {
+    constexpr int L = N_TILE / 2;
+    constexpr int kAccCols = 2 * N_TILE;
+    constexpr uint32_t kRowBytes = N_TILE * 4;
+    constexpr int kLanesPerPixel = L / 2;             // a lane owns the layer pair (2k, 2k + 1)
+    constexpr int kPixPerIter = 32 / kLanesPerPixel;  // L = 32: two pixels per warp iteration; L = 64: one
+    const uint32_t qbase = stage_base + (uint32_t)quarter * 32u * kRowBytes;
+    const int half = ew >> 2;  // 0: this warp reads the blend weights out of TMEM, 1: the alphas
+    const int sub = lane / kLanesPerPixel, k = lane - sub * kLanesPerPixel;
+    const float inv = 1.0f / MSI_ACT_SCALE;
+    int local = 0;
+    for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
+        const TileCoord tc = decode_unit(p, unit, 0, 1, N_TILE);
+        const int acc = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(tfull0 + 8u * acc, use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
+#pragma unroll 1
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            const int c = half * L + c0;
+            uint32_t r[32], r2[32];
+            tmem_ld32(taddr + (uint32_t)c, r);
+            tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 + 32 >= L) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p.bias + c + j));
+                float4 v;
+                v.x = __fadd_rn(fast_tanh(__fadd_rn(__fmul_rn(__uint_as_float(r[j + 0]) + __uint_as_float(r2[j + 0]), p.unscale), q.x)), 1.0f) * 0.5f;
+                v.y = __fadd_rn(fast_tanh(__fadd_rn(__fmul_rn(__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]), p.unscale), q.y)), 1.0f) * 0.5f;
+                v.z = __fadd_rn(fast_tanh(__fadd_rn(__fmul_rn(__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), p.unscale), q.z)), 1.0f) * 0.5f;
+                v.w = __fadd_rn(fast_tanh(__fadd_rn(__fmul_rn(__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]), p.unscale), q.w)), 1.0f) * 0.5f;
+                const int ch = (c + j) >> 2;  // 16-byte chunk of the row
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(qbase + (uint32_t)lane * kRowBytes + (uint32_t)((ch >> 3) << 7) +
+                                                                             (uint32_t)(((ch & 7) ^ (lane & 7)) << 4)),
+                             "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+            }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+#pragma unroll 2
+        for (int i = 0; i < 16; i += kPixPerIter) {
+            const int rr = half * 16 + i + sub;  // row of the quarter = pixel
+            const int m = quarter * 32 + rr;     // pixel of the M tile
+            const int ly = m / p.BW, lx = m - ly * p.BW;
+            const int oy = tc.oy0 + ly, ox = tc.ox0 + lx;
+            const bool valid = (oy < p.Mh) && (ox < p.Mw) && !tc.dummy;
+            const int chw = k >> 1, cha = (L >> 2) + (k >> 1);
+            float2 w2, a2;
+            const uint32_t rowaddr = qbase + (uint32_t)rr * kRowBytes + (uint32_t)((k & 1) << 3);
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(w2.x), "=f"(w2.y)
+                         : "r"(rowaddr + (uint32_t)((chw >> 3) << 7) + (uint32_t)(((chw & 7) ^ (rr & 7)) << 4))
+                         : "memory");
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(a2.x), "=f"(a2.y)
+                         : "r"(rowaddr + (uint32_t)((cha >> 3) << 7) + (uint32_t)(((cha & 7) ^ (rr & 7)) << 4))
+                         : "memory");
+            if (valid) {
+                const size_t poff = (((size_t)tc.b * p.Hout + oy) * p.psv_Wp + ox + p.psv_xpad) * p.psv_cstride + 6 * k;
+                const unsigned* fh = reinterpret_cast<const unsigned*>(p.psv_hi + poff);
+                const unsigned* fl = reinterpret_cast<const unsigned*>(p.psv_lo + poff);
+                const unsigned* bh = reinterpret_cast<const unsigned*>(p.psv_hi + poff + 3 * L);
+                const unsigned* bl = reinterpret_cast<const unsigned*>(p.psv_lo + poff + 3 * L);
+                unsigned wfh[3], wfl[3], wbh[3], wbl[3];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    wfh[t] = __ldg(fh + t);
+                    wfl[t] = __ldg(fl + t);
+                    wbh[t] = __ldg(bh + t);
+                    wbl[t] = __ldg(bl + t);
+                }
+                float fg[6], bg[6];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&wfh[t]));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&wfl[t]));
+                    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&wbh[t]));
+                    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&wbl[t]));
+                    fg[2 * t] = __fmul_rn(__fadd_rn(a.x, b.x), inv);
+                    fg[2 * t + 1] = __fmul_rn(__fadd_rn(a.y, b.y), inv);
+                    bg[2 * t] = __fmul_rn(__fadd_rn(c.x, d.x), inv);
+                    bg[2 * t + 1] = __fmul_rn(__fadd_rn(c.y, d.y), inv);
+                }
+                const float om0 = __fsub_rn(1.0f, w2.x), om1 = __fsub_rn(1.0f, w2.y);
+                float4 o0, o1;
+                o0.x = __fadd_rn(__fmul_rn(w2.x, fg[0]), __fmul_rn(om0, bg[0]));
+                o0.y = __fadd_rn(__fmul_rn(w2.x, fg[1]), __fmul_rn(om0, bg[1]));
+                o0.z = __fadd_rn(__fmul_rn(w2.x, fg[2]), __fmul_rn(om0, bg[2]));
+                o0.w = a2.x;
+                o1.x = __fadd_rn(__fmul_rn(w2.y, fg[3]), __fmul_rn(om1, bg[3]));
+                o1.y = __fadd_rn(__fmul_rn(w2.y, fg[4]), __fmul_rn(om1, bg[4]));
+                o1.z = __fadd_rn(__fmul_rn(w2.y, fg[5]), __fmul_rn(om1, bg[5]));
+                o1.w = a2.y;
+                float4* dst = p.rgba + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * L + 2 * k;
+                dst[0] = o0;
+                dst[1] = o1;
+            }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");  // the tile may be overwritten
     }
 }
 
@@ -796,8 +925,12 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         // =============================== epilogue (warps 2..9) ===============================
         const int row = (warp & 3) * 32 + lane;  // M index inside the tile
         const int ly = row / p.BW;
-        epilogue_role<N_TILE, SPLIT, CL>(p, warp - 2, warp & 3, lane, row - ly * p.BW, ly, cluster_id, n_clusters, cta_rank,
-                                         tmem_base, tfull0, tempty0, &s_is_last, s_red);
+        if (SPLIT && CL == 1 && p.rgba != nullptr)
+            epilogue_head_rgba<N_TILE>(p, warp - 2, warp & 3, lane, cluster_id, n_clusters, tmem_base, tfull0, tempty0,
+                                       smem_base + (uint32_t)(stages * kStageBytes));
+        else
+            epilogue_role<N_TILE, SPLIT, CL>(p, warp - 2, warp & 3, lane, row - ly * p.BW, ly, cluster_id, n_clusters, cta_rank,
+                                             tmem_base, tfull0, tempty0, &s_is_last, s_red);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1596,14 +1729,16 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     p.cb_Win = L.Win;
     p.bias = (L.kind == kHead) ? L.bias : nullptr;
     const int stage_bytes = (kATileBytes + plan->n_tile * kBlockK * 2) * (plan->split ? 2 : 1);
-    p.stages = (kMaxDynSmem - 1024) / stage_bytes;
+    // the head keeps room for the [128 pixels][n_tile] float tile of its fused RGBA epilogue
+    const int rgba_tile_bytes = (L.kind == kHead) ? kBlockM * plan->n_tile * 4 : 0;
+    p.stages = (kMaxDynSmem - 1024 - rgba_tile_bytes) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) {
         delete plan;
         set_error("conv_tc: layer %s does not fit 2 pipeline stages", L.scope);
         return MSI_ERR_UNSUPPORTED;
     }
-    plan->smem_bytes = p.stages * stage_bytes + 1024;
+    plan->smem_bytes = p.stages * stage_bytes + 1024 + rgba_tile_bytes;
     p.do_stats = (L.kind != kHead) ? 1 : 0;
     p.n_partials = L.n_partials;
     p.partials = L.partials;
@@ -1716,7 +1851,13 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
 
 // The caller has zeroed L.partials / L.counter on `st` before this launch (net.cu does one memset
 // for all layers per forward).  On return L.stats holds (mean, rstd) per frame.
-int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st) {
+bool conv_tc_can_fuse_rgba(const LayerPlan& L) {
+    const TcPlan* plan = reinterpret_cast<const TcPlan*>(L.tc_plan);
+    return plan && L.kind == kHead && !plan->halo && plan->split && plan->cl == 1 && plan->n_tile == L.cout &&
+           (L.cout == 64 || L.cout == 128);
+}
+
+int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st, const HeadFuse* fuse) {
     TcPlan* plan = reinterpret_cast<TcPlan*>(L.tc_plan);
     if (!plan) {
         set_error("conv_tc_forward: layer %s has no plan", L.scope);
@@ -1725,6 +1866,19 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
     TcParams p = plan->p;
     p.out = out;
     p.B = B;
+    p.rgba = nullptr;
+    if (fuse != nullptr) {
+        if (!conv_tc_can_fuse_rgba(L)) {
+            set_error("conv_tc_forward: layer %s cannot take the fused RGBA epilogue", L.scope);
+            return MSI_ERR_UNSUPPORTED;
+        }
+        p.rgba = reinterpret_cast<float4*>(fuse->rgba);
+        p.psv_hi = fuse->psv_hi;
+        p.psv_lo = fuse->psv_lo;
+        p.psv_cstride = fuse->c_stride;
+        p.psv_Wp = fuse->Wp;
+        p.psv_xpad = fuse->x_pad;
+    }
     const int cl = plan->cl;
     p.m_tiles = B * p.tiles_x * p.tiles_y;
     p.units_per_col = (p.m_tiles + cl - 1) / cl;

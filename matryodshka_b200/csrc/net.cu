@@ -371,11 +371,29 @@ extern "C" int msi_net_load_layer(msi_net* net, const char* scope, const float* 
 }
 
 static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
-                            float* pred, void* stream, cudaEvent_t* ev);
+                            float* pred, void* stream, cudaEvent_t* ev, float* rgba = nullptr);
 
 extern "C" int msi_net_forward(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
                                float* pred, void* stream) {
     return net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, nullptr);
+}
+
+// The head's epilogue can assemble the RGBA layers itself when the net is the `blend_psv` net of the tensor-core
+// back end: c_in = 6P PSV channels, c_out = 2L with L = P, fp16x3 operands, L = 32 or 64 (one N tile).
+extern "C" int msi_net_can_fuse_rgba(const msi_net* net) {
+    if (!net || !net->bound || net->conv_impl != MSI_CONV_TCGEN05 || net->precision != MSI_PREC_FP16X3) return 0;
+    if (net->c_in != 3 * net->c_out) return 0;
+    return conv_tc_can_fuse_rgba(net->layers[kNumLayers - 1]) ? 1 : 0;
+}
+
+extern "C" int msi_net_forward_rgba(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
+                                    float* rgba, void* stream) {
+    MSI_CHECK_ARG(net && rgba, "net_forward_rgba: null pointer");
+    if (!msi_net_can_fuse_rgba(net)) {
+        set_error("net_forward_rgba: this net cannot fuse the RGBA assembly (needs tcgen05, fp16x3, c_in = 3 c_out, c_out 64 or 128)");
+        return MSI_ERR_UNSUPPORTED;
+    }
+    return net_forward_impl(net, in_f32, in_hi, in_lo, B, nullptr, stream, nullptr, rgba);
 }
 
 // Measurement forward: every layer runs once (the real forward), then its conv kernel and its
@@ -430,8 +448,8 @@ extern "C" double msi_net_layer_flops(const msi_net* net, int i) {
 }
 
 static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
-                            float* pred, void* stream, cudaEvent_t* ev) {
-    MSI_CHECK_ARG(net && pred, "net_forward: null pointer");
+                            float* pred, void* stream, cudaEvent_t* ev, float* rgba) {
+    MSI_CHECK_ARG(net && (pred || rgba), "net_forward: null pointer");
     MSI_CHECK_ARG(B >= 1 && B <= net->max_batch, "net_forward: B=%d outside [1, %d]", B, net->max_batch);
     MSI_CHECK_ARG(in_f32 || (in_hi && in_lo), "net_forward: need in_f32 or the hi/lo pair");
     if (!net->bound) {
@@ -473,10 +491,21 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
         const int conv_runs = ev ? 1 + kProfReps : 1;
         for (int r = 0; r < conv_runs; ++r) {
             if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i], st));
-            if (net->conv_impl == MSI_CONV_SIMT)
+            if (net->conv_impl == MSI_CONV_SIMT) {
                 rc = conv_simt_forward(L, srcs, B, out, st);
-            else  // the first conv follows a memset / copy, every later one follows our own LayerNorm kernel
+            } else if (L.kind == kHead && rgba != nullptr) {
+                // fused RGBA assembly: the PSV eyes of a pixel come from the net's own input operand
+                HeadFuse hf;
+                hf.rgba = rgba;
+                hf.psv_hi = net->acts[0].hi;
+                hf.psv_lo = net->acts[0].lo;
+                hf.c_stride = net->acts[0].c_stride;
+                hf.Wp = net->acts[0].Wp;
+                hf.x_pad = net->acts[0].x_pad;
+                rc = conv_tc_forward(L, B, nullptr, /*after_kernel=*/true, st, &hf);
+            } else {  // the first conv follows a memset / copy, every later one follows our own LayerNorm kernel
                 rc = conv_tc_forward(L, B, out, /*after_kernel=*/i > 0 || r > 0, st);
+            }
             if (rc != MSI_OK) return rc;
         }
         if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 1], st));

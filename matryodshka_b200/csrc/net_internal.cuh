@@ -113,7 +113,16 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
 void conv_tc_plan_destroy(LayerPlan& L);
 // after_kernel: the previous operation in the stream is one of this library's kernels that calls
 // griddepcontrol.wait itself, so this launch may use programmatic dependent launch
-int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st);
+// fuse != null (head only, conv_tc_can_fuse_rgba): the epilogue assembles the RGBA layers (msi.py:130-147) from the
+// prediction and the PSV operand instead of storing the prediction; `out` is then unused
+struct HeadFuse {
+    float* rgba;          // [B,H,W,L,4]
+    const __half* psv_hi; // the net's input operand [B,H,Wp,c_stride], pixel x at column x + x_pad
+    const __half* psv_lo;
+    int c_stride, Wp, x_pad;
+};
+bool conv_tc_can_fuse_rgba(const LayerPlan& L);
+int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cudaStream_t st, const HeadFuse* fuse = nullptr);
 bool pdl_enabled();
 int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
 

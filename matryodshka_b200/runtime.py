@@ -134,6 +134,26 @@ class NetEngine:
               "msi_net_forward")
         return out if self.c_out_eng == self.c_out else out[..., :self.c_out]
 
+    @property
+    def can_fuse_rgba(self):
+        return bool(self.lib.msi_net_can_fuse_rgba(self._h))
+
+    def forward_rgba(self, psv=None, *, hi_lo=None, out=None):
+        """msi_net_forward_rgba: the forward with the `blend_psv` RGBA assembly (msi.py:130-147) fused into the
+        head's epilogue.  Returns rgba [B,H,W,L,4] (L = c_out / 2); the prediction is never written."""
+        if psv is not None:
+            B = psv.shape[0]
+            psv = psv.contiguous()
+        else:
+            B = hi_lo[0].shape[0]
+        L = self.c_out // 2
+        if out is None:
+            out = torch.empty((B, self.H, self.W, L, 4), dtype=torch.float32, device=self.device)
+        hi, lo = hi_lo if hi_lo is not None else (None, None)
+        check(self.lib.msi_net_forward_rgba(self._h, ptr(psv), ptr(hi), ptr(lo), B, ptr(out), stream_ptr()),
+              "msi_net_forward_rgba")
+        return out
+
     def read_activation(self, scope, B=1):
         from .nets import layer_channels, layer_geometry
         ch = layer_channels(self.c_in, self.c_out, self.ngf)[scope]
@@ -166,8 +186,9 @@ class MSIPipeline:
       K1 msi_psv_gather     -> PSV as the net's fp16 hi/lo operand, written straight into the net input; the sample
                                coordinates come from the per-rig table (ops.sweep_table) -- ``static_rig=False``
                                evaluates them every frame instead (msi_psv_build: same bits)
-      K2 msi_net_forward    -> pred [B,H,W,n_pred] (pixel stride = the engine's padded head width)
-      K4 msi_rgba_assemble_strided -> RGBA layers [B,H,W,L,4]
+      K2 msi_net_forward_rgba -> RGBA layers [B,H,W,L,4] straight out of the head's epilogue (`blend_psv`, L = 32 / 64);
+         otherwise msi_net_forward -> pred [B,H,W,n_pred] (pixel stride = the engine's padded head width) and
+      K4 msi_rgba_assemble_strided -> RGBA layers
       K5 msi_render_composite -> rgb / depth (float32 + uint8)
     ``coord_net`` picks nets.msi_coord_train_net / nets.msi_train_net (FLAGS.coord_net, msi.py:120-127) and
     ``which_color_pred`` the head and assembly (msi.py:107-273), as MSI.infer_msi does.
@@ -176,7 +197,7 @@ class MSIPipeline:
     def __init__(self, weights, H=320, W=640, num_planes=32, ngf=64, batch=1, device="cuda",
                  min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16x3",
                  img_dtype=torch.float32, use_graph=True, coord_net=True, which_color_pred="blend_psv",
-                 static_rig=True):
+                 static_rig=True, fuse_rgba=True):
         _lib.require_cuda()
         from .msi import MSI
         self.device = torch.device(device)
@@ -206,6 +227,8 @@ class MSIPipeline:
             self.hi = torch.zeros((B, H, W, self.net.in_c_stride), dtype=torch.float16, device=dev)
             self.lo = torch.zeros_like(self.hi)
         self.psv_scratch = ops.psv_scratch(B, H, W, dev)
+        # `blend_psv` on the tensor-core back end: the head's epilogue assembles the RGBA layers (no `pred`, no K4 launch)
+        self.fused_rgba = bool(fuse_rgba and which_color_pred == "blend_psv" and self.net.can_fuse_rgba)
         # the engine's head may be wider than n_pred (padded for the kernels' channel tiling): K4 reads it in place
         self.pred_buf = torch.empty((B, H, W, self.net.c_out_eng), dtype=torch.float32, device=dev)
         self.pred = self.pred_buf[..., :self.n_pred]
@@ -225,7 +248,7 @@ class MSIPipeline:
         self.use_graph = use_graph
         self._graph = None
         self.gather = None   # FrameGather: the render kernel also stores its uint8 view into every rank's gathered buffer
-        self.launches_per_step = self.net.launches_per_forward + 3
+        self.launches_per_step = self.net.launches_per_forward + (3 if self.fused_rgba else 4)
 
     # -- device-resident step ---------------------------------------------------------------
     def _stages(self):
@@ -248,7 +271,10 @@ class MSIPipeline:
                   "msi_psv_build")
 
         def k2():
-            self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred_buf)
+            if self.fused_rgba:
+                self.net.forward_rgba(hi_lo=(self.hi, self.lo), out=self.rgba)
+            else:
+                self.net.forward(hi_lo=(self.hi, self.lo), out=self.pred_buf)
 
         def k4():
             check(lib.msi_rgba_assemble_strided(ptr(self.pred_buf), self.n_pred, self.net.c_out_eng, None, ptr(self.hi),
@@ -270,6 +296,8 @@ class MSIPipeline:
                     c_void_p(g.peers_dev), g.world, c_void_p(g.multicast_ptr) if g.multicast_ptr else None,
                     g.first_frame, stream_ptr()), "msi_render_composite_gather")
 
+        if self.fused_rgba:
+            return [("psv_build", k1), ("net", k2), ("render_composite", k5)]
         return [("psv_build", k1), ("net", k2), ("rgba_assemble", k4), ("render_composite", k5)]
 
     def sweep_table(self):

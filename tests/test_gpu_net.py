@@ -412,3 +412,77 @@ def test_cta_pair_kernel_matches_single_cta_kernel(monkeypatch, H, W, B):
     assert max(errs.values()) < 5e-5, errs
     if H * W >= 4 * 128:   # conv1_1 has several pixel tiles per frame, so it runs as pairs (different summation order)
         assert errs["conv1_1"] > 0.0, "the pair kernel was not selected (outputs are bit-identical)"
+
+
+@pytest.mark.parametrize("H,W,P,B,coord", [(64, 128, 32, 1, True), (24, 72, 32, 2, True), (32, 64, 64, 1, True),
+                                           (32, 64, 32, 1, False)])
+def test_head_fused_rgba_equals_forward_plus_assemble_bit_for_bit(H, W, P, B, coord):
+    """msi_net_forward_rgba (the head's epilogue assembles the RGBA layers, msi.py:130-147) against msi_net_forward +
+    msi_rgba_assemble on the same fp16 hi / lo PSV operand: same arithmetic in the same order, so the SAME BITS.
+    Cases: L = 32 (two pixels per warp iteration), a batch with ragged tiles (72 = 64 + 8 columns), L = 64 (N tile
+    128), and the wrap-padded input of msi_train_net (the PSV rows are stored 2 pixels wider on both sides)."""
+    ngf = 64
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (B, H, W, 6 * P)).astype(F32)
+    wts = synth.net_weights(6 * P, 2 * P, ngf, coord=coord)
+    eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, DEV, max_batch=B, variant="coord" if coord else "wrap")
+    assert eng.can_fuse_rgba
+    pred = eng.forward(_t(x)).clone()
+    cs = eng.in_c_stride
+    # the operand the net itself consumed: hi / lo split of the scaled input (dense copy; for the wrap variant the
+    # engine's own buffer is wrap-padded, so split the input again the same way)
+    xs = _t(x) * 16.0
+    hi = torch.zeros((B, H, W, cs), dtype=torch.float16, device=DEV)
+    lo = torch.zeros_like(hi)
+    hi[..., :6 * P] = xs.to(torch.float16)
+    lo[..., :6 * P] = (xs - hi[..., :6 * P].float()).to(torch.float16)
+    want, _, _ = ops.rgba_assemble(pred, None, hi_lo=(hi, lo), c_stride=cs)
+    got = eng.forward_rgba(_t(x))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), float((got - want).abs().max())
+    # and against the oracle's assembly of the oracle's prediction
+    with torch.no_grad():
+        fn = net_torch.msi_coord_train_net if coord else net_torch.msi_train_net
+        opred = fn(torch.from_numpy(x), 2 * P, wts, ngf=ngf).numpy()
+    orgba, _, _ = msi_np.assemble_rgba(opred, x, P)
+    assert float(np.abs(got.cpu().numpy() - orgba).max()) < TOL
+
+
+def test_pipeline_fused_head_equals_unfused_pipeline():
+    """MSIPipeline with the fused head (default) and with the separate K4 launch: identical frames."""
+    H, W, P, ngf = 64, 128, 32, 64
+    ref, src = synth.ods_pair(1, H, W, seed=77)
+    tp = synth.target_positions(1, 77)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    outs = []
+    for fuse in (True, False):
+        pipe = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, fuse_rgba=fuse)
+        assert pipe.fused_rgba == fuse
+        assert [n for n, _ in pipe._stages()] == (["psv_build", "net", "render_composite"] if fuse else
+                                                  ["psv_build", "net", "rgba_assemble", "render_composite"])
+        pipe.set_inputs(ref, src, tgt_pos=tp)
+        pipe.step()
+        pipe.step()
+        torch.cuda.synchronize()
+        outs.append((pipe.rgba.clone(), pipe.out["rgb"].clone(), pipe.out["rgb_u8"].clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_pipeline_static_rig_table_equals_per_frame_chain_and_follows_the_rig():
+    """static_rig=True (cached coordinate table, default) and False (the chain evaluated every frame) render the same
+    bits; changing the baseline through set_inputs rebuilds the table (and re-captures the graph)."""
+    H, W, P, ngf = 32, 64, 32, 64
+    ref, src = synth.ods_pair(1, H, W, seed=78)
+    tp = synth.target_positions(1, 78)
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    a = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, static_rig=True)
+    b = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, static_rig=False)
+    for base in (0.032, 0.05):
+        for pipe in (a, b):
+            pipe.set_inputs(ref, src, tgt_pos=tp, baselines=[base])
+            pipe.step()
+            pipe.step()
+        torch.cuda.synchronize()
+        assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+        assert torch.equal(a.out["rgb"], b.out["rgb"]) and torch.equal(a.out["depth_u8"], b.out["depth_u8"])
