@@ -35,6 +35,13 @@ import torch  # noqa: E402
 
 METRIC = "erp_frames_per_sec_640x320_32spheres"
 UNIT = "frames/s"
+MIN_WARMUP = 3   # timing rule: at least 3 warm-up steps (both arms report the warm-up they actually ran)
+REPEATS = 10     # the K-step timed region is repeated this many times inside one run; `value` is the median region
+
+
+def workload_string(W, H, P, batch, ngf):
+    """config.workload, the same string in both arms (the driver compares them)."""
+    return f"{W}x{H} ERP, {P}-sphere MSI, batch={batch}/GPU, ngf={ngf} (BASELINE.json configs[1])"
 
 
 def log(*a):
@@ -193,9 +200,9 @@ def oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, n_threads):
     return dict(net_input=net_input, rgba=rgba, view=view, depth=depth, u8=u8), (t1 - t0, t2 - t1)
 
 
-def oracle_frame_seconds(H, W, P, ngf, n_frames, seed=8964):
+def oracle_frame_seconds(H, W, P, ngf, n_frames, seed=8964, want_outputs=False):
     """Times the CPU oracle on n_frames full frames (PSV + net + assemble + view + depth render) with all host
-    cores.  Returns (seconds per frame list, per-stage seconds of the last frame)."""
+    cores.  Returns (seconds per frame list, per-stage seconds of the last frame[, the last frame's outputs])."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import msi_np
     from matryodshka_b200 import synth
@@ -205,13 +212,75 @@ def oracle_frame_seconds(H, W, P, ngf, n_frames, seed=8964):
     wts = synth.net_weights(6 * P, 2 * P, ngf, seed)
     tp = synth.target_positions(1, seed)
     planes = msi_np.inv_depths(1, 100, P)
-    times, stages = [], {}
+    times, stages, out = [], {}, None
     with ThreadPoolExecutor(max_workers=cores) as pool:
         for _ in range(n_frames):
-            _, (ta, tb) = oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, cores)
+            out, (ta, tb) = oracle_frame_threaded(ref, src, wts, tp, planes, P, ngf, pool, cores)
             times.append(ta + tb)
             stages = {"infer_msi_s": ta, "render_view_and_depth_s": tb}
+    if want_outputs:
+        out.update(tgt_pos=tp, planes=planes)
+        return times, stages, out
     return times, stages
+
+
+def parity_block(pipe, ora, H, W, P, dev):
+    """Parity of the bench frame against the oracle's frame (the cpu_baseline run), once per run, so that a kernel
+    change that widens the relaxed integer contract shows up in BENCH_r*.json and not only in a test threshold:
+    floor() flips of the sample-index grids (sweep table, render coordinates as the fused kernel evaluates them),
+    how many of them lie away from a knife edge (> 1e-3 px from an integer: must be 0), validity-mask mismatches,
+    uint8 mismatches of the rendered view / depth, and max-abs of the float RGBA layers and the float view."""
+    from oracle import geometry_np as g
+    from matryodshka_b200 import ops, synth
+    F = np.float32
+    planes = ora["planes"]
+    eye = np.eye(4, dtype=F)[None]
+
+    def flips(c_dev, c_ref):
+        bad = np.floor(c_dev) != np.floor(c_ref)
+        far = bad & (np.abs(c_ref - np.round(c_ref)) > 1e-3)
+        return int(bad.sum()), int(far.sum())
+
+    pipe.step()
+    torch.cuda.synchronize(dev)
+    out = {"frame": "the bench frame (lane 0, rank 0) vs the oracle port's frame of the cpu_baseline run"}
+    # K1: the cached table against project_ods of the oracle
+    S, T = g.lat_long_grid((H, W))
+    pts = g.backproject_spherical(S, T, F(planes))
+    tbl = pipe.sweep_table().table[0].cpu().numpy() if pipe.static_rig else None   # [H,W,P,4]
+    if tbl is not None:
+        n_bad = n_far = n_mask = 0
+        for e, order in enumerate((1, -1)):
+            ref_uv, aux = g.project_ods(pts, order, None, synth.intrinsics(1), W, H, return_aux=True)   # [P,H,W,2]
+            dev_uv = np.transpose(tbl[..., 2 * e:2 * e + 2], (2, 0, 1, 3))
+            ok = aux["valid"]
+            n_mask += int((np.all(dev_uv == 1.0, axis=-1) & ok).sum() + (~np.all(dev_uv[~ok] == 1.0, axis=-1)).sum())
+            for k in range(2):
+                a, b = flips(dev_uv[..., k][ok], ref_uv[..., k][ok])
+                n_bad, n_far = n_bad + a, n_far + b
+        out["sweep"] = {"samples": int(tbl.size // 2), "index_flips": n_bad, "index_flips_off_edge": n_far,
+                        "validity_mask_mismatches": n_mask}
+    # K5: the fused kernel's own (fast-chain) coordinates against intersect_sphere of the oracle
+    tp = np.asarray(ora["tgt_pos"], F)
+    uvf = ops.intersect_sphere_coords(eye, tp, planes, 1, H, W, dev, fast=True).cpu().numpy()[0]
+    ref_uv = g.intersect_sphere(eye[0], tp[0], F(planes), P, 1, W, H)
+    n_bad = n_far = 0
+    for k in range(2):
+        a, b = flips(uvf[..., k], ref_uv[..., k])
+        n_bad, n_far = n_bad + a, n_far + b
+    out["render"] = {"samples": int(uvf.size // 2), "index_flips": n_bad, "index_flips_off_edge": n_far,
+                     "max_abs_coord_px": float(np.abs(uvf - ref_uv).max())}
+    out["index_flips"] = n_bad + (out["sweep"]["index_flips"] if "sweep" in out else 0)
+    out["index_flips_off_edge"] = n_far + (out["sweep"]["index_flips_off_edge"] if "sweep" in out else 0)
+    v8, d8 = pipe.out["rgb_u8"].cpu().numpy(), pipe.out["depth_u8"].cpu().numpy()
+    out["u8_mismatches"] = int((v8 != ora["u8"][0]).sum() + (d8 != ora["u8"][1]).sum())
+    out["u8_values"] = int(v8.size + d8.size)
+    out["u8_max_abs"] = int(max(np.abs(v8.astype(int) - ora["u8"][0].astype(int)).max(),
+                                np.abs(d8.astype(int) - ora["u8"][1].astype(int)).max()))
+    out["max_abs_rgba"] = float(np.abs(pipe.rgba.cpu().numpy() - ora["rgba"]).max())
+    out["max_abs_view"] = float(np.abs(pipe.out["rgb"].cpu().numpy() - ora["view"]).max())
+    out["tolerance_float"] = 1e-3
+    return out
 
 
 def run_reference(args):
@@ -221,7 +290,10 @@ def run_reference(args):
     H, W, P, ngf = args.height, args.width, args.planes, args.ngf
     budget_s = 150.0
     t_start = time.perf_counter()
-    if args.warmup > 0:
+    # a CPU frame takes seconds: ONE warm-up frame (thread pools, allocator) stands for the requested warm-up and is
+    # what the line reports when it differs from --warmup
+    warm_frames = 1 if args.warmup > 0 else 0
+    for _ in range(warm_frames):
         oracle_frame_seconds(H, W, P, ngf, 1)
     times = []
     stages = {}
@@ -235,11 +307,14 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} ERP, {P}-sphere MSI, batch=1, ngf={ngf} (BASELINE.json configs[1])",
+        "config": {"workload": workload_string(W, H, P, 1, ngf),
+                   "warmup_frames_run": warm_frames, "steps_requested": args.steps,
                    "note": "oracle port of the reference path on host cores; the reference itself needs "
-                           "Python 2.7 + TensorFlow 1.14 and cannot run here"},
+                           "Python 2.7 + TensorFlow 1.14 and cannot run here.  A step = one full frame (seconds on a "
+                           "CPU): the run stops after the requested steps or ~150 s, whichever comes first, and one "
+                           "warm-up frame stands for the requested warm-up"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{len(times)} full frame(s): NumPy float32 geometry (planes / layers over {cores} threads) + "
                                    f"torch-CPU float32 conv net ({torch.get_num_threads()} threads); stages {stages}"},
@@ -272,7 +347,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     H, W, P, ngf, Bp = args.height, args.width, args.planes, args.ngf, args.batch
-    K, Wm = args.steps, max(args.warmup, 3)
+    K, Wm = args.steps, max(args.warmup, MIN_WARMUP)
     seed = 8964 + rank
     ref, src = synth.ods_pair(Bp, H, W, seed)
     wts = synth.net_weights(6 * P, 2 * P, ngf, 8964)
@@ -356,18 +431,21 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # ---- device-resident timed region: inputs already in HBM ------------------------------------
-    dev_ms = timed(K, one_step)
+    # EXACTLY K steps between the two events, barrier + synchronize on both sides; the region is repeated REPEATS
+    # times (a 20-step region is ~20 ms: one scheduling hiccup on one rank moves a single sample by percents) and
+    # the line reports the median region, with min / max beside it
+    dev_all = [timed(K, one_step) for _ in range(REPEATS)]
     if gathers:
         check_gathered()
     # the same K steps on ONE lane (one frame at a time), reported beside the headline for reference
-    single_ms = dev_ms
+    single_all = dev_all
     if n_lanes > 1:
         def lane0_step():
             with torch.cuda.stream(lanes.streams[0]):
                 pipe.step()
                 if gather is not None:
                     gather(pipe)
-        single_ms = timed(K, lane0_step)
+        single_all = [timed(K, lane0_step) for _ in range(max(3, REPEATS // 3))]
 
     # ---- end-to-end region: host (pinned) images in, host uint8 view + depth out ----------------
     # Every step copies its inputs host -> device from pinned memory and its results (uint8 view +
@@ -387,11 +465,13 @@ def run_ours(args):
         return last
 
     e2e_loop(2 * in_flight)
-    barrier()
-    t0 = time.perf_counter()
-    last = e2e_loop(K)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_all = []
+    for _ in range(REPEATS):
+        barrier()
+        t0 = time.perf_counter()
+        last = e2e_loop(K)
+        barrier()
+        e2e_all.append((time.perf_counter() - t0) * 1e3)
     assert torch.equal(last[0], pipe.out["rgb_u8"].cpu()), "e2e result differs from the device-resident result"
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) ---------------
@@ -403,10 +483,20 @@ def run_ours(args):
     stage_ms = None if args.no_layer_profile else pipe.stage_times(reps=5)
     clocks = sampler.stop() if rank == 0 else None
 
+    # max over ranks of every repeat (a region ends when the slowest rank ends), then the median repeat
+    per_rank = None
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms, single_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, single_ms = float(t[0]), float(t[1]), float(t[2])
+        def max_over_ranks(xs):
+            t = torch.tensor(xs, device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return [float(v) for v in t]
+        mine = torch.tensor([statistics.median(dev_all), statistics.median(e2e_all)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"device_ms_per_step": [round(float(a[0]) / K, 5) for a in allr],
+                    "e2e_ms_per_step": [round(float(a[1]) / K, 5) for a in allr]}
+        dev_all, e2e_all, single_all = max_over_ranks(dev_all), max_over_ranks(e2e_all), max_over_ranks(single_all)
+    dev_ms, e2e_ms, single_ms = statistics.median(dev_all), statistics.median(e2e_all), statistics.median(single_all)
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -443,26 +533,43 @@ def run_ours(args):
                     "render_composite": npx * 4 * P * 4 + 2 * npx * 3 * 4,
                     "rgba_assemble": npx * 2 * P * 4 + npx * 6 * P * 2 * s_out + npx * 4 * P * 4}
             hbm_peak = float(peaks["hbm_gbs"])
+            times_ms = dict(stage_ms)
+            if pipe.fused_rgba:
+                # K4 lives in the head's epilogue: the head launch reads conv8_2 (hi + lo, as many bytes as `pred`) and
+                # the PSV and writes the RGBA layers -- the bytes of SURVEY 8d's K4 -- timed as the color_pred launch
+                times_ms["rgba_assemble"] = float(conv_ms[list(scopes).index("color_pred")])
             roofline["hbm_kernels"] = {
-                k: {"ms": stage_ms[k], "algorithmic_bytes": algo[k], "achieved_gbs": algo[k] / (stage_ms[k] * 1e-3) / 1e9,
-                    "frac": algo[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak} for k in algo}
-            wc = (algo["psv_build"] + algo["render_composite"]) / ((stage_ms["psv_build"] + stage_ms["render_composite"]) * 1e-3) / 1e9
+                k: {"ms": times_ms[k], "algorithmic_bytes": algo[k], "achieved_gbs": algo[k] / (times_ms[k] * 1e-3) / 1e9,
+                    "frac": algo[k] / (times_ms[k] * 1e-3) / 1e9 / hbm_peak} for k in algo}
+            hk = roofline["hbm_kernels"]
+            if pipe.fused_rgba:
+                hk["rgba_assemble"]["kernel"] = "fused into the color_pred head epilogue (msi_net_forward_rgba): no separate launch"
+            if pipe.static_rig:
+                # what the gather really moves: the cached coordinate table is read once per frame on top of the
+                # algorithmic bytes (16 B per (pixel, plane)); reported so that `frac` is not mistaken for DRAM idleness
+                tbl = npx * P * 16
+                hk["psv_build"]["kernel"] = "prep_images + psv_gather_pair (coordinates from the per-rig table, ops.sweep_table)"
+                hk["psv_build"]["bytes_moved_incl_table"] = algo["psv_build"] + tbl
+                hk["psv_build"]["dram_frac_incl_table"] = (algo["psv_build"] + tbl) / (times_ms["psv_build"] * 1e-3) / 1e9 / hbm_peak
+            wc = (algo["psv_build"] + algo["render_composite"]) / ((times_ms["psv_build"] + times_ms["render_composite"]) * 1e-3) / 1e9
             roofline["warp_plus_composite"] = {"bound": "hbm", "achieved": wc, "peak": hbm_peak, "unit": "GB/s",
                                                "frac": wc / hbm_peak,
-                                               "note": "K1 + K5 are instruction-issue bound (82 % issue-slot utilisation, "
-                                                       "profiles/r1_v6_geom_ncu_full_summary.csv): the reference's float32 "
-                                                       "coordinate chain is evaluated op for op (IEEE div / sqrt, no FMA) so "
-                                                       "that the validity mask and the sample-index grid match it"}
+                                               "note": "K1 gathers from a cached per-rig coordinate table (bits identical to the "
+                                                       "per-frame chain) and is bound by load latency / L1 throughput; K5 evaluates "
+                                                       "its per-frame coordinates with a fast chain and is instruction-issue bound "
+                                                       "(profiles/r2_geom_ncu_full_summary.csv)"}
             roofline["net_ms_per_step"] = stage_ms["net"]
         if args.no_layer_profile:
             roofline = None
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            times, stages = oracle_frame_seconds(H, W, P, ngf, 1)
+            times, stages, ora = oracle_frame_seconds(H, W, P, ngf, 1, want_outputs=True)
             cpu = {"value": 1.0 / times[0], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"1 full frame of the same workload through the oracle port: NumPy float32 geometry "
                              f"(planes / layers over {os.cpu_count() or 1} threads) + torch-CPU float32 net "
                              f"({torch.get_num_threads()} threads); {stages}"}
+            if Bp == 1:   # (the oracle frame is frame 0 of a batch-1 run of the same seed)
+                parity = parity_block(pipe, ora, H, W, P, dev)
         ws_gb = (pipe.net.ws_bytes + pipe.rgba.numel() * 4) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -470,8 +577,14 @@ def run_ours(args):
             "dtype": "f16x3-split operands, f32 accumulate" if mma_mult == 3.0 else
                      ("f16 operands, f32 accumulate" if args.conv_impl == "tcgen05" else "f32"),
             "data": "synthetic",
-            "config": {"workload": f"{W}x{H} ERP, {P}-sphere MSI, batch={Bp}/GPU, ngf={ngf} (BASELINE.json configs[1])",
+            "config": {"workload": workload_string(W, H, P, Bp, ngf),
                        "frames_per_step": world * Bp, "conv_impl": args.conv_impl, "precision": args.precision,
+                       "timed_regions": {"repeats": REPEATS, "steps_each": K, "statistic": "median (max over ranks per repeat)",
+                                         "device_ms_per_step_min_med_max": [min(dev_all) / K, dev_ms / K, max(dev_all) / K],
+                                         "e2e_ms_per_step_min_med_max": [min(e2e_all) / K, e2e_ms / K, max(e2e_all) / K],
+                                         "per_rank_median": per_rank},
+                       "sweep_coordinates": "cached per-rig table (static rig)" if pipe.static_rig else "evaluated per frame",
+                       "rgba_assembly": "fused into the head epilogue" if pipe.fused_rgba else "separate kernel",
                        "cuda_graph": not args.no_graph, "frames_in_flight": n_lanes,
                        "one_frame_at_a_time": {"value": frames / (single_ms * 1e-3), "unit": UNIT,
                                                "ms_per_step": single_ms / K},
@@ -485,6 +598,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         emit(line)
     if world > 1:

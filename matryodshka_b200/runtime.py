@@ -369,8 +369,12 @@ class MSIPipeline:
         self._graph.replay()
 
     def set_inputs(self, ref, src, tgt_pos=None, baselines=None):
-        self.ref.copy_(torch.as_tensor(ref).to(self.ref.dtype), non_blocking=True)
-        self.src.copy_(torch.as_tensor(src).to(self.src.dtype), non_blocking=True)
+        ref, src = torch.as_tensor(ref), torch.as_tensor(src)
+        if self.img_dtype == torch.uint8 and (ref.is_floating_point() or src.is_floating_point()):
+            raise _lib.MsiError("set_inputs: this pipeline takes uint8 images; a float [0, 1] image would be truncated "
+                                "to 0 / 1 by the cast (build the pipeline with img_dtype=torch.float32)")
+        self.ref.copy_(ref.to(self.ref.dtype), non_blocking=True)
+        self.src.copy_(src.to(self.src.dtype), non_blocking=True)
         if tgt_pos is not None:
             self.tgt_pos.copy_(torch.as_tensor(tgt_pos, dtype=torch.float32))
         if baselines is not None:
@@ -405,6 +409,10 @@ class MSIPipeline:
                             torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)) for _ in range(depth)]
         self._h_out = [(torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
                         torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()) for _ in range(depth)]
+        # pinned staging for pageable inputs, one pair per slot: the H2D copy out of it is asynchronous, so a
+        # single pair would let the host overwrite batch i's pixels with batch i+1's while the DMA still reads them
+        self._h_in = [(torch.empty((B, H, W, 3), dtype=dt).pin_memory(), torch.empty((B, H, W, 3), dtype=dt).pin_memory())
+                      for _ in range(depth)]
         mk = lambda: [torch.cuda.Event() for _ in range(depth)]
         self._ev_h2d, self._ev_in_free, self._ev_done, self._ev_d2h = mk(), mk(), mk(), mk()
         self._submitted = 0
@@ -423,12 +431,15 @@ class MSIPipeline:
         k = self._submitted % self._depth
         cur = torch.cuda.current_stream(self.device)
         ref_host, src_host = torch.as_tensor(ref_host), torch.as_tensor(src_host)
-        if not ref_host.is_pinned():
-            self.h_ref.copy_(ref_host)
-            ref_host = self.h_ref
-        if not src_host.is_pinned():
-            self.h_src.copy_(src_host)
-            src_host = self.h_src
+        if not (ref_host.is_pinned() and src_host.is_pinned()):
+            self._ev_h2d[k].synchronize()   # the previous H2D out of this slot's staging pair has finished
+            h_ref, h_src = self._h_in[k]
+            if not ref_host.is_pinned():
+                h_ref.copy_(ref_host)
+                ref_host = h_ref
+            if not src_host.is_pinned():
+                h_src.copy_(src_host)
+                src_host = h_src
         in_ref, in_src = self._in_stage[k]
         with torch.cuda.stream(self._copy_s):
             self._copy_s.wait_event(self._ev_in_free[k])      # compute has consumed this staging slot

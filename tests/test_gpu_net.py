@@ -486,3 +486,30 @@ def test_pipeline_static_rig_table_equals_per_frame_chain_and_follows_the_rig():
         torch.cuda.synchronize()
         assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
         assert torch.equal(a.out["rgb"], b.out["rgb"]) and torch.equal(a.out["depth_u8"], b.out["depth_u8"])
+
+
+def test_submit_pageable_batches_back_to_back():
+    """`depth` pageable (un-pinned) batches submitted back to back, no collect in between: every batch is staged
+    through its own pinned buffer pair, so the asynchronous H2D copy of batch i never reads pixels of batch i + 1.
+    The pattern s0 s1 c0 c1 s2 s3 c2 c3 is repeated at a frame size whose copy takes long enough to expose a race."""
+    H, W, P, ngf = 64, 128, 32, 64
+    wts = synth.net_weights(6 * P, 2 * P, ngf)
+    pipe = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV)
+    frames = [synth.ods_pair(1, H, W, seed=300 + i) for i in range(6)]
+    want = []
+    for ref, src in frames:
+        pipe.set_inputs(ref, src)
+        pipe.step()
+        torch.cuda.synchronize()
+        want.append(pipe.out["rgb_u8"].cpu().clone())
+    got = []
+    for i in range(0, 6, 2):
+        pipe.submit(frames[i][0].copy(), frames[i][1].copy())
+        pipe.submit(frames[i + 1][0].copy(), frames[i + 1][1].copy())
+        got.append(pipe.collect()[0].clone())
+        got.append(pipe.collect()[0].clone())
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    with pytest.raises(Exception):
+        u8 = MSIPipeline(wts, H, W, P, ngf, batch=1, device=DEV, img_dtype=torch.uint8)
+        u8.set_inputs(frames[0][0], frames[0][1])   # float images into a uint8 pipeline
