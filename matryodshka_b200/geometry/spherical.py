@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from .. import torch_ops  # noqa: F401  (registers torch.ops.msi.*)
 
 
 def lat_long_grid(shape, epsilon=1.0e-12, device="cuda"):
@@ -21,9 +22,8 @@ def intersect_sphere(pos, center, radius, num_planes, num_batch, width, height, 
     """spherical.py:268-326 -> uv [L, H, W, 2]: where the target-view ray of every ERP pixel
     hits each sphere, in source pixel coordinates.  pos [4,4], center [3], radius [L]."""
     dev = radius.device if torch.is_tensor(radius) else (pos.device if torch.is_tensor(pos) else "cuda")
-    pos = torch.as_tensor(pos, dtype=torch.float32).reshape(1, 4, 4)
-    center = torch.as_tensor(center, dtype=torch.float32).reshape(1, 3)
-    uv = ops.intersect_sphere_coords(pos, center, radius, 1, height, width, dev)
+    uv = torch.ops.msi.intersect_sphere_coords(ops._dev_f32(pos, dev, (1, 16)), ops._dev_f32(center, dev, (1, 3)),
+                                               ops._dev_f32(radius, dev, (-1,)), height, width, False)
     return uv[0]
 
 

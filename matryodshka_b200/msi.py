@@ -22,12 +22,16 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .runtime import NetEngine
+from . import torch_ops  # noqa: F401  (registers torch.ops.msi.*)
+from .runtime import NetEngine, nvtx_range
 
 
 @dataclass(frozen=True)
 class MSIConfig:
-    """The reference's flags for this path, same names and defaults (test.py:39-83, loader.py:30-42)."""
+    """The reference's flags for this path, same names (test.py:39-83, loader.py:30-42) and the same defaults
+    EXCEPT ``coord_net``: the reference defaults to False (test.py:52) while its released model and BASELINE's
+    configs are the coord net (``--coord_net``), which is the default here.  ``MSI`` checks the choice against the
+    shape of the conv1_1 weights it is given and refuses a mismatch."""
     height: int = 320
     width: int = 640
     num_psv_planes: int = 32
@@ -67,6 +71,11 @@ def _host(x):
     return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
 
 
+def _dev(x, device, shape=None):
+    """Host array / tensor -> contiguous float32 tensor on ``device`` (the custom ops take tensors only)."""
+    return ops._dev_f32(x, device, shape)
+
+
 class MSI(object):
     """Multi-sphere-image inference (reference class ``MSI``, msi.py:33)."""
 
@@ -75,6 +84,16 @@ class MSI(object):
         self.weights = weights
         self.device = torch.device(device)
         self._engines = {}
+
+    def load_weights(self, weights):
+        """``MSI()`` as the reference constructs it (no arguments), weights attached afterwards: a dict keyed by the
+        TF variable names, or the prefix of a TensorFlow checkpoint (what ``saver.restore`` takes, test.py:192-202)."""
+        if isinstance(weights, (str, bytes)):
+            from .tf_checkpoint import load_checkpoint
+            weights = {k: v for k, v in load_checkpoint(weights).items() if k.startswith("net/")}
+        self.weights = weights
+        self._engines = {}
+        return self
 
     # ---- msi.py:1196-1217 ------------------------------------------------------------------
     def inv_depths(self, start_depth, end_depth, num_depths):
@@ -124,7 +143,9 @@ class MSI(object):
         eye*3P + p*3 + rgb, eye 0 = ref (order +1), eye 1 = src (order -1)."""
         poses = self._sweep_poses(ref_pose, src_pose, ref_pose_inv, jitter_pose_inv)
         baselines = _host(intrinsics).astype(np.float32).reshape(-1, 3, 3)[:, 0, 0]
-        return ops.psv_build(ref_image, src_image, poses, baselines, list(planes), preprocess=False)
+        dev = ref_image.device
+        return torch.ops.msi.psv_build(ref_image, src_image, _dev(poses, dev), _dev(baselines, dev),
+                                       _dev(list(planes), dev), False)
 
     def sweep_src(self, image, order, depths, pose, intrinsics):
         from .geometry import projector as pj
@@ -134,9 +155,21 @@ class MSI(object):
     def _engine(self, H, W, c_in, c_out, ngf, max_batch):
         key = (H, W, c_in, c_out, ngf, max_batch)
         eng = self._engines.get(key)
+        if eng is None:   # an engine built for a larger batch serves a smaller one
+            for k2, e2 in self._engines.items():
+                if k2[:5] == key[:5] and k2[5] >= max_batch:
+                    eng = e2
+                    break
         if eng is None:
             if self.weights is None:
-                raise _lib.MsiError("MSI.infer_msi needs weights (MSI(weights=...))")
+                raise _lib.MsiError("MSI.infer_msi needs weights (MSI(weights=...) or MSI().load_weights(...))")
+            w0 = self.weights.get("net/conv1_1/weights")
+            if w0 is not None and tuple(w0.shape)[2] != c_in + (1 if self.config.coord_net else 0):
+                raise _lib.MsiError(
+                    "MSIConfig.coord_net=%s but net/conv1_1/weights has %d input channels for a %d-channel PSV (%s): "
+                    "set MSIConfig(coord_net=%s)" % (self.config.coord_net, tuple(w0.shape)[2], c_in,
+                                                     "coord net" if tuple(w0.shape)[2] == c_in + 1 else "msi_train_net",
+                                                     tuple(w0.shape)[2] == c_in + 1))
             # FLAGS.coord_net picks nets.msi_coord_train_net or nets.msi_train_net (msi.py:120-127)
             eng = NetEngine(self.weights, H, W, c_in, c_out, ngf, self.device, max_batch=max_batch,
                             conv_impl=self.config.conv_impl, precision=self.config.precision,
@@ -171,13 +204,15 @@ class MSI(object):
         # preprocessing (msi.py:73-75) is fused into the sweep kernel
         # a static rig (every frame of the reference's data: identity eye poses, one baseline) gathers from the
         # cached coordinate table; the jittered sweep evaluates the chain per call.  Same bits either way.
-        net_input = ops.psv_build(raw_ref_image, raw_src_image, poses, baselines, list(psv_planes),
-                                  preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride,
-                                  cache_coords=jitter_pose_inv is None)
+        with nvtx_range("psv_build"):
+            net_input = ops.psv_build(raw_ref_image, raw_src_image, poses, baselines, list(psv_planes),
+                                      preprocess=True, want_f32=True, hi_lo=(hi, lo), c_stride=eng.in_c_stride,
+                                      cache_coords=jitter_pose_inv is None)
         if cfg.net_only:
             eng.forward(hi_lo=(hi, lo))
             return None
-        msi_pred = eng.forward(hi_lo=(hi, lo))
+        with nvtx_range("net"):
+            msi_pred = eng.forward(hi_lo=(hi, lo))
         want_w = ('blend_weights' in extra_outputs) or ('alpha' in extra_outputs)
         bgw = None
         if which_color_pred == 'blend_psv':
@@ -199,22 +234,32 @@ class MSI(object):
     # ---- msi.py:384-452 ------------------------------------------------------------------------
     def msi_render_equirect_view(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
         """Rendered view [B,H,W,3] in [-1,1]."""
-        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes), want_rgb=True,
-                                    want_depth=False, want_u8=False)["rgb"]
+        return self._render(rgba_layers, tgt_pose_rt, tgt_pos, planes)[0]
 
     def msi_render_equirect_depth(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
         """Composited normalised layer index [B,H,W,3] in [0,1)."""
-        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes), want_rgb=False,
-                                    want_depth=True, want_u8=False)["depth"]
+        return self._render(rgba_layers, tgt_pose_rt, tgt_pos, planes)[1]
+
+    @staticmethod
+    def _render(rgba_layers, tgt_pose_rt, tgt_pos, planes):
+        """torch.ops.msi.render_composite: (rgb, depth, rgb_u8, depth_u8) from ONE reprojection."""
+        dev = rgba_layers.device
+        B = rgba_layers.shape[0]
+        return torch.ops.msi.render_composite(rgba_layers.contiguous(), _dev(tgt_pose_rt, dev, (B, 16)),
+                                              _dev(tgt_pos, dev, (B, 3)), _dev(list(planes), dev))
 
     def msi_render_equirect(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
         """Ours: colour and depth (float32 + deprocessed uint8) from ONE reprojection."""
-        return ops.render_composite(rgba_layers, tgt_pose_rt, tgt_pos, list(planes))
+        rgb, depth, rgb_u8, depth_u8 = self._render(rgba_layers, tgt_pose_rt, tgt_pos, planes)
+        return {"rgb": rgb, "depth": depth, "rgb_u8": rgb_u8, "depth_u8": depth_u8}
 
     def msi_render_equirect_view_single(self, rgba_layers, tgt_pose_rt, tgt_pos, planes, intrinsics=None):
         """Reprojected layers without compositing [L,B,H,W,4] (msi.py:431-452)."""
         planes = planes.tolist() if torch.is_tensor(planes) else list(planes)
-        return ops.project_layers(rgba_layers, tgt_pose_rt, tgt_pos, planes)
+        dev = rgba_layers.device
+        B = rgba_layers.shape[0]
+        return torch.ops.msi.project_layers(rgba_layers.contiguous(), _dev(tgt_pose_rt, dev, (B, 16)),
+                                            _dev(tgt_pos, dev, (B, 3)), _dev(planes, dev))
 
     msi_render_equirect_depth_single = msi_render_equirect_view_single
 

@@ -120,8 +120,8 @@ def msi_coord_train_net(inputs, num_outputs, ngf=64, vscope="net", reuse_weights
         if weights is None:
             raise ValueError("msi_coord_train_net needs weights= (TF-named dict) or engine=")
         B, H, W, C = inputs.shape
-        engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope)
-    return engine.forward(inputs)
+        engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope, max_batch=B)
+    return _forward_op(engine, inputs)
 
 
 def msi_train_net(inputs, num_outputs, ngf=64, vscope="net", reuse_weights=False, *, weights=None, engine=None):
@@ -135,5 +135,14 @@ def msi_train_net(inputs, num_outputs, ngf=64, vscope="net", reuse_weights=False
         if weights is None:
             raise ValueError("msi_train_net needs weights= (TF-named dict) or engine=")
         B, H, W, C = inputs.shape
-        engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope, variant="wrap")
-    return engine.forward(inputs)
+        engine = NetEngine.cached(weights, H, W, C, num_outputs, ngf, inputs.device, vscope=vscope, max_batch=B, variant="wrap")
+    return _forward_op(engine, inputs)
+
+
+def _forward_op(engine, inputs):
+    """torch.ops.msi.net_forward on the engine's dispatcher handle."""
+    import torch
+    from . import torch_ops
+    if getattr(engine, "_op_handle", None) is None:
+        engine._op_handle = torch_ops.register_engine(engine)
+    return torch.ops.msi.net_forward(inputs.contiguous().float(), engine._op_handle)

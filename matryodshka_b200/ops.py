@@ -63,6 +63,7 @@ def erp_tables(H, W, device) -> ErpTables:
 
 def _dev_f32(x, device, shape=None):
     """Small host array / tensor -> contiguous float32 CUDA tensor."""
+    _lib.require_cuda()   # (the mirror API reaches the kernels through torch.ops.msi.*: fail with our own message first)
     if torch.is_tensor(x):
         t = x.to(device=device, dtype=torch.float32)
     else:

@@ -25,6 +25,27 @@ _PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16}
 _VARIANT = {"coord": _lib.NET_COORD, "wrap": _lib.NET_WRAP}
 
 
+class nvtx_range:
+    """NVTX range around one stage of the path (visible in Nsight Systems / ncu --nvtx; SURVEY.md 5 tracing row).
+    Host-side markers only: they cost ~1 us and are harmless inside a CUDA-graph capture."""
+
+    def __init__(self, name):
+        self.name = "msi/" + name
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+            self._on = True
+        except Exception:   # NVTX library unavailable: tracing is optional
+            self._on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self._on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _host_f32(x):
     return x.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(x) else np.asarray(x, np.float32)
 
@@ -73,13 +94,36 @@ class NetEngine:
             self.load_weights(weights, vscope)
         self.launches_per_forward = int(self.lib.msi_net_num_launches_per_forward(self._h))
 
+    _cache_max = 4   # every engine pins a workspace + arena (about 1 GB per frame of max_batch at 320 x 640)
+
+    @staticmethod
+    def _fingerprint(weights):
+        """Cheap content key of a weights dict: names, shapes and a strided sample of every array.  (Keying on
+        ``id(weights)`` would hand out stale packed weights after an in-place reload, or after CPython recycles the id.)"""
+        items = []
+        for name in sorted(weights):
+            w = weights[name]
+            a = w.detach().reshape(-1) if torch.is_tensor(w) else np.asarray(w).reshape(-1)
+            step = max(1, a.shape[0] // 256)
+            samp = a[::step][:256]
+            samp = samp.float().cpu().numpy() if torch.is_tensor(samp) else np.asarray(samp, np.float32)
+            items.append((name, tuple(w.shape), samp.tobytes()))
+        return hash(tuple(items))
+
     @classmethod
-    def cached(cls, weights, H, W, c_in, c_out, ngf, device, vscope="net", **kw):
-        key = (id(weights), H, W, c_in, c_out, ngf, str(device), vscope, tuple(sorted(kw.items())))
-        eng = cls._cache.get(key)
-        if eng is None:
-            eng = cls(weights, H, W, c_in, c_out, ngf, device, vscope=vscope, **kw)
-            cls._cache[key] = eng
+    def cached(cls, weights, H, W, c_in, c_out, ngf, device, vscope="net", max_batch=1, **kw):
+        """An engine for these weights and this shape out of a small LRU cache; an engine built for a larger batch is
+        reused for any smaller one."""
+        base = (cls._fingerprint(weights), H, W, c_in, c_out, ngf, str(device), vscope, tuple(sorted(kw.items())))
+        for key in list(cls._cache):
+            if key[:-1] == base and key[-1] >= max_batch:
+                eng = cls._cache.pop(key)
+                cls._cache[key] = eng          # most recently used last
+                return eng
+        eng = cls(weights, H, W, c_in, c_out, ngf, device, vscope=vscope, max_batch=max_batch, **kw)
+        while len(cls._cache) >= cls._cache_max:
+            cls._cache.pop(next(iter(cls._cache)))
+        cls._cache[base + (max_batch,)] = eng
         return eng
 
     def load_weights(self, weights, vscope="net"):
@@ -323,8 +367,9 @@ class MSIPipeline:
         self._graph = None
 
     def _enqueue(self):
-        for _, fn in self._stages():
-            fn()
+        for name, fn in self._stages():
+            with nvtx_range(name):
+                fn()
 
     def stage_times(self, reps=5):
         """Milliseconds per launch of each stage, timed alone on the current stream: ``reps`` back-to-back

@@ -183,6 +183,14 @@ def main(argv=None):
     if flags.gcn or flags.input_type != "ODS" or kinds:
         raise SystemExit("only the ODS inference path is built (test_type: on_video, high_res, high_res_only concatenated "
                          "with _; no gcn / PP)")
+    # flags the reference's test.py accepts that change its outputs and that this driver does not implement: refuse them
+    # rather than exit 0 with files missing (test.py:141-146,160-165: jitter_output_*, jitter_msi_*; export-only flags)
+    unbuilt = [n for n in ("transform_inverse_reg", "jitter", "smoothed", "net_only") if getattr(flags, n)]
+    if unbuilt:
+        raise SystemExit("not built in this driver: --" + ", --".join(unbuilt) + " (the jittered sweep itself is available "
+                         "through MSI.infer_msi(jitter_pose_inv=...))")
+    if flags.rot_factor != 1.0 or flags.tr_factor != 1.0:
+        raise SystemExit("--rot_factor / --tr_factor only scale the training-time jitter; not built in this driver")
     import torch
     from matryodshka_b200.msi import MSI, MSIConfig
 
@@ -237,6 +245,18 @@ def main(argv=None):
             write_image(output_dir + "/tgt_image_%s.png" % dirname, imgs[2] * 255.0)
             write_image(output_dir + "/output_tgt_%s.png" % dirname, r["rgb_u8"][0].cpu().numpy())
             write_image(output_dir + "/output_depth_%s.png" % dirname, r["depth_u8"][0].cpu().numpy())
+        rgba_layers, tgt_pos1 = outs["rgba_layers"], s["tgt_pos"][None]
+        if "ref_output_image" in to:    # test.py:179-187,240-241: the MSI seen from the reference (left) ODS eye
+            v = model.deprocess_image(model.msi_render_ods_view(rgba_layers, 1, eye, tgt_pos1, msi_planes, intrinsics))
+            write_image(output_dir + "/output_ref_%s.png" % dirname, v[0].cpu().numpy())
+        if "src_output_image" in to:    # test.py:171-178,242-243
+            v = model.deprocess_image(model.msi_render_ods_view(rgba_layers, -1, eye, tgt_pos1, msi_planes, intrinsics))
+            write_image(output_dir + "/output_src_%s.png" % dirname, v[0].cpu().numpy())
+        if "psp" in to:                 # test.py:161-170,245-249: four perspective crops
+            for vw in range(4):
+                v = model.deprocess_image(model.msi_render_perspective_view(rgba_layers, eye, tgt_pos1, msi_planes, intrinsics,
+                                                                            viewing_window=vw))
+                write_image(output_dir + "/output_ptgt%d_%s.png" % (vw, dirname), v[0].cpu().numpy())
         if "src_image" in to:
             write_image(output_dir + "/src_image_%s.png" % dirname, imgs[1] * 255.0)
         if "ref_image" in to:

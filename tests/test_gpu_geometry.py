@@ -218,10 +218,16 @@ def test_alpha_one_shows_nearest_layer_and_project_layers():
     want = msi_np.msi_render_equirect_view_single(rgba, eye, tp, d)
     assert np.abs(proj.cpu().numpy() - want).max() < TOL
     out = m.msi_render_equirect_view(_t(rgba), eye, tp, d).cpu().numpy()
-    assert np.abs(out - proj[L - 1, ..., :3].cpu().numpy()).max() < 1e-6
+    # (project_layers evaluates the strict coordinate chain, the fused render its fast chain: ~1e-5 px apart)
+    assert np.abs(out - proj[L - 1, ..., :3].cpu().numpy()).max() < 1e-5
     from matryodshka_b200.geometry import projector as pj
     comp = pj.over_composite([proj[l] for l in range(L)]).cpu().numpy()
-    assert np.array_equal(comp, out)  # same recurrence order in both kernels
+    assert np.abs(comp - out).max() < 1e-5
+    # same recurrence order in both kernels: from the SAME projected layers the composite is bit-identical
+    rgba2 = _smooth_layers(1, H, W, L, 9)
+    proj2 = m.msi_render_equirect_view_single(_t(rgba2), eye, np.zeros((1, 3), F32), d)
+    assert np.array_equal(pj.over_composite([proj2[l] for l in range(L)]).cpu().numpy(),
+                          ops.over_composite(proj2.contiguous()).cpu().numpy())
 
 
 def test_resample_wraps_like_the_oracle():

@@ -223,3 +223,48 @@ def test_threaded_cpu_arm_equals_the_oracle_bit_for_bit():
     assert np.array_equal(got["view"], msi_np.msi_render_equirect_view(out["rgba_layers"], e4, tp, planes))
     assert np.array_equal(got["depth"], msi_np.msi_render_equirect_depth(out["rgba_layers"], e4, tp, planes))
     assert bench._chunks(32, 16) == [(2 * i, 2 * i + 2) for i in range(16)] and bench._chunks(3, 8) == [(0, 1), (1, 2), (2, 3)]
+
+
+def test_torch_library_ops_are_registered_with_fake_impls():
+    """torch.ops.msi.* (SURVEY.md 8b): every op is registered, infers shapes on meta tensors without touching the CUDA
+    library, and has NO CPU kernel (the dispatcher refuses CPU tensors: no fallback)."""
+    import torch
+    from matryodshka_b200 import torch_ops
+    for name in torch_ops.OP_NAMES:
+        assert hasattr(torch.ops.msi, name), name
+    m = lambda *s, dt=torch.float32: torch.empty(s, device="meta", dtype=dt)  # noqa: E731
+    B, H, W, P = 2, 8, 16, 4
+    psv = torch.ops.msi.psv_build(m(B, H, W, 3), m(B, H, W, 3), m(B, 2, 16), m(B), m(P), True)
+    assert psv.shape == (B, H, W, 6 * P) and psv.device.type == "meta"
+    table = torch.ops.msi.sweep_table(m(1, 2, 16), m(1), m(P), H, W)
+    assert table.shape == (1, H, W, P, 4)
+    assert torch.ops.msi.psv_gather(m(B, H, W, 3, dt=torch.uint8), m(B, H, W, 3, dt=torch.uint8), table, True).shape == psv.shape
+    rgba, bw, al, bgw = torch.ops.msi.rgba_assemble(m(B, H, W, 3 * P + 3), psv, 2, P)
+    assert rgba.shape == (B, H, W, P, 4) and bw.shape == al.shape == bgw.shape == (B, H, W, P)
+    rgb, depth, rgb8, dep8 = torch.ops.msi.render_composite(rgba, m(B, 16), m(B, 3), m(P))
+    assert rgb.shape == (B, H, W, 3) and rgb8.dtype == torch.uint8 and depth.dtype == torch.float32
+    assert torch.ops.msi.project_layers(rgba, m(B, 16), m(B, 3), m(P)).shape == (P, B, H, W, 4)
+    assert torch.ops.msi.intersect_sphere_coords(m(B, 16), m(B, 3), m(P), H, W, True).shape == (B, P, H, W, 2)
+    assert torch.ops.msi.resample(m(3, H, W, 5), m(3, 2, 7, 2)).shape == (3, 2, 7, 5)
+    assert torch.ops.msi.over_composite(m(P, B, H, W, 4), True).shape == (B, H, W, 3)
+    with pytest.raises(NotImplementedError):
+        torch.ops.msi.over_composite(torch.zeros(2, 1, 4, 4, 4), False)
+
+
+def test_reference_module_names_resolve():
+    """`from matryodshka.msi import MSI` / `import geometry.projector as pj` (reference test.py:27, msi.py:26-31)."""
+    from matryodshka.msi import MSI
+    from matryodshka import nets
+    import geometry.projector as pj
+    import geometry.sampling as sampling
+    import geometry.spherical as spherical
+    from matryodshka_b200.msi import MSI as Ours
+    assert MSI is Ours and MSI().inv_depths(1, 100, 32)[1] == pytest.approx(23.846153846153847)
+    for mod, names in ((pj, ["ods_sphere_sweep", "sweep_one", "projective_forward_sphere", "over_composite",
+                             "over_composite_depth", "apply_pose"]),
+                       (sampling, ["bilinear_wrapper2", "resample"]),
+                       (spherical, ["lat_long_grid", "backproject_spherical", "project_ods", "project_spherical",
+                                    "intersect_sphere", "theta_phi_to_pixels"]),
+                       (nets, ["msi_coord_train_net", "msi_train_net"])):
+        for n in names:
+            assert callable(getattr(mod, n)), (mod.__name__, n)
