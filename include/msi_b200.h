@@ -378,6 +378,13 @@ int msi_net_num_launches_per_forward(const msi_net* net);
  * (2 x MACs, coord channels counted: SURVEY.md 8a a10 table). */
 int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
                              int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host);
+/* Same, with two options: `flush` (device buffer larger than the L2, or NULL) is overwritten before every timed
+ * launch and each launch gets its own event pair, so the durations are cold-L2 (inputs come from HBM, as in the frame
+ * for every tensor larger than the L2); `rgba` (or NULL) runs the head with the fused RGBA assembly
+ * (msi_net_forward_rgba), `pred` is then unused and may be NULL. */
+int msi_net_forward_profiled_flush(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
+                                   int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host,
+                                   void* flush, size_t flush_bytes, float* rgba);
 int msi_net_num_layers(const msi_net* net);
 const char* msi_net_layer_scope(const msi_net* net, int i);
 double msi_net_layer_flops(const msi_net* net, int i);

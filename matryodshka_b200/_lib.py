@@ -68,6 +68,8 @@ SIGNATURES = {
     "msi_net_read_raw": (c_int, [_P, c_char_p, _I, _P, _P]),
     "msi_net_num_launches_per_forward": (c_int, [_P]),
     "msi_net_forward_profiled": (c_int, [_P, _P, _P, _P, _I, _P, _P, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "msi_net_forward_profiled_flush": (c_int, [_P, _P, _P, _P, _I, _P, _P, POINTER(ctypes.c_float), POINTER(ctypes.c_float),
+                                               _P, c_size_t, _P]),
     "msi_net_num_layers": (c_int, [_P]),
     "msi_net_layer_scope": (c_char_p, [_P, _I]),
     "msi_net_layer_flops": (ctypes.c_double, [_P, _I]),

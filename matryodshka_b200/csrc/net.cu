@@ -370,8 +370,9 @@ extern "C" int msi_net_load_layer(msi_net* net, const char* scope, const float* 
     return MSI_OK;
 }
 
+struct ProfCtx;
 static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
-                            float* pred, void* stream, cudaEvent_t* ev, float* rgba = nullptr);
+                            float* pred, void* stream, ProfCtx* ev, float* rgba = nullptr);
 
 extern "C" int msi_net_forward(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
                                float* pred, void* stream) {
@@ -405,12 +406,29 @@ extern "C" int msi_net_forward_rgba(msi_net* net, const float* in_f32, const voi
 // returns per-layer milliseconds per launch (host arrays of msi_net_num_layers() floats; ln_ms of the
 // head is 0).  Not capturable into a graph.
 static const int kProfReps = 4;
-extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
-                                        int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host) {
+struct ProfCtx {
+    std::vector<cudaEvent_t> ev;   // per layer: conv begin / end, LayerNorm begin / end of every repeat
+    void* flush = nullptr;         // cold-L2 mode: this buffer (larger than the L2) is overwritten before every timed launch
+    size_t flush_bytes = 0;
+    cudaEvent_t& at(int layer, int which, int rep) { return ev[((size_t)layer * 4 + which) * kProfReps + rep]; }
+};
+static int net_forward_prof(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B, float* pred,
+                            void* stream, ProfCtx* prof, float* rgba);
+
+extern "C" int msi_net_forward_profiled_flush(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
+                                              int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host,
+                                              void* flush, size_t flush_bytes, float* rgba) {
     MSI_CHECK_ARG(conv_ms_host && ln_ms_host, "net_forward_profiled: null output");
-    std::vector<cudaEvent_t> ev(4 * kNumLayers);
-    for (auto& e : ev) MSI_CUDA(cudaEventCreate(&e));
-    int rc = net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, ev.data());
+    if (rgba != nullptr && !msi_net_can_fuse_rgba(net)) {
+        set_error("net_forward_profiled: this net cannot fuse the RGBA assembly");
+        return MSI_ERR_UNSUPPORTED;
+    }
+    ProfCtx prof;
+    prof.ev.resize((size_t)kNumLayers * 4 * kProfReps);
+    prof.flush = flush;
+    prof.flush_bytes = flush ? flush_bytes : 0;
+    for (auto& e : prof.ev) MSI_CUDA(cudaEventCreate(&e));
+    int rc = net_forward_prof(net, in_f32, in_hi, in_lo, B, pred, stream, &prof, rgba);
     if (rc == MSI_OK) {
         cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) {
@@ -420,18 +438,31 @@ extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const
     }
     if (rc == MSI_OK) {
         for (int i = 0; i < kNumLayers; ++i) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[4 * i], ev[4 * i + 1]);
-            conv_ms_host[i] = ms / kProfReps;
-            ln_ms_host[i] = 0.f;
-            if (net->layers[i].kind != kHead) {
-                cudaEventElapsedTime(&ms, ev[4 * i + 2], ev[4 * i + 3]);
-                ln_ms_host[i] = ms / kProfReps;
+            // warm mode: one event pair around the kProfReps back-to-back launches (rep 0 slots);
+            // cold mode: one pair per launch, the flush in between is not timed
+            const int pairs = prof.flush ? kProfReps : 1;
+            float conv = 0.f, ln = 0.f;
+            for (int r = 0; r < pairs; ++r) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, prof.at(i, 0, r), prof.at(i, 1, r));
+                conv += ms;
+                if (net->layers[i].kind != kHead) {
+                    cudaEventElapsedTime(&ms, prof.at(i, 2, r), prof.at(i, 3, r));
+                    ln += ms;
+                }
             }
+            conv_ms_host[i] = conv / kProfReps;
+            ln_ms_host[i] = ln / kProfReps;
         }
     }
-    for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& e : prof.ev) cudaEventDestroy(e);
     return rc;
+}
+
+extern "C" int msi_net_forward_profiled(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo,
+                                        int B, float* pred, void* stream, float* conv_ms_host, float* ln_ms_host) {
+    return msi_net_forward_profiled_flush(net, in_f32, in_hi, in_lo, B, pred, stream, conv_ms_host, ln_ms_host, nullptr, 0,
+                                          nullptr);
 }
 
 extern "C" int msi_net_num_layers(const msi_net* net) { return net ? kNumLayers : 0; }
@@ -447,8 +478,13 @@ extern "C" double msi_net_layer_flops(const msi_net* net, int i) {
     return 2.0 * L.Hout * L.Wout * (double)L.cin_total * L.cout;
 }
 
+static int net_forward_prof(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B, float* pred,
+                            void* stream, ProfCtx* prof, float* rgba) {
+    return net_forward_impl(net, in_f32, in_hi, in_lo, B, pred, stream, prof, rgba);
+}
+
 static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi, const void* in_lo, int B,
-                            float* pred, void* stream, cudaEvent_t* ev, float* rgba) {
+                            float* pred, void* stream, ProfCtx* ev, float* rgba) {
     MSI_CHECK_ARG(net && (pred || rgba), "net_forward: null pointer");
     MSI_CHECK_ARG(B >= 1 && B <= net->max_batch, "net_forward: B=%d outside [1, %d]", B, net->max_batch);
     MSI_CHECK_ARG(in_f32 || (in_hi && in_lo), "net_forward: need in_f32 or the hi/lo pair");
@@ -489,8 +525,10 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
         for (int s = 0; s < L.nsrc; ++s) srcs[s] = net->acts[L.src[s]];
         float* out = (L.kind == kHead) ? pred : L.raw;
         const int conv_runs = ev ? 1 + kProfReps : 1;
+        const bool cold = ev && ev->flush != nullptr;
         for (int r = 0; r < conv_runs; ++r) {
-            if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i], st));
+            if (cold && r >= 1) MSI_CUDA(cudaMemsetAsync(ev->flush, r, ev->flush_bytes, st));
+            if (ev && (r == 1 || (cold && r >= 1))) MSI_CUDA(cudaEventRecord(ev->at(i, 0, cold ? r - 1 : 0), st));
             if (net->conv_impl == MSI_CONV_SIMT) {
                 rc = conv_simt_forward(L, srcs, B, out, st);
             } else if (L.kind == kHead && rgba != nullptr) {
@@ -504,21 +542,24 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
                 hf.x_pad = net->acts[0].x_pad;
                 rc = conv_tc_forward(L, B, nullptr, /*after_kernel=*/true, st, &hf);
             } else {  // the first conv follows a memset / copy, every later one follows our own LayerNorm kernel
-                rc = conv_tc_forward(L, B, out, /*after_kernel=*/i > 0 || r > 0, st);
+                rc = conv_tc_forward(L, B, out, /*after_kernel=*/(i > 0 || r > 0) && !(cold && r >= 1), st);
             }
             if (rc != MSI_OK) return rc;
+            if (cold && r >= 1) MSI_CUDA(cudaEventRecord(ev->at(i, 1, r - 1), st));
         }
-        if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 1], st));
+        if (ev && !cold) MSI_CUDA(cudaEventRecord(ev->at(i, 1, 0), st));
         if (L.kind != kHead) {
             const long long n_per = (long long)L.Hout * L.Wout * L.cout;
             for (int r = 0; r < conv_runs; ++r) {
-                if (ev && r == 1) MSI_CUDA(cudaEventRecord(ev[4 * i + 2], st));
+                if (cold && r >= 1) MSI_CUDA(cudaMemsetAsync(ev->flush, r, ev->flush_bytes, st));
+                if (ev && (r == 1 || (cold && r >= 1))) MSI_CUDA(cudaEventRecord(ev->at(i, 2, cold ? r - 1 : 0), st));
                 rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc, L.Wout,
+                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc && !(cold && r >= 1), L.Wout,
                                 net->acts[i + 1].x_pad, st);
                 if (rc != MSI_OK) return rc;
+                if (cold && r >= 1) MSI_CUDA(cudaEventRecord(ev->at(i, 3, r - 1), st));
             }
-            if (ev) MSI_CUDA(cudaEventRecord(ev[4 * i + 3], st));
+            if (ev && !cold) MSI_CUDA(cudaEventRecord(ev->at(i, 3, 0), st));
         }
     }
     return MSI_OK;

@@ -656,18 +656,22 @@ def all_gather_frames(local: torch.Tensor, world_size: int, group=None) -> torch
     return out
 
 
-def profile_net_layers(net: NetEngine, hi_lo, out, reps: int = 3):
+def profile_net_layers(net: NetEngine, hi_lo, out, reps: int = 3, rgba=None, cold_l2: bool = False):
     """Per-layer conv / LayerNorm milliseconds (CUDA events on the launching stream, average of
-    ``reps`` forwards) and algorithmic FLOPs per layer.  Used by bench.py for the roofline."""
+    ``reps`` forwards) and algorithmic FLOPs per layer.  Used by bench.py for the roofline.
+    ``rgba``: run the head with the fused RGBA assembly (as the pipeline does); ``cold_l2``: overwrite a 256 MB
+    buffer before every timed launch (each launch timed on its own) instead of timing back-to-back repeats."""
     lib = net.lib
     n = int(lib.msi_net_num_layers(net._h))
     conv = (ctypes.c_float * n)()
     ln = (ctypes.c_float * n)()
     B = hi_lo[0].shape[0]
     acc_c, acc_l = np.zeros(n), np.zeros(n)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=net.device) if cold_l2 else None
     for _ in range(reps):
-        check(lib.msi_net_forward_profiled(net._h, None, ptr(hi_lo[0]), ptr(hi_lo[1]), B, ptr(out), stream_ptr(),
-                                           conv, ln), "msi_net_forward_profiled")
+        check(lib.msi_net_forward_profiled_flush(net._h, None, ptr(hi_lo[0]), ptr(hi_lo[1]), B, ptr(out), stream_ptr(),
+                                                 conv, ln, ptr(flush), flush.numel() if flush is not None else 0,
+                                                 ptr(rgba)), "msi_net_forward_profiled_flush")
         acc_c += np.frombuffer(conv, dtype=np.float32)
         acc_l += np.frombuffer(ln, dtype=np.float32)
     scopes = [lib.msi_net_layer_scope(net._h, i).decode() for i in range(n)]
