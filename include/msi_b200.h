@@ -48,6 +48,10 @@ extern "C" {
 /* operand precision of the tcgen05 back end */
 #define MSI_PREC_FP16X3 0 /* fp16 hi/lo split, 3 MMAs per product: ~fp32 accuracy (default; meets 1e-3) */
 #define MSI_PREC_FP16 1   /* single fp16 MMA: 3x fewer MMAs, ~7e-3 max-abs on the net output  */
+#define MSI_PREC_FP16_FP8X 2 /* fp16 main product + both cross terms as ONE e4m3 MMA of twice the K, on the layers
+                              * whose N tile is 128 (every conv / deconv with Cout >= 128); the Cout = 64 layers and the
+                              * head keep MSI_PREC_FP16X3.  2 MMA units per product instead of 3; ~2.5e-4 max-abs on
+                              * the net output (meets 1e-3) */
 
 int msi_b200_abi_version(void);
 const char* msi_last_error(void);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MSI_B200_LIB") or os.path.join(_HERE, "libmsi_b200.so
 MSI_OK = 0
 IMG_F32, IMG_U8 = 0, 1
 CONV_TCGEN05, CONV_SIMT = 0, 1
-PREC_FP16X3, PREC_FP16 = 0, 1
+PREC_FP16X3, PREC_FP16, PREC_FP16_FP8X = 0, 1, 2
 NET_COORD, NET_WRAP = 0, 1
 COLOR_MODES = {"blend_psv": 0, "blend_bg": 1, "blend_bg_psv": 2, "alpha_only": 3}
 ACT_SCALE = 16.0

@@ -31,6 +31,7 @@
 //   warps 2-5 epilogue: tcgen05.ld -> un-scale + coord bias (+ bias, tanh for the head) -> float32
 //            NHWC stores + LayerNorm partial sums
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include <algorithm>
 
@@ -117,6 +118,7 @@ struct TcParams {
 struct TcPlan {
     TcParams p;
     int pair;                 // 1: the halo kernel runs as CTA pairs (tcgen05 cta_group::2, W rows split between the CTAs)
+    int fp8x;                 // 1: MSI_PREC_FP16_FP8X layer (cross terms in e4m3; the "lo" maps point at the e4m3 copies)
     int halo;                 // 1: conv_halo_tcgen05_kernel (a_map[s][0] = 5-D hi+lo map, w_map[0] = 4-D [kb][hi|lo][cout][64])
     int n_tile, split;
     int cl;                   // cluster size along M: CTAs of a cluster multicast the W tile to each other
@@ -232,6 +234,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
+// kind::f8f6f4 with e4m3 operands (the instruction descriptor's format fields are 0 for e4m3 as they are for f16): K = 32
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
@@ -341,6 +352,14 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -465,7 +484,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
         for (int c = c_begin; c < c_end; c += 32) {
             uint32_t r[32];
             uint32_t r2[SPLIT ? 32 : 1];
-            if (!PAIR) {
+            if (!(PAIR && SPLIT)) {  // (a pair in MSI_PREC_FP16_FP8X has ONE accumulator column per cout)
                 tmem_ld32(taddr + (uint32_t)c, r);
                 if (SPLIT) tmem_ld32(taddr + (uint32_t)(N_TILE + c), r2);
             } else {
@@ -621,8 +640,8 @@ __device__ __forceinline__ void epilogue_head_rgba(const TcParams& p, const int 
     constexpr int L = N_TILE / 2;
     constexpr int kAccCols = 2 * N_TILE;
     constexpr uint32_t kRowBytes = N_TILE * 4;
-    constexpr int kLanesPerPixel = L / 2;             // a lane owns the layer pair (2k, 2k + 1)
-    constexpr int kPixPerIter = 32 / kLanesPerPixel;  // L = 32: two pixels per warp iteration; L = 64: one
+    constexpr int kLanesPerPixel = L / 4;             // a lane owns four layers (4k .. 4k + 3)
+    constexpr int kPixPerIter = 32 / kLanesPerPixel;  // L = 32: four pixels per warp step; L = 64: two
     const uint32_t qbase = stage_base + (uint32_t)quarter * 32u * kRowBytes;
     const int half = ew >> 2;  // 0: this warp reads the blend weights out of TMEM, 1: the alphas
     const int sub = lane / kLanesPerPixel, k = lane - sub * kLanesPerPixel;
@@ -663,63 +682,83 @@ __device__ __forceinline__ void epilogue_head_rgba(const TcParams& p, const int 
             }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
-#pragma unroll 2
-        for (int i = 0; i < 16; i += kPixPerIter) {
-            const int rr = half * 16 + i + sub;  // row of the quarter = pixel
-            const int m = quarter * 32 + rr;     // pixel of the M tile
-            const int ly = m / p.BW, lx = m - ly * p.BW;
-            const int oy = tc.oy0 + ly, ox = tc.ox0 + lx;
-            const bool valid = (oy < p.Mh) && (ox < p.Mw) && !tc.dummy;
-            const int chw = k >> 1, cha = (L >> 2) + (k >> 1);
-            float2 w2, a2;
-            const uint32_t rowaddr = qbase + (uint32_t)rr * kRowBytes + (uint32_t)((k & 1) << 3);
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                         : "=f"(w2.x), "=f"(w2.y)
-                         : "r"(rowaddr + (uint32_t)((chw >> 3) << 7) + (uint32_t)(((chw & 7) ^ (rr & 7)) << 4))
-                         : "memory");
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                         : "=f"(a2.x), "=f"(a2.y)
-                         : "r"(rowaddr + (uint32_t)((cha >> 3) << 7) + (uint32_t)(((cha & 7) ^ (rr & 7)) << 4))
-                         : "memory");
-            if (valid) {
-                const size_t poff = (((size_t)tc.b * p.Hout + oy) * p.psv_Wp + ox + p.psv_xpad) * p.psv_cstride + 6 * k;
-                const unsigned* fh = reinterpret_cast<const unsigned*>(p.psv_hi + poff);
-                const unsigned* fl = reinterpret_cast<const unsigned*>(p.psv_lo + poff);
-                const unsigned* bh = reinterpret_cast<const unsigned*>(p.psv_hi + poff + 3 * L);
-                const unsigned* bl = reinterpret_cast<const unsigned*>(p.psv_lo + poff + 3 * L);
-                unsigned wfh[3], wfl[3], wbh[3], wbl[3];
+        // Assembly.  A lane owns FOUR layers (4k .. 4k + 3) of one pixel: its PSV taps are 12 consecutive halves = three
+        // 8-byte loads per array (fg / bg x hi / lo), its weights and alphas one 16-byte chunk each, its output four
+        // float4 = 64 contiguous bytes.  Two steps (kPixPerIter pixels each) are processed together with all 24 loads
+        // issued before the first use: the epilogue has only 8 warps per SM, so the bytes in flight per warp decide
+        // whether this phase runs at HBM speed (measured: one pixel pair per step with 4-byte loads took 106 us per
+        // frame, more than the unfused head + the separate assembly kernel).
+#pragma unroll 1
+        for (int i = 0; i < 16; i += 2 * kPixPerIter) {
+            uint2 wfh[2][3], wfl[2][3], wbh[2][3], wbl[2][3];
+            float4 w4[2], a4[2];
+            bool valid[2];
+            float4* dst[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int rr = half * 16 + i + u * kPixPerIter + sub;  // row of the quarter = pixel
+                const int m = quarter * 32 + rr;                       // pixel of the M tile
+                const int ly = m / p.BW, lx = m - ly * p.BW;
+                const int oy = tc.oy0 + ly, ox = tc.ox0 + lx;
+                valid[u] = (oy < p.Mh) && (ox < p.Mw) && !tc.dummy;
+                const int chw = k, cha = (L >> 2) + k;  // 16-byte chunks of the row holding w[4k..4k+3] / alpha[4k..4k+3]
+                const uint32_t rowaddr = qbase + (uint32_t)rr * kRowBytes;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(w4[u].x), "=f"(w4[u].y), "=f"(w4[u].z), "=f"(w4[u].w)
+                             : "r"(rowaddr + (uint32_t)((chw >> 3) << 7) + (uint32_t)(((chw & 7) ^ (rr & 7)) << 4))
+                             : "memory");
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(a4[u].x), "=f"(a4[u].y), "=f"(a4[u].z), "=f"(a4[u].w)
+                             : "r"(rowaddr + (uint32_t)((cha >> 3) << 7) + (uint32_t)(((cha & 7) ^ (rr & 7)) << 4))
+                             : "memory");
+                const int oyc = valid[u] ? oy : 0, oxc = valid[u] ? ox : 0;  // masked lanes read pixel (0, 0) and store nothing
+                const size_t poff = (((size_t)tc.b * p.Hout + oyc) * p.psv_Wp + oxc + p.psv_xpad) * p.psv_cstride + 12 * k;
+                const uint2* fh = reinterpret_cast<const uint2*>(p.psv_hi + poff);
+                const uint2* fl = reinterpret_cast<const uint2*>(p.psv_lo + poff);
+                const uint2* bh = reinterpret_cast<const uint2*>(p.psv_hi + poff + 3 * L);
+                const uint2* bl = reinterpret_cast<const uint2*>(p.psv_lo + poff + 3 * L);
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    wfh[t] = __ldg(fh + t);
-                    wfl[t] = __ldg(fl + t);
-                    wbh[t] = __ldg(bh + t);
-                    wbl[t] = __ldg(bl + t);
+                    wfh[u][t] = __ldg(fh + t);
+                    wfl[u][t] = __ldg(fl + t);
+                    wbh[u][t] = __ldg(bh + t);
+                    wbl[u][t] = __ldg(bl + t);
                 }
-                float fg[6], bg[6];
+                dst[u] = p.rgba + (((size_t)tc.b * p.Hout + oyc) * p.Wout + oxc) * L + 4 * k;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float fg[12], bg[12];
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&wfh[t]));
-                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&wfl[t]));
-                    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&wbh[t]));
-                    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&wbl[t]));
-                    fg[2 * t] = __fmul_rn(__fadd_rn(a.x, b.x), inv);
-                    fg[2 * t + 1] = __fmul_rn(__fadd_rn(a.y, b.y), inv);
-                    bg[2 * t] = __fmul_rn(__fadd_rn(c.x, d.x), inv);
-                    bg[2 * t + 1] = __fmul_rn(__fadd_rn(c.y, d.y), inv);
+                    const unsigned hw[2] = {wfh[u][t].x, wfh[u][t].y}, lw[2] = {wfl[u][t].x, wfl[u][t].y};
+                    const unsigned gw[2] = {wbh[u][t].x, wbh[u][t].y}, mw[2] = {wbl[u][t].x, wbl[u][t].y};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&gw[e]));
+                        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&mw[e]));
+                        fg[4 * t + 2 * e] = __fmul_rn(__fadd_rn(a.x, b.x), inv);
+                        fg[4 * t + 2 * e + 1] = __fmul_rn(__fadd_rn(a.y, b.y), inv);
+                        bg[4 * t + 2 * e] = __fmul_rn(__fadd_rn(c.x, d.x), inv);
+                        bg[4 * t + 2 * e + 1] = __fmul_rn(__fadd_rn(c.y, d.y), inv);
+                    }
                 }
-                const float om0 = __fsub_rn(1.0f, w2.x), om1 = __fsub_rn(1.0f, w2.y);
-                float4 o0, o1;
-                o0.x = __fadd_rn(__fmul_rn(w2.x, fg[0]), __fmul_rn(om0, bg[0]));
-                o0.y = __fadd_rn(__fmul_rn(w2.x, fg[1]), __fmul_rn(om0, bg[1]));
-                o0.z = __fadd_rn(__fmul_rn(w2.x, fg[2]), __fmul_rn(om0, bg[2]));
-                o0.w = a2.x;
-                o1.x = __fadd_rn(__fmul_rn(w2.y, fg[3]), __fmul_rn(om1, bg[3]));
-                o1.y = __fadd_rn(__fmul_rn(w2.y, fg[4]), __fmul_rn(om1, bg[4]));
-                o1.z = __fadd_rn(__fmul_rn(w2.y, fg[5]), __fmul_rn(om1, bg[5]));
-                o1.w = a2.y;
-                float4* dst = p.rgba + (((size_t)tc.b * p.Hout + oy) * p.Wout + ox) * L + 2 * k;
-                dst[0] = o0;
-                dst[1] = o1;
+                const float wv[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+                const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+                if (valid[u]) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float om = __fsub_rn(1.0f, wv[j]);
+                        float4 o;
+                        o.x = __fadd_rn(__fmul_rn(wv[j], fg[3 * j + 0]), __fmul_rn(om, bg[3 * j + 0]));
+                        o.y = __fadd_rn(__fmul_rn(wv[j], fg[3 * j + 1]), __fmul_rn(om, bg[3 * j + 1]));
+                        o.z = __fadd_rn(__fmul_rn(wv[j], fg[3 * j + 2]), __fmul_rn(om, bg[3 * j + 2]));
+                        o.w = av[j];
+                        dst[u][j] = o;
+                    }
+                }
             }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");  // the tile may be overwritten
@@ -741,9 +780,11 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     const int cta_rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
     const int cluster_id = blockIdx.x / CL;
     const int n_clusters = gridDim.x / CL;
+    // SPLIT: 0 = one fp16 MMA; 1 = fp16x3 (A_hi x [W_hi | W_lo] and A_lo x W_hi); 2 = MSI_PREC_FP16_FP8X (A_hi x W_hi in
+    // fp16, [A_hi8 | A_lo8] x [W_lo8 | W_hi8] in e4m3 into the SAME accumulator columns: the "lo" tiles hold the e4m3 copies)
     constexpr int kStageBytes = (kATileBytes + kWTileBytes) * (SPLIT ? 2 : 1);
-    constexpr int kAccCols = SPLIT ? 2 * N_TILE : N_TILE;  // TMEM columns of one accumulator
-    constexpr int kTmemCols = 2 * kAccCols;                // double-buffered
+    constexpr int kAccCols = (SPLIT == 1) ? 2 * N_TILE : N_TILE;  // TMEM columns of one accumulator
+    constexpr int kTmemCols = 2 * kAccCols;                       // double-buffered
     constexpr uint32_t kTxBytes = (uint32_t)kStageBytes;
     // stage layout: [A_hi][A_lo][W_hi][W_lo] (SPLIT) or [A][W]
     constexpr int kOffALo = kATileBytes;
@@ -865,8 +906,9 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         const bool leader = elect_one();
-        constexpr uint32_t idesc_wide = make_idesc(SPLIT ? 2 * N_TILE : N_TILE);
+        constexpr uint32_t idesc_wide = make_idesc(SPLIT == 1 ? 2 * N_TILE : N_TILE);
         constexpr uint32_t idesc_n = make_idesc(N_TILE);
+        constexpr uint64_t kDescWLo = (uint64_t)(kOffWLo >> 4);
         const int total_units = p.total_units, units_per_col = p.units_per_col, n_tiles = p.n_tiles;
         int stage = 0;
         uint32_t phase = 0;
@@ -898,7 +940,14 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                         // A_hi x [W_hi | W_lo] -> columns [0, 2N)   (fp16 mode: A x W -> [0, N))
                         umma_f16(d_tmem, da + adv, da + kDescWHi + adv, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);
                         // A_lo x W_hi -> accumulates into columns [0, N)
-                        if (SPLIT) umma_f16(d_tmem, da + kDescALo + adv, da + kDescWHi + adv, idesc_n, 1u);
+                        if (SPLIT == 1) umma_f16(d_tmem, da + kDescALo + adv, da + kDescWHi + adv, idesc_n, 1u);
+                    }
+                    if (SPLIT == 2) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {  // 128 e4m3 per row = 4 K steps of 32: [hi8 | lo8] x [w_lo8 | w_hi8]
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            umma_f8(d_tmem, da + kDescALo + adv, da + kDescWLo + adv, idesc_n, 1u);
+                        }
                     }
                     // free the smem slot when these MMAs retire -- in every CTA of the cluster, because
                     // the peers' next multicast W slices land in this CTA's slot too
@@ -925,12 +974,12 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         // =============================== epilogue (warps 2..9) ===============================
         const int row = (warp & 3) * 32 + lane;  // M index inside the tile
         const int ly = row / p.BW;
-        if (SPLIT && CL == 1 && p.rgba != nullptr)
+        if (SPLIT == 1 && CL == 1 && p.rgba != nullptr)
             epilogue_head_rgba<N_TILE>(p, warp - 2, warp & 3, lane, cluster_id, n_clusters, tmem_base, tfull0, tempty0,
                                        smem_base + (uint32_t)(stages * kStageBytes));
         else
-            epilogue_role<N_TILE, SPLIT, CL>(p, warp - 2, warp & 3, lane, row - ly * p.BW, ly, cluster_id, n_clusters, cta_rank,
-                                             tmem_base, tfull0, tempty0, &s_is_last, s_red);
+            epilogue_role<N_TILE, SPLIT == 1, CL>(p, warp - 2, warp & 3, lane, row - ly * p.BW, ly, cluster_id, n_clusters, cta_rank,
+                                                  tmem_base, tfull0, tempty0, &s_is_last, s_red);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -956,11 +1005,15 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
 //   warp 0  A producer (halo ring, a_stages slots)      warp 2  W producer (w_stages slots of T taps)
 //   warp 1  MMA issuer + TMEM allocator                 warps 3-10  epilogue (shared with the kernel above)
 constexpr int kHaloThreads = 96 + 32 * kEpiWarps;
-template <int N_TILE, int T, bool PAIR>
+// FP8X (MSI_PREC_FP16_FP8X): the "lo" halves of the halo tile and of the weight slot hold the e4m3 copies
+// ([hi8 | lo8] per activation row, [w_lo8 | w_hi8] per weight row); per tap and chunk the MMA warp issues four fp16 MMAs
+// (K = 16: hi x hi) and four e4m3 MMAs (K = 32: both cross terms) of width N into ONE set of N accumulator columns --
+// 8 N-wide MMAs where fp16x3 issues 4 of width 2N and 4 of width N.
+template <int N_TILE, int T, bool PAIR, bool FP8X = false>
 __global__ void __launch_bounds__(kRegCapThreads, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                          const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
-    constexpr int kAccCols = 2 * N_TILE;
+    constexpr int kAccCols = FP8X ? N_TILE : 2 * N_TILE;
     constexpr int kTmemCols = 2 * kAccCols;
     // PAIR: two CTAs of a cluster share every weight tile (tcgen05 cta_group::2, M = 256 = both CTAs'
     // pixel tiles): each holds HALF of the rows, arranged [W_hi rows r*N/2.. | W_lo rows (1-r)*N/2..] for
@@ -1122,6 +1175,8 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         const bool leader = elect_one();
         constexpr uint32_t idesc_wide = PAIR ? make_idesc_pair(2 * N_TILE) : make_idesc(2 * N_TILE);
         constexpr uint32_t idesc_n = PAIR ? make_idesc_pair(N_TILE) : make_idesc(N_TILE);
+        // FP8X: the e4m3 weight rows follow this CTA's fp16 rows inside a tap (N rows, or N / 2 for a pair)
+        constexpr uint64_t kW8Adv = (uint64_t)(((PAIR ? N_TILE / 2 : N_TILE) * kBlockK * 2) >> 4);
         constexpr uint64_t kDescFlags = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         const uint64_t a_desc_hi = kDescFlags | ((uint64_t)(p.PF * 8) << 32);  // SBO = PF rows of 128 bytes (>> 4)
         const uint64_t lo_adv = (uint64_t)(p.a_rows * 8);                       // hi halo -> lo halo
@@ -1186,7 +1241,13 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t adv = (uint64_t)(k * 2);
-                                if (!PAIR) {
+                                if (FP8X) {
+                                    if (!PAIR)
+                                        umma_f16(d_tmem, da + adv, db + adv, idesc_n, accumulate);       // A_hi x W_hi
+                                    else
+                                        umma_f16_pair(d_tmem, da + adv, db + adv, idesc_n, accumulate);
+                                    accumulate = 1u;
+                                } else if (!PAIR) {
                                     umma_f16(d_tmem, da + adv, db + adv, idesc_wide, accumulate);  // A_hi x [W_hi | W_lo]
                                     accumulate = 1u;
                                     umma_f16(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);    // A_lo x W_hi
@@ -1194,6 +1255,16 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                                     umma_f16_pair(d_tmem, da + adv, db + adv, idesc_wide, accumulate);
                                     accumulate = 1u;
                                     umma_f16_pair(d_tmem, da + lo_adv + adv, db + adv, idesc_n, 1u);
+                                }
+                            }
+                            if (FP8X) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k) {  // [A_hi8 | A_lo8] x [W_lo8 | W_hi8], K = 32 per step
+                                    const uint64_t adv = (uint64_t)(k * 2);
+                                    if (!PAIR)
+                                        umma_f8(d_tmem, da + lo_adv + adv, db + kW8Adv + adv, idesc_n, 1u);
+                                    else
+                                        umma_f8_pair(d_tmem, da + lo_adv + adv, db + kW8Adv + adv, idesc_n, 1u);
                                 }
                             }
                         }
@@ -1224,12 +1295,13 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         const int lx = (p.orient == 0) ? (row & 7) : (row >> 3);
         const int ly = (p.orient == 0) ? (row >> 3) : (row & 7);
         if (p.stage_out)
-            epilogue_role<N_TILE, 1, PAIR ? 2 : 1, true, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas, cta_rank,
-                                                               tmem_base, tfull0, tempty0, &s_is_last, s_red, tr_launch,
-                                                               w_ring + (uint32_t)w_stages * w_slot_bytes);
+            epilogue_role<N_TILE, FP8X ? 0 : 1, PAIR ? 2 : 1, true, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas,
+                                                                          cta_rank, tmem_base, tfull0, tempty0, &s_is_last, s_red,
+                                                                          tr_launch, w_ring + (uint32_t)w_stages * w_slot_bytes);
         else
-            epilogue_role<N_TILE, 1, PAIR ? 2 : 1, false, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas, cta_rank,
-                                                                tmem_base, tfull0, tempty0, &s_is_last, s_red, tr_launch);
+            epilogue_role<N_TILE, FP8X ? 0 : 1, PAIR ? 2 : 1, false, PAIR>(p, warp - 3, warp & 3, lane, lx, ly, cluster_id, n_ctas,
+                                                                           cta_rank, tmem_base, tfull0, tempty0, &s_is_last, s_red,
+                                                                           tr_launch);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1246,12 +1318,21 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     }
 }
 
+// e4m3 weight copies of MSI_PREC_FP16_FP8X (scales: net_internal.cuh)
+__device__ __forceinline__ uint8_t w_lo8(float w_scaled, __half h) {
+    return (uint8_t)__nv_cvt_float_to_fp8((w_scaled - __half2float(h)) * (float)(1 << kFp8HiShift), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ uint8_t w_hi8(__half h) {
+    return (uint8_t)__nv_cvt_float_to_fp8(__half2float(h) * (1.0f / (float)(1 << kFp8LoShift)), __NV_SATFINITE, __NV_E4M3);
+}
+
 // ---- weight packing ----------------------------------------------------------------------------
 // w_f32 (TF layout) -> fp16 hi/lo [cls][cout][K], K = tap * cs_total + packed channel, x MSI_WEIGHT_SCALE.
 struct PackParams {
     const float* w;
     __half* hi;
     __half* lo;
+    int fp8x;  // MSI_PREC_FP16_FP8X layer: the "lo" rows hold [w_lo8 x 64 | w_hi8 x 64] (e4m3) instead of fp16 residuals
     int kind, ncls, cout, K, cs_total, cin_total, coord;
     int nsrc, cin[2], cstride[2];
     TapList taps[4];
@@ -1286,7 +1367,14 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams q) {
     __half h, l;
     split_half(v * MSI_WEIGHT_SCALE, h, l);
     q.hi[idx] = h;
-    q.lo[idx] = l;
+    if (!q.fp8x) {
+        q.lo[idx] = l;
+    } else {
+        // the row of 64-channel K block kc as 128 bytes: w_lo8 (pairs with A_hi8), then w_hi8 (pairs with A_lo8)
+        uint8_t* row = reinterpret_cast<uint8_t*>(q.lo) + ((idx - (k & 63)) * 2);
+        row[k & 63] = w_lo8(v * MSI_WEIGHT_SCALE, h);
+        row[64 + (k & 63)] = w_hi8(h);
+    }
 }
 
 // K-block-major packing of the halo kernel: [kb][hi|lo][cout][64] with kb = (cls * chunks + chunk) *
@@ -1321,7 +1409,25 @@ __global__ void __launch_bounds__(256) pack_weights_halo_kernel(PackParams q, in
     }
     __half h, l;
     split_half(v * MSI_WEIGHT_SCALE, h, l);
-    if (pair_tile == 0) {
+    if (q.fp8x) {
+        // fp16 row and e4m3 row ([w_lo8 x 64 | w_hi8 x 64]) of this cout.  Single CTA: planes [hi rows | e4m3 rows] of the
+        // K block.  Pair: rank r holds couts [r N/2, (r+1) N/2) of every N tile, fp16 rows first, their e4m3 rows after.
+        size_t row_h, row_8;
+        if (pair_tile == 0) {
+            row_h = ((size_t)kb * 2 + 0) * q.cout + n;
+            row_8 = ((size_t)kb * 2 + 1) * q.cout + n;
+        } else {
+            const int half_rows = pair_tile / 2;
+            const int tile0 = (n / pair_tile) * pair_tile, in_tile = n % pair_tile;
+            const int r = in_tile / half_rows, i = in_tile % half_rows;
+            row_h = ((size_t)kb * 2 + r) * q.cout + tile0 + i;
+            row_8 = ((size_t)kb * 2 + r) * q.cout + tile0 + half_rows + i;
+        }
+        q.hi[row_h * kBlockK + k64] = h;
+        uint8_t* row = reinterpret_cast<uint8_t*>(q.hi + row_8 * kBlockK);
+        row[k64] = w_lo8(v * MSI_WEIGHT_SCALE, h);
+        row[64 + k64] = w_hi8(h);
+    } else if (pair_tile == 0) {
         q.hi[(((size_t)kb * 2 + 0) * q.cout + n) * kBlockK + k64] = h;
         q.hi[(((size_t)kb * 2 + 1) * q.cout + n) * kBlockK + k64] = l;
     } else {
@@ -1533,10 +1639,10 @@ long long* trace_buffer() {
 // Launch attribute for programmatic dependent launch (MSI_PDL=0 turns it off): the kernel may begin
 // before the previous kernel in the stream has finished; it calls griddepcontrol.wait before
 // touching anything that kernel wrote.  `first` = no kernel precedes it in the forward (memset).
-template <int N_TILE, int T, bool PAIR>
+template <int N_TILE, int T, bool PAIR, bool FP8X = false>
 int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = conv_halo_tcgen05_kernel<N_TILE, T, PAIR>;
+    auto kern = conv_halo_tcgen05_kernel<N_TILE, T, PAIR, FP8X>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) {
@@ -1639,8 +1745,8 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     if (L.w_lo != L.w_hi + (size_t)L.ncls * L.cout * L.K) return MSI_ERR_UNSUPPORTED;  // one [.. hi|lo ..] buffer
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s)
-        rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, srcs[s].lo, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch,
-                             p.orient, p.PF, p.PS);
+        rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, plan->fp8x ? reinterpret_cast<const __half*>(srcs[s].q8) : srcs[s].lo,
+                             srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.orient, p.PF, p.PS);
     if (rc == MSI_OK && L.nsrc == 1) plan->a_map[1][0] = plan->a_map[0][0];
     const int nkb = L.ncls * (p.chunks[0] + p.chunks[1]) * ntaps;
     if (rc == MSI_OK) rc = encode_w_map4(&plan->w_map[0], L.w_hi, L.cout, nkb, plan->n_tile, p.T, plan->pair ? 1 : 2);
@@ -1662,12 +1768,26 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     TcPlan* plan = new TcPlan();
     memset(plan, 0, sizeof(TcPlan));
     TcParams& p = plan->p;
-    plan->split = (precision == MSI_PREC_FP16X3) ? 1 : 0;
+    plan->split = (precision == MSI_PREC_FP16X3 || precision == MSI_PREC_FP16_FP8X) ? 1 : 0;
     plan->n_tile = (L.cout % 128 == 0) ? 128 : 64;
+    plan->fp8x = (L.fp8x && plan->n_tile == 128) ? 1 : 0;
+    if (L.fp8x && !plan->fp8x) {
+        delete plan;
+        set_error("conv_tc: layer %s is marked fp8x but its N tile is %d", L.scope, plan->n_tile);
+        return MSI_ERR_STATE;
+    }
     if (L.cout % plan->n_tile != 0) {
         delete plan;
         set_error("conv_tc: layer %s has cout=%d; the tcgen05 back end needs a multiple of 64", L.scope, L.cout);
         return MSI_ERR_UNSUPPORTED;
+    }
+    for (int s = 0; s < L.nsrc; ++s) {
+        const void* second = plan->fp8x ? (const void*)srcs[s].q8 : (const void*)srcs[s].lo;
+        if (srcs[s].hi == nullptr || (plan->split && second == nullptr)) {
+            delete plan;
+            set_error("conv_tc: layer %s source %d lacks the %s operand", L.scope, s, plan->fp8x ? "e4m3" : "fp16 lo");
+            return MSI_ERR_STATE;
+        }
     }
     p.kind = L.kind;
     p.nsrc = L.nsrc;
@@ -1779,8 +1899,8 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
         rc = encode_act_map(&plan->a_map[s][0], srcs[s].hi, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.BW,
                             p.BH, p.in_stride);
         if (rc == MSI_OK)
-            rc = encode_act_map(&plan->a_map[s][1], srcs[s].lo, srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch,
-                                p.BW, p.BH, p.in_stride);
+            rc = encode_act_map(&plan->a_map[s][1], plan->fp8x ? reinterpret_cast<const __half*>(srcs[s].q8) : srcs[s].lo,
+                                srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.BW, p.BH, p.in_stride);
     }
     if (rc == MSI_OK && L.nsrc == 1) {
         plan->a_map[1][0] = plan->a_map[0][0];
@@ -1827,6 +1947,7 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
     q.K = L.K;
     q.cin_total = L.cin_total;
     q.coord = L.coord ? 1 : 0;
+    q.fp8x = L.fp8x ? 1 : 0;
     q.nsrc = L.nsrc;
     q.cs_total = 0;
     for (int s = 0; s < 2; ++s) {
@@ -1895,7 +2016,15 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
     }
     int rc;
     const bool pdl = after_kernel && pdl_enabled();
-    if (plan->halo && plan->pair) {
+    if (plan->fp8x && plan->halo) {
+        rc = plan->pair ? launch_halo<128, 1, true, true>(plan, p, pdl, st) : launch_halo<128, 1, false, true>(plan, p, pdl, st);
+    } else if (plan->fp8x) {
+        if (plan->cl != 1) {
+            set_error("conv_tc_forward: the per-tap fp8x kernel has no cluster form");
+            return MSI_ERR_UNSUPPORTED;
+        }
+        rc = launch_tc<128, 2, 1>(plan, p, pdl, st);
+    } else if (plan->halo && plan->pair) {
         if (plan->n_tile == 128)
             rc = launch_halo<128, 1, true>(plan, p, pdl, st);
         else if (p.T == 3)

@@ -5,6 +5,8 @@
 // eps = 1e-12:  inv = rsqrt(var + eps) * gamma;  y = x * inv + (beta - mean * inv).
 // 13.1 M elements per frame after conv1_1, so the reduction is grid-wide: per-block (sum, sumsq)
 // partials in float64, a one-block finalize, and a fused normalise + ReLU + fp16 hi/lo split pass.
+#include <cuda_fp8.h>
+
 #include "net_internal.cuh"
 
 namespace msi {
@@ -98,11 +100,24 @@ __device__ __forceinline__ void wrap_offsets(long long lin, int W, int C, int x_
     if (x >= W - x_pad) copy_off = (row * Wp + x - W + x_pad) * C + c;
 }
 
+// e4m3 pair of two floats (round to nearest, saturating): low byte = a
+__device__ __forceinline__ unsigned short to_e4m3x2(float a, float b) {
+    return (unsigned short)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+
+// byte offset, inside the q8 tensor, of the hi8 run of 8 channels starting at element offset `e` of the fp16-shaped
+// tensor [.., C] (e % 8 == 0, C % 64 == 0): chunk k = c / 64 holds [hi8 x 64 | lo8 x 64]; the lo8 run is 64 bytes on
+__device__ __forceinline__ size_t q8_offset(size_t e, int C) {
+    const size_t pix = e / C;
+    const int c = (int)(e - pix * C);
+    return pix * (size_t)C * 2 + (size_t)(c >> 6) * 128 + (c & 63);
+}
+
 template <bool WRAP>
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
-                __half* __restrict__ out_lo, int W, int x_pad) {
+                __half* __restrict__ out_lo, uint8_t* __restrict__ out_q8, int W, int x_pad) {
     // programmatic dependent launch: let the next conv kernel set itself up, then wait for the conv
     // kernel that produced `raw` and `stats` (no-ops when launched without the attribute)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -135,34 +150,62 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
         const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         __align__(16) __half hi[8];
         __align__(16) __half lo[8];
+        float hf[8], lf[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float inv = st.y * gm[q];
             const float sh = bt[q] - st.x * inv;
             float y = x[q] * inv + sh;
-            y = fmaxf(y, 0.f);
-            split_half(y * MSI_ACT_SCALE, hi[q], lo[q]);
+            y = fmaxf(y, 0.f) * MSI_ACT_SCALE;
+            hi[q] = __float2half_rn(y);
+            hf[q] = __half2float(hi[q]);
+            lf[q] = y - hf[q];
+            lo[q] = __float2half_rn(lf[q]);
+        }
+        uint2 h8 = make_uint2(0u, 0u), l8 = make_uint2(0u, 0u);
+        if (out_q8 != nullptr) {
+            const float sh_hi = 1.0f / (float)(1 << kFp8HiShift), sh_lo = (float)(1 << kFp8LoShift);
+            h8.x = (unsigned)to_e4m3x2(hf[0] * sh_hi, hf[1] * sh_hi) | ((unsigned)to_e4m3x2(hf[2] * sh_hi, hf[3] * sh_hi) << 16);
+            h8.y = (unsigned)to_e4m3x2(hf[4] * sh_hi, hf[5] * sh_hi) | ((unsigned)to_e4m3x2(hf[6] * sh_hi, hf[7] * sh_hi) << 16);
+            l8.x = (unsigned)to_e4m3x2(lf[0] * sh_lo, lf[1] * sh_lo) | ((unsigned)to_e4m3x2(lf[2] * sh_lo, lf[3] * sh_lo) << 16);
+            l8.y = (unsigned)to_e4m3x2(lf[4] * sh_lo, lf[5] * sh_lo) | ((unsigned)to_e4m3x2(lf[6] * sh_lo, lf[7] * sh_lo) << 16);
         }
         if (!WRAP) {
             *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            if (out_q8 != nullptr) {
+                uint8_t* q = out_q8 + q8_offset(off, C);
+                *reinterpret_cast<uint2*>(q) = h8;
+                *reinterpret_cast<uint2*>(q + 64) = l8;
+            }
         } else {
             long long m, cp;
             wrap_offsets((long long)off, W, C, x_pad, m, cp);  // `off` runs over [B * rows, W, C]
             *reinterpret_cast<uint4*>(out_hi + m) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(out_lo + m) = *reinterpret_cast<const uint4*>(lo);
+            if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + m) = *reinterpret_cast<const uint4*>(lo);
+            if (out_q8 != nullptr) {
+                uint8_t* q = out_q8 + q8_offset((size_t)m, C);
+                *reinterpret_cast<uint2*>(q) = h8;
+                *reinterpret_cast<uint2*>(q + 64) = l8;
+            }
             if (cp >= 0) {
                 *reinterpret_cast<uint4*>(out_hi + cp) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(out_lo + cp) = *reinterpret_cast<const uint4*>(lo);
+                if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + cp) = *reinterpret_cast<const uint4*>(lo);
+                if (out_q8 != nullptr) {
+                    uint8_t* q = out_q8 + q8_offset((size_t)cp, C);
+                    *reinterpret_cast<uint2*>(q) = h8;
+                    *reinterpret_cast<uint2*>(q + 64) = l8;
+                }
             }
         }
     }
 }
 
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
-               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
+               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo, uint8_t* out_q8,
                bool stats_ready, bool pdl, int W, int x_pad, cudaStream_t st) {
     MSI_CHECK_ARG(C % 8 == 0, "layer_norm: C=%d must be a multiple of 8", C);
+    MSI_CHECK_ARG(out_q8 == nullptr || C % 64 == 0, "layer_norm: the e4m3 copy needs C=%d to be a multiple of 64", C);
     if (!stats_ready) {
         // stand-alone statistics (SIMT back end); the tcgen05 conv kernel produces `stats` itself
         const int np = ln_partials_count(n_per_sample);
@@ -183,10 +226,10 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
     cfg.numAttrs = (pdl && stats_ready && pdl_enabled()) ? 1 : 0;
     if (x_pad > 0)
         MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<true>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
-                                    out_hi, out_lo, W, x_pad));
+                                    out_hi, out_lo, out_q8, W, x_pad));
     else
         MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<false>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
-                                    out_hi, out_lo, W, x_pad));
+                                    out_hi, out_lo, out_q8, W, x_pad));
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }
@@ -249,20 +292,29 @@ int wrap_copy(const __half* in_hi, const __half* in_lo, long long rows, int W, i
 }
 
 __global__ void __launch_bounds__(256)
-merge_activation_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long npix, int C,
-                        int c_stride, float* __restrict__ out, int W, int x_pad) {
+merge_activation_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const uint8_t* __restrict__ q8,
+                        long long npix, int C, int c_stride, float* __restrict__ out, int W, int x_pad) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= npix * C) return;
     const long long pix = idx / C;
     const int c = (int)(idx % C);
     const long long row = pix / W;
-    const size_t o = (size_t)(row * (W + 2 * x_pad) + (pix - row * W) + x_pad) * c_stride + c;
-    out[idx] = (__half2float(hi[o]) + __half2float(lo[o])) * (1.0f / MSI_ACT_SCALE);
+    const size_t opix = (size_t)(row * (W + 2 * x_pad) + (pix - row * W) + x_pad);
+    const size_t o = opix * c_stride + c;
+    float l;
+    if (lo != nullptr) {
+        l = __half2float(lo[o]);
+    } else {  // the e4m3 residual
+        const __nv_fp8_storage_t b = q8[opix * (size_t)c_stride * 2 + (size_t)(c >> 6) * 128 + 64 + (c & 63)];
+        l = __half2float(__half(__nv_cvt_fp8_to_halfraw(b, __NV_E4M3))) * (1.0f / (float)(1 << kFp8LoShift));
+    }
+    out[idx] = (__half2float(hi[o]) + l) * (1.0f / MSI_ACT_SCALE);
 }
 
-int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out, int W,
-                     int x_pad, cudaStream_t st) {
-    merge_activation_kernel<<<ceil_div(npix * C, 256), 256, 0, st>>>(hi, lo, npix, C, c_stride, out, W, x_pad);
+int merge_activation(const __half* hi, const __half* lo, const uint8_t* q8, long long npix, int C, int c_stride, float* out,
+                     int W, int x_pad, cudaStream_t st) {
+    MSI_CHECK_ARG(lo != nullptr || q8 != nullptr, "merge_activation: neither residual format is stored");
+    merge_activation_kernel<<<ceil_div(npix * C, 256), 256, 0, st>>>(hi, lo, q8, npix, C, c_stride, out, W, x_pad);
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

@@ -23,7 +23,8 @@ struct msi_net {
     // carve-out offsets (filled at create, turned into pointers at bind)
     struct Off {
         size_t w_f32, gamma, beta, bias, cbias, w_hi, w_lo;  // arena
-        size_t raw, partials, counter, stats, act_hi, act_lo;  // workspace
+        size_t raw, partials, counter, stats, act_hi, act_lo, act_q8;  // workspace
+        bool need_lo, need_q8;  // which residual formats the consumers of this layer's activation read
     };
     std::vector<Off> off;
     size_t in_hi_off = 0, in_lo_off = 0;
@@ -103,7 +104,8 @@ extern "C" int msi_net_create_ex(msi_net** out, int H, int W, int c_in, int c_ou
     MSI_CHECK_ARG(ngf >= 8 && ngf % 8 == 0, "net_create: ngf=%d must be a multiple of 8", ngf);
     MSI_CHECK_ARG(max_batch >= 1, "net_create: max_batch=%d", max_batch);
     MSI_CHECK_ARG(conv_impl == MSI_CONV_TCGEN05 || conv_impl == MSI_CONV_SIMT, "net_create: conv_impl=%d", conv_impl);
-    MSI_CHECK_ARG(precision == MSI_PREC_FP16X3 || precision == MSI_PREC_FP16, "net_create: precision=%d", precision);
+    MSI_CHECK_ARG(precision == MSI_PREC_FP16X3 || precision == MSI_PREC_FP16 || precision == MSI_PREC_FP16_FP8X,
+                  "net_create: precision=%d", precision);
     if (conv_impl == MSI_CONV_TCGEN05) {
         if (ngf % 64 != 0 || c_out % 16 != 0 || c_out > 256) {
             set_error("net_create: the tcgen05 back end needs ngf %% 64 == 0 and c_out %% 16 == 0, c_out <= 256 (got ngf=%d c_out=%d)", ngf, c_out);
@@ -135,6 +137,26 @@ extern "C" int msi_net_create_ex(msi_net** out, int H, int W, int c_in, int c_ou
     net->off.resize(kNumLayers);
     net->coord_rows_host.resize(kNumLayers);
 
+    // MSI_PREC_FP16_FP8X: the layers with an N tile of 128 form their cross terms in e4m3 and read the e4m3 copy of
+    // their inputs; the others (Cout = 64, the head) read the fp16 residual.  An activation stores what its consumers read.
+    std::vector<bool> layer_fp8x(kNumLayers, false), need_lo(kNumLayers + 1, false), need_q8(kNumLayers + 1, false);
+    {
+        auto act_of = [&](const char* scope) {
+            if (strcmp(scope, "input") == 0) return 0;
+            for (int j = 0; j < kNumLayers; ++j)
+                if (strcmp(kArch[j].scope, scope) == 0) return j + 1;
+            return -1;
+        };
+        for (int i = 0; i < kNumLayers; ++i) {
+            const int cout = (kArch[i].kind == kHead) ? c_out : ngf * kArch[i].mult;
+            layer_fp8x[i] = conv_impl == MSI_CONV_TCGEN05 && precision == MSI_PREC_FP16_FP8X && kArch[i].kind != kHead &&
+                            cout % 128 == 0;
+            for (int s = 0; s < kArch[i].nsrc; ++s) {
+                const int ai = act_of(kArch[i].src[s]);
+                (layer_fp8x[i] ? need_q8 : need_lo)[ai] = true;
+            }
+        }
+    }
     size_t a = 0, w = 0;
     const size_t B = (size_t)max_batch;
     net->in_hi_off = w;
@@ -185,6 +207,7 @@ extern "C" int msi_net_create_ex(msi_net** out, int H, int W, int c_in, int c_ou
             L.ncls = 1;
         }
         L.coord = (variant == MSI_NET_COORD);
+        L.fp8x = layer_fp8x[i];
         L.out_act = i + 1;
         ActBuf& o = net->acts[i + 1];
         o.H = L.Hout;
@@ -233,8 +256,12 @@ extern "C" int msi_net_create_ex(msi_net** out, int H, int W, int c_in, int c_ou
         const size_t n_act = (size_t)L.Hout * o.Wp * L.cout;  // wrap-padded rows
         f.act_hi = w;
         if (r.kind != kHead) w += align_up(B * n_act * sizeof(__half));
+        f.need_lo = need_lo[i + 1] || !need_q8[i + 1];   // (an activation nobody reads in e4m3 keeps the fp16 pair)
+        f.need_q8 = need_q8[i + 1];
         f.act_lo = w;
-        if (r.kind != kHead) w += align_up(B * n_act * sizeof(__half));
+        if (r.kind != kHead && f.need_lo) w += align_up(B * n_act * sizeof(__half));
+        f.act_q8 = w;
+        if (r.kind != kHead && f.need_q8) w += align_up(B * n_act * sizeof(__half));
 
         if (r.kind == kConv) {
             // nets.py:262-263: |sin(linspace(-pi/2, pi/2, H))| in float64, cast to float32
@@ -306,7 +333,8 @@ extern "C" int msi_net_bind(msi_net* net, void* workspace, size_t workspace_byte
         L.stats = (float2*)(net->ws + f.stats);
         if (L.kind != kHead) {
             net->acts[i + 1].hi = (__half*)(net->ws + f.act_hi);
-            net->acts[i + 1].lo = (__half*)(net->ws + f.act_lo);
+            net->acts[i + 1].lo = f.need_lo ? (__half*)(net->ws + f.act_lo) : nullptr;
+            net->acts[i + 1].q8 = f.need_q8 ? (uint8_t*)(net->ws + f.act_q8) : nullptr;
         }
         L.loaded = false;
     }
@@ -382,7 +410,9 @@ extern "C" int msi_net_forward(msi_net* net, const float* in_f32, const void* in
 // The head's epilogue can assemble the RGBA layers itself when the net is the `blend_psv` net of the tensor-core
 // back end: c_in = 6P PSV channels, c_out = 2L with L = P, fp16x3 operands, L = 32 or 64 (one N tile).
 extern "C" int msi_net_can_fuse_rgba(const msi_net* net) {
-    if (!net || !net->bound || net->conv_impl != MSI_CONV_TCGEN05 || net->precision != MSI_PREC_FP16X3) return 0;
+    if (!net || !net->bound || net->conv_impl != MSI_CONV_TCGEN05 ||
+        (net->precision != MSI_PREC_FP16X3 && net->precision != MSI_PREC_FP16_FP8X))
+        return 0;
     if (net->c_in != 3 * net->c_out) return 0;
     return conv_tc_can_fuse_rgba(net->layers[kNumLayers - 1]) ? 1 : 0;
 }
@@ -554,8 +584,8 @@ static int net_forward_impl(msi_net* net, const float* in_f32, const void* in_hi
                 if (cold && r >= 1) MSI_CUDA(cudaMemsetAsync(ev->flush, r, ev->flush_bytes, st));
                 if (ev && (r == 1 || (cold && r >= 1))) MSI_CUDA(cudaEventRecord(ev->at(i, 2, cold ? r - 1 : 0), st));
                 rc = ln_forward(L.raw, B, n_per, L.cout, L.gamma, L.beta, L.partials, L.n_partials, L.stats,
-                                net->acts[i + 1].hi, net->acts[i + 1].lo, /*stats_ready=*/tc, /*pdl=*/tc && !(cold && r >= 1), L.Wout,
-                                net->acts[i + 1].x_pad, st);
+                                net->acts[i + 1].hi, net->acts[i + 1].lo, net->acts[i + 1].q8, /*stats_ready=*/tc,
+                                /*pdl=*/tc && !(cold && r >= 1), L.Wout, net->acts[i + 1].x_pad, st);
                 if (rc != MSI_OK) return rc;
                 if (cold && r >= 1) MSI_CUDA(cudaEventRecord(ev->at(i, 3, r - 1), st));
             }
@@ -587,7 +617,7 @@ extern "C" int msi_net_read_activation(msi_net* net, const char* scope, int B, f
     const int ai = find_act(net, scope);
     MSI_CHECK_ARG(ai >= 0 && ai < kNumLayers, "net_read_activation: unknown or un-normalised scope '%s'", scope);
     const ActBuf& a = net->acts[ai];
-    return merge_activation(a.hi, a.lo, (long long)B * a.H * a.W, a.C, a.c_stride, out, a.W, a.x_pad,
+    return merge_activation(a.hi, a.lo, a.q8, (long long)B * a.H * a.W, a.C, a.c_stride, out, a.W, a.x_pad,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -9,6 +9,17 @@ namespace msi {
 
 enum LayerKind { kConv = 0, kDeconv = 1, kHead = 2 };
 
+// MSI_PREC_FP16_FP8X.  x * w ~= x_hi * w_hi (fp16 MMA) + x_hi8 * w_lo8 + x_lo8 * w_hi8 (ONE e4m3 MMA of twice the K):
+// the cross terms are ~2^-11 of the main term, so 4 significand bits carry them to ~2^-15 of the product.  The scales
+// pair up so that every product has the scale MSI_ACT_SCALE * MSI_WEIGHT_SCALE of the main term:
+//   x_hi8 = e4m3(x_hi * 2^-kFp8HiShift)   w_lo8 = e4m3(w_lo * 2^+kFp8HiShift)
+//   x_lo8 = e4m3(x_lo * 2^+kFp8LoShift)   w_hi8 = e4m3(w_hi * 2^-kFp8LoShift)
+// (x_hi = fp16(16 x) up to ~450 for |x| < 28 -> x_hi8 < 112; |x_lo| <= 2^-11 x_hi -> x_lo8 < 56; measured on the net:
+// max-abs 2.3e-4 on the prediction at 160 x 320 against 1.5e-5 for fp16x3 and 6.5e-3 for one fp16 pass,
+// scripts/exp_fp8_cross.py.)
+constexpr int kFp8HiShift = 2;
+constexpr int kFp8LoShift = 9;
+
 // persistent conv kernel: at most this many CTAs (B200 has 148 SMs); 4 statistic slots per CTA
 constexpr int kMaxPersistentCtas = 160;
 
@@ -16,7 +27,10 @@ constexpr int kMaxPersistentCtas = 160;
 // split into fp16 hi + lo, NHWC with channel stride c_stride (>= C, multiple of 64 for tcgen05).
 struct ActBuf {
     __half* hi = nullptr;
-    __half* lo = nullptr;
+    __half* lo = nullptr;     // fp16 residual (consumers on the fp16x3 product); may be null when only q8 is consumed
+    // MSI_PREC_FP16_FP8X: e4m3 copies for the cross terms, shaped like the fp16 tensor (2 bytes per channel): per pixel
+    // and 64-channel chunk, 64 bytes hi8 = e4m3(hi * 2^-kFp8HiShift) then 64 bytes lo8 = e4m3(lo * 2^kFp8LoShift)
+    uint8_t* q8 = nullptr;
     int H = 0, W = 0, C = 0, c_stride = 0;
     // MSI_NET_WRAP: rows are stored x_pad pixels wider on both sides (Wp = W + 2 * x_pad) and the pad
     // columns hold the circular wrap of the row, so a TMA box that leaves the image along x reads the
@@ -36,6 +50,7 @@ struct LayerPlan {
     int Hin, Win, Hout, Wout;
     int pad_t, pad_l;  // SAME padding before (conv)
     bool coord = true; // the 3x3 convs take an extra |sin(latitude)| input channel (msi_coord_train_net)
+    bool fp8x = false; // this layer forms its cross terms in e4m3 (MSI_PREC_FP16_FP8X and an N tile of 128)
     // arena (parameters)
     float* w_f32 = nullptr;   // TF layout as loaded
     float* gamma = nullptr;
@@ -128,14 +143,16 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st);
 
 // LayerNorm ---------------------------------------------------------------------------------
 int ln_partials_count(long long n_per_sample);
+// out_lo / out_q8: either may be null (the formats the consumers of this activation read)
 int ln_forward(const float* raw, int B, long long n_per_sample, int C, const float* gamma, const float* beta,
-               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo,
+               double2* partials, int n_partials, float2* stats, __half* out_hi, __half* out_lo, uint8_t* out_q8,
                bool stats_ready, bool pdl, int W, int x_pad, cudaStream_t st);
 // W / x_pad: row width and wrap padding of the fp16 tensor (x_pad = 0: dense rows)
 int split_input(const float* in, long long npix, int C, int c_stride, __half* hi, __half* lo, int W, int x_pad,
                 cudaStream_t st);
-int merge_activation(const __half* hi, const __half* lo, long long npix, int C, int c_stride, float* out, int W,
-                     int x_pad, cudaStream_t st);
+// lo == null: the residual is taken from the e4m3 copy q8 (~4 bits of it)
+int merge_activation(const __half* hi, const __half* lo, const uint8_t* q8, long long npix, int C, int c_stride, float* out,
+                     int W, int x_pad, cudaStream_t st);
 // dense fp16 hi/lo [rows, W, c_stride] -> wrap-padded [rows, W + 2 x_pad, c_stride]
 int wrap_copy(const __half* in_hi, const __half* in_lo, long long rows, int W, int c_stride, int x_pad, __half* out_hi,
               __half* out_lo, cudaStream_t st);

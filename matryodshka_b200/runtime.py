@@ -21,7 +21,8 @@ from ._lib import check, ptr, stream_ptr
 from .nets import ARCH
 
 _CONV_IMPL = {"tcgen05": _lib.CONV_TCGEN05, "simt": _lib.CONV_SIMT}
-_PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16}
+# "fp16_fp8x": fp16 main product + e4m3 cross terms on the N = 128 layers (2 MMA units per product instead of 3)
+_PRECISION = {"fp16x3": _lib.PREC_FP16X3, "fp16": _lib.PREC_FP16, "fp16_fp8x": _lib.PREC_FP16_FP8X}
 _VARIANT = {"coord": _lib.NET_COORD, "wrap": _lib.NET_WRAP}
 
 
