@@ -39,9 +39,21 @@ MIN_WARMUP = 3   # timing rule: at least 3 warm-up steps (both arms report the w
 REPEATS = 10     # the K-step timed region is repeated this many times inside one run; `value` is the median region
 
 
-def workload_string(W, H, P, batch, ngf):
-    """config.workload, the same string in both arms (the driver compares them)."""
-    return f"{W}x{H} ERP, {P}-sphere MSI, batch={batch}/GPU, ngf={ngf} (BASELINE.json configs[1])"
+def workload_string(W, H, P, batch, ngf, world=1):
+    """config.workload, the same string in both arms (the driver compares them).  Names the BASELINE.json config the
+    shape belongs to: [1] 640x320 / 32 spheres / batch 1 per GPU (the metric's config, any N); [2] 64 spheres, batch 8;
+    [3] 1280x640, batch 16 over 4 GPUs; [4] 640x320 video, batch 64 over 8 GPUs."""
+    if (W, H, P) == (640, 320, 64) and batch == 8:
+        cfg = "configs[2]"
+    elif (W, H, P) == (1280, 640, 32) and batch * world == 16:
+        cfg = "configs[3]"
+    elif (W, H, P) == (640, 320, 32) and batch * world == 64:
+        cfg = "configs[4]"
+    elif (W, H, P, batch) == (640, 320, 32, 1):
+        cfg = "configs[1]"
+    else:
+        cfg = "a shape outside configs"
+    return f"{W}x{H} ERP, {P}-sphere MSI, batch={batch}/GPU, ngf={ngf} (BASELINE.json {cfg})"
 
 
 def log(*a):
@@ -84,11 +96,15 @@ def conv_traffic(H, W, P, B, args):
         return None
     try:
         t = json.load(open(p))
+        t = t.get("by_precision", {}).get(args.precision, t if "workload" in t else None)
+        if t is None:
+            return None
         w = t["workload"]
         if (w["H"], w["W"], w["P"], w["precision"]) != (H, W, P, args.precision):
             return None
         return {"dram_bytes_per_step": t["dram_bytes_per_forward"] * B / w["B"], "unit": "B",
-                "source": "profiles/conv_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+                "algorithmic_bytes_note": "operands + outputs of the 18 conv launches, once each = 0.73 GB per frame",
+                "source": t.get("source", "profiles/conv_traffic.json")}
     except Exception:
         return None
 
@@ -309,7 +325,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(W, H, P, 1, ngf),
+        "config": {"workload": workload_string(W, H, P, args.batch, ngf, args.gpus),
+                   "frames_per_cpu_step": 1,
                    "warmup_frames_run": warm_frames, "steps_requested": args.steps,
                    "note": "oracle port of the reference path on host cores; the reference itself needs "
                            "Python 2.7 + TensorFlow 1.14 and cannot run here.  A step = one full frame (seconds on a "
@@ -591,7 +608,7 @@ def run_ours(args):
                       "fp16_fp8x": "f16 main product + e4m3 cross terms (f16x3 on the Cout = 64 layers), f32 accumulate",
                       "fp16": "f16 operands, f32 accumulate"}[args.precision] if args.conv_impl == "tcgen05" else "f32",
             "data": "synthetic",
-            "config": {"workload": workload_string(W, H, P, Bp, ngf),
+            "config": {"workload": workload_string(W, H, P, Bp, ngf, world),
                        "frames_per_step": world * Bp, "conv_impl": args.conv_impl, "precision": args.precision,
                        "timed_regions": {"repeats": REPEATS, "steps_each": K, "statistic": "median (max over ranks per repeat)",
                                          "device_ms_per_step_min_med_max": [min(dev_all) / K, dev_ms / K, max(dev_all) / K],
@@ -633,7 +650,7 @@ def main():
     ap.add_argument("--ngf", type=int, default=64)
     ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--conv-impl", default="tcgen05", choices=["tcgen05", "simt"])
-    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16", "fp16_fp8x"])
+    ap.add_argument("--precision", default="fp16_fp8x", choices=["fp16_fp8x", "fp16x3", "fp16"])
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (independent pipelines on own streams)")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
                     help="N > 1: how the rendered frames reach every rank (default: fused into the render kernel)")

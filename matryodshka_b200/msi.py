@@ -50,7 +50,7 @@ class MSIConfig:
     batch_size: int = 1
     # back-end selection (ours)
     conv_impl: str = "tcgen05"
-    precision: str = "fp16x3"
+    precision: str = "fp16_fp8x"
 
 
 def _matmul44_f32(a, b):

@@ -68,7 +68,7 @@ class NetEngine:
     _cache: Dict[tuple, "NetEngine"] = {}
 
     def __init__(self, weights, H, W, c_in, c_out, ngf=64, device="cuda", max_batch=1,
-                 conv_impl="tcgen05", precision="fp16x3", vscope="net", variant="coord"):
+                 conv_impl="tcgen05", precision="fp16_fp8x", vscope="net", variant="coord"):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.variant = variant
@@ -240,7 +240,7 @@ class MSIPipeline:
     """
 
     def __init__(self, weights, H=320, W=640, num_planes=32, ngf=64, batch=1, device="cuda",
-                 min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16x3",
+                 min_depth=1.0, max_depth=100.0, conv_impl="tcgen05", precision="fp16_fp8x",
                  img_dtype=torch.float32, use_graph=True, coord_net=True, which_color_pred="blend_psv",
                  static_rig=True, fuse_rgba=True):
         _lib.require_cuda()

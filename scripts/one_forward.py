@@ -7,7 +7,7 @@ from matryodshka_b200.runtime import NetEngine
 
 H, W, P, ngf, B = 320, 640, 32, 64, int(os.environ.get("B", "1"))
 wts = synth.net_weights(6 * P, 2 * P, ngf)
-eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, "cuda", max_batch=B, precision=os.environ.get("PREC", "fp16x3"))
+eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, "cuda", max_batch=B, precision=os.environ.get("PREC", "fp16_fp8x"))
 hi, lo = eng.input_buffers(B)
 hi.normal_(); lo.zero_()
 out = torch.empty((B, H, W, 2 * P), device="cuda")
