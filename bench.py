@@ -651,7 +651,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--conv-impl", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--precision", default="fp16_fp8x", choices=["fp16_fp8x", "fp16x3", "fp16"])
-    ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (independent pipelines on own streams)")
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (independent pipelines on own streams)")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
                     help="N > 1: how the rendered frames reach every rank (default: fused into the render kernel)")
     ap.add_argument("--no-graph", action="store_true")

@@ -6,8 +6,12 @@ the ``{variable name: ndarray}`` dict that ``NetEngine`` / ``MSI`` take (``net/c
 ``net/conv1_1/LayerNorm/gamma`` ... -- the names ARE the bundle keys).
 
 Format [TensorFlow 1.14, tensorflow/core/util/tensor_bundle + tensorflow/core/lib/io/table, restated
-from the published format; parity unpinned: no real checkpoint is available in this sandbox, the
-reader is tested against this module's own writer]:
+from the published format].  Parity: no TensorFlow binary and no TensorFlow-written checkpoint exist in this
+sandbox; the reader is pinned to tests/golden/tf_bundle/, a bundle assembled INDEPENDENTLY of this module
+(tests/golden/make_tf_bundle_fixture.py: protocol buffers serialized by the official protobuf runtime from the
+published tensor_bundle.proto and TensorBoard's generated TensorShapeProto / DataType / VersionDef, crc32c and its
+masking from TensorBoard's TFRecord code, the table container written after leveldb's table_format.md with
+TensorFlow's options), and to this module's own writer:
 
 * ``<prefix>.index``  a LevelDB-format sorted table, written WITHOUT compression
   (tensor_bundle.cc: ``options.compression = table::kNoCompression``):
@@ -212,10 +216,11 @@ def list_variables(prefix: str):
     return out
 
 
-def load_checkpoint(prefix: str, verify_data_crc: bool = False) -> Dict[str, np.ndarray]:
+def load_checkpoint(prefix: str, verify_data_crc: bool = False, name_prefix: str = None) -> Dict[str, np.ndarray]:
     """{variable name: ndarray} of the bundle ``<prefix>.index`` + ``<prefix>.data-*``.  The table
     blocks are always checksummed; ``verify_data_crc`` also checks every tensor (pure-Python crc32c:
-    ~10 s for the 68 MB of this net)."""
+    ~10 s for the 68 MB of this net).  ``name_prefix`` (e.g. ``"net/"``) materialises only the variables whose
+    name starts with it (plus ``global_step``): a training checkpoint carries two Adam slots per weight."""
     table = read_table(prefix + ".index")
     num_shards, endian = 1, 0
     for f, _, v in _proto_fields(table.get(b"", b"")):
@@ -229,6 +234,11 @@ def load_checkpoint(prefix: str, verify_data_crc: bool = False) -> Dict[str, np.
     out = {}
     for k, v in table.items():
         if k == b"":
+            continue
+        name = k.decode()
+        if name_prefix is not None and name != "global_step" and not name.startswith(name_prefix):
+            continue
+        if name_prefix is not None and re.search(r"/Adam(_1)?$", name):
             continue
         e = _parse_entry(v)
         if e["slices"]:
@@ -245,7 +255,7 @@ def load_checkpoint(prefix: str, verify_data_crc: bool = False) -> Dict[str, np.
             raise ValueError("%r: %d bytes for shape %s %s" % (k.decode(), e["size"], e["shape"], dt))
         if verify_data_crc and e["crc32c"] is not None and masked_crc32c(raw.tobytes()) != e["crc32c"]:
             raise ValueError("tensor %r: crc32c mismatch" % k.decode())
-        out[k.decode()] = np.frombuffer(raw.tobytes(), dtype=dt).reshape(e["shape"]).copy()
+        out[name] = np.array(np.frombuffer(raw, dtype=dt).reshape(e["shape"]))   # one copy, out of the mapping
     return out
 
 
@@ -340,7 +350,7 @@ def load_weights(path: str) -> Dict[str, np.ndarray]:
         prefix = latest_checkpoint(path)
         if prefix is None:
             raise FileNotFoundError("no 'checkpoint' file in %s" % path)
-        return load_checkpoint(prefix)
+        return load_checkpoint(prefix, name_prefix="net/")
     if path.endswith(".npz"):
         with np.load(path) as z:
             return {k: z[k] for k in z.files}

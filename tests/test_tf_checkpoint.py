@@ -1,6 +1,8 @@
 """matryodshka_b200.tf_checkpoint: checkpoint-v2 tensor bundles without TensorFlow (CPU only).
-The reader is exercised against the module's own writer (no real checkpoint exists in the sandbox:
-parity unpinned), plus known answers for the pieces that have them (crc32c, varints, table framing)."""
+The reader is pinned to tests/golden/tf_bundle/ -- a bundle assembled independently of the module (official protobuf
+runtime, TensorBoard's generated protos and crc32c; tests/golden/make_tf_bundle_fixture.py) -- and exercised against the
+module's own writer, plus known answers for the pieces that have them (crc32c, varints, table framing).  No
+TensorFlow-written file exists in the sandbox."""
 import os
 import struct
 
@@ -70,3 +72,57 @@ def test_npz_weights(tmp_path):
     np.savez(tmp_path / "weights.npz", **wts)
     got = tfc.load_weights(str(tmp_path / "weights.npz"))
     assert all(np.array_equal(got[k], wts[k]) for k in wts)
+
+
+# ---- the independently built bundle (tests/golden/tf_bundle/, written by tests/golden/make_tf_bundle_fixture.py) ----
+FIX = os.path.join(os.path.dirname(__file__), "golden", "tf_bundle")
+
+
+def _fixture_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_tf_bundle_fixture",
+                                                  os.path.join(os.path.dirname(__file__), "golden", "make_tf_bundle_fixture.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["model.ckpt-410000", "small_blocks.ckpt"])
+def test_reader_against_the_independent_bundle(name):
+    """Every tensor of the committed bundle (one 256 KB table block as TensorFlow writes it / many 512-byte blocks with
+    shortened index separators), data crc32c verified with OUR crc32c against TensorBoard's, values from the seed."""
+    want = _fixture_module().fixture_tensors()
+    got = tfc.load_checkpoint(os.path.join(FIX, name), verify_data_crc=True)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        v = np.asarray(v)
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    assert int(got["global_step"]) == 410000 and got["global_step"].dtype == np.int64
+    names = [n for n, _, _ in tfc.list_variables(os.path.join(FIX, name))]
+    assert names == sorted(want, key=lambda s: s.encode())
+    # the Saver's directory layout and the net/ filter the driver uses (Adam slots and optimizer scalars dropped)
+    assert tfc.latest_checkpoint(FIX) == os.path.join(FIX, "model.ckpt-410000")
+    w = tfc.load_weights(FIX)
+    assert set(w) == {k for k in want if k.startswith("net/") and not k.endswith(("/Adam", "/Adam_1"))} | {"global_step"}
+
+
+def test_the_fixture_script_reproduces_the_committed_bytes(tmp_path):
+    """Where TensorBoard / protobuf are importable (they are in this image) the builder script rewrites the committed
+    files bit for bit -- the fixture is not a hand-edited blob."""
+    pytest.importorskip("tensorboard")
+    m = _fixture_module()
+    t = m.fixture_tensors()
+    for name, bs in (("model.ckpt-410000", 262144), ("small_blocks.ckpt", 512)):
+        m.write_bundle(str(tmp_path / name), t, block_size=bs)
+        for ext in (".index", ".data-00000-of-00001"):
+            assert open(str(tmp_path / name) + ext, "rb").read() == open(os.path.join(FIX, name) + ext, "rb").read(), name + ext
+    # and our own writer produces a table our reader AND the fixture's independent protos agree on
+    tfc.save_checkpoint(str(tmp_path / "ours.ckpt"), {k: np.asarray(v) for k, v in t.items()})
+    Header, Entry = m.bundle_protos()
+    table = tfc.read_table(str(tmp_path / "ours.ckpt.index"))
+    h = Header.FromString(table[b""])
+    assert h.num_shards == 1 and h.endianness == 0 and h.version.producer == 1
+    e = Entry.FromString(table[b"net/conv1_2/weights"])
+    assert [d.size for d in e.shape.dim] == [3, 3, 5, 8] and e.size == 3 * 3 * 5 * 8 * 4 and e.dtype == 1
+    from tensorboard.compat.tensorflow_stub.pywrap_tensorflow import masked_crc32c as tb_crc
+    assert e.crc32c == tb_crc(np.asarray(t["net/conv1_2/weights"]).tobytes())
