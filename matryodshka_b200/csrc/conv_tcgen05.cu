@@ -47,6 +47,17 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, half the columns each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxDynSmem = 227 * 1024 - 4096;      // 227 KB minus this kernel's static shared memory
+// Shared memory the persistent conv CTAs leave FREE on their SM (MSI_CONV_SMEM_RESERVE, bytes; default 0), so that a
+// block of another frame's sweep kernel (12.3 KB) can be resident beside them (runtime.MSIFrameLanes).
+inline int smem_reserve() {
+    static int r = -1;
+    if (r < 0) {
+        const char* env = getenv("MSI_CONV_SMEM_RESERVE");
+        r = env ? atoi(env) : 0;
+        if (r < 0 || r > 64 * 1024) r = 0;
+    }
+    return r;
+}
 // __launch_bounds__ is given 512 threads although the kernels launch 320 / 352: that caps ptxas at
 // 128 registers per thread, which leaves a third of the register file to the kernels of the OTHER
 // frames in flight (runtime.MSIFrameLanes) so that they can co-reside with the persistent conv CTA
@@ -1725,7 +1736,7 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     // unit, 56 us as pairs vs 51 us; every layer with >= 8 slots per unit is 10-18 % faster as pairs).
     if (plan->pair && (p.chunks[0] + p.chunks[1]) * (ntaps / p.T) < 6) return MSI_ERR_UNSUPPORTED;
     const int w_slot = p.T * (plan->pair ? 1 : 2) * plan->n_tile * kBlockK * 2;  // pair: this CTA's half of the rows
-    const int budget = kMaxDynSmem - 1024 - p.a_stages * p.a_slot_bytes;
+    const int budget = kMaxDynSmem - smem_reserve() - 1024 - p.a_stages * p.a_slot_bytes;
     const int stage_bytes = kEpiWarps * 4096;  // one 32 x 32 float tile per epilogue warp
     {
         const char* env = getenv("MSI_CONV_STAGE");
@@ -1851,7 +1862,7 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     const int stage_bytes = (kATileBytes + plan->n_tile * kBlockK * 2) * (plan->split ? 2 : 1);
     // the head keeps room for the [128 pixels][n_tile] float tile of its fused RGBA epilogue
     const int rgba_tile_bytes = (L.kind == kHead) ? kBlockM * plan->n_tile * 4 : 0;
-    p.stages = (kMaxDynSmem - 1024 - rgba_tile_bytes) / stage_bytes;
+    p.stages = (kMaxDynSmem - smem_reserve() - 1024 - rgba_tile_bytes) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) {
         delete plan;

@@ -286,7 +286,12 @@ __device__ __forceinline__ void split_half2(float a, float b, __half2& hi, __hal
 // floor-mod wrap of sampling.resample (taps_in_range).  rgbx holds the images pre-scaled by
 // MSI_ACT_SCALE (exact: a power of two), so the staged values are the conv operand before the split.
 constexpr int kGatherGroups = 4;
-__global__ void __launch_bounds__(256) psv_gather_pair_kernel(PsvParams p, const float4* __restrict__ rgbx, int log2p) {
+// min blocks per SM = the register budget.  Measured (scripts/exp_ab.sh): 8 blocks (32 registers, taps loaded in pairs)
+// 75 us, 6 blocks 76, 4 blocks (all eight taps in flight) 80, unconstrained 115: occupancy beats per-thread ILP here
+#ifndef MSI_GATHER_MINBLOCKS
+#define MSI_GATHER_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, MSI_GATHER_MINBLOCKS) psv_gather_pair_kernel(PsvParams p, const float4* __restrict__ rgbx, int log2p) {
     __shared__ __align__(16) float stage[2][1536];
     const int P = p.P, W = p.W, H = p.H;
     const unsigned ppb = 256u >> log2p;
