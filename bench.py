@@ -56,8 +56,16 @@ def workload_string(W, H, P, batch, ngf, world=1):
     return f"{W}x{H} ERP, {P}-sphere MSI, batch={batch}/GPU, ngf={ngf} (BASELINE.json {cfg})"
 
 
+_T0 = time.perf_counter()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def phase(msg):
+    """Progress line on stderr (rank-tagged, seconds since start): a run that stalls is attributable from its log."""
+    log(f"[bench +{time.perf_counter() - _T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}")
 
 
 # Libraries (NCCL's version banner, for one) write to fd 1.  main() keeps the real stdout for the ONE JSON
@@ -361,7 +369,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     H, W, P, ngf, Bp = args.height, args.width, args.planes, args.ngf, args.batch
     K, Wm = args.steps, max(args.warmup, MIN_WARMUP)
@@ -376,6 +385,7 @@ def run_ours(args):
                           precision=args.precision, use_graph=not args.no_graph)
     lanes.set_inputs(ref, src, tgt_pos=tp)
     pipe = lanes.lanes[0]
+    phase(f"pipelines built: {n_lanes} lane(s), batch {Bp}, world {world}")
 
     def barrier():
         if world > 1:
@@ -387,7 +397,7 @@ def run_ours(args):
         for lane, g in zip(lanes.lanes, gathers):
             torch.cuda.synchronize(dev)
             g.barrier()
-            mine = g.frames[g.first_frame:g.first_frame + Bp]
+            mine = g.frames[rank * Bp:(rank + 1) * Bp]   # (first_frame counts from the start of the whole allocation)
             assert torch.equal(mine, lane.out["rgb_u8"]), "fused gather: own slot differs from the local frame"
             per_rank = g.frames.view(world, -1).float().mean(dim=1)
             assert bool((per_rank > 0).all()), "fused gather: a rank's slot is empty"
@@ -400,14 +410,31 @@ def run_ours(args):
     gather, gathers, collective = None, [], "none"
     if world > 1:
         if args.gather != "nccl":
-            try:
-                gathers = [FrameGather(Bp, H, W, dev, mode=args.gather) for _ in lanes.lanes]
+            # ONE symmetric allocation for all lanes (one rendezvous, one multicast object), set up under a time limit:
+            # if it cannot be had within 90 s on EVERY rank, all ranks use the NCCL all-gather instead
+            box = {}
+
+            def setup():
+                try:
+                    box["g"] = FrameGather(Bp, H, W, dev, mode=args.gather, slots=n_lanes)
+                except Exception as e:  # noqa: BLE001
+                    box["err"] = f"{type(e).__name__}: {e}"
+
+            phase("setting up the symmetric gathered buffer")
+            th = threading.Thread(target=setup, daemon=True)
+            th.start()
+            th.join(90.0)
+            ok = torch.tensor([1 if "g" in box else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                gathers = [box["g"].slot(k) for k in range(n_lanes)]
                 for lane, g in zip(lanes.lanes, gathers):
                     lane.attach_gather(g)
                 collective = ("fused into the render kernel: uint8 frames stored into every rank's gathered buffer, "
                               + gathers[0].mode + " (symmetric memory); barrier at the end of the timed region")
-            except Exception as e:  # noqa: BLE001
-                log(f"fused gather unavailable ({type(e).__name__}: {e}); using NCCL all_gather")
+            else:
+                log(f"fused gather unavailable on some rank ({box.get('err', 'timed out' if 'g' not in box else 'ok here')}); "
+                    "using NCCL all_gather")
                 gathers = []
         if not gathers:
             gather = lambda lane: all_gather_frames(lane.out["rgb_u8"], world)  # noqa: E731
@@ -438,11 +465,13 @@ def run_ours(args):
     launches_per_step = _lib.launch_count() - c0
     pipe.use_graph = was_graph
 
+    phase(f"collective: {collective}")
     lanes.fork()
     for _ in range(Wm * n_lanes):
         one_step()
     lanes.join()
     barrier()
+    phase("warm-up done")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -452,8 +481,10 @@ def run_ours(args):
     # times (a 20-step region is ~20 ms: one scheduling hiccup on one rank moves a single sample by percents) and
     # the line reports the median region, with min / max beside it
     dev_all = [timed(K, one_step) for _ in range(REPEATS)]
+    phase(f"device-resident regions done: median {statistics.median(dev_all) / K:.4f} ms/step")
     if gathers:
         check_gathered()
+        phase("gathered buffers checked")
     # the same K steps on ONE lane (one frame at a time), reported beside the headline for reference
     single_all = dev_all
     if n_lanes > 1:
@@ -481,6 +512,7 @@ def run_ours(args):
             last = lanes.collect()
         return last
 
+    phase("one-lane regions done")
     e2e_loop(2 * in_flight)
     e2e_all = []
     for _ in range(REPEATS):
@@ -490,6 +522,7 @@ def run_ours(args):
         barrier()
         e2e_all.append((time.perf_counter() - t0) * 1e3)
     assert torch.equal(last[0], pipe.out["rgb_u8"].cpu()), "e2e result differs from the device-resident result"
+    phase(f"end-to-end regions done: median {statistics.median(e2e_all) / K:.4f} ms/step")
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) ---------------
     if args.no_layer_profile:  # e.g. under `ncu` for the launch list: only the real steps' kernels
@@ -505,6 +538,7 @@ def run_ours(args):
                                                       cold_l2=True)
     stage_ms = None if args.no_layer_profile else pipe.stage_times(reps=5)
     clocks = sampler.stop() if rank == 0 else None
+    phase("per-kernel profile done")
 
     # max over ranks of every repeat (a region ends when the slowest rank ends), then the median repeat
     per_rank = None
@@ -660,6 +694,10 @@ def main():
                     help="skip the per-kernel timing pass (roofline numbers become NaN); for ncu launch lists")
     args = ap.parse_args()
     reserve_stdout_for_json()
+    # a stalled run dumps every thread's stack to stderr (and again every 120 s) instead of dying silently at the
+    # driver's timeout
+    import faulthandler
+    faulthandler.dump_traceback_later(180, repeat=True, file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -610,17 +610,22 @@ class FrameGather:
     -- so that no all-gather kernel (and no per-step rendezvous of the ranks) follows it.  Readers call
     ``barrier()`` before they look at ``frames`` and again before the producers may overwrite it.
 
+    ``slots`` > 1: ONE symmetric allocation (one rendezvous, one multicast object) carved into that many
+    independent gathered buffers, one per frame lane (``slot(k)``); a lane's render kernel addresses its
+    slot through ``first_frame``.
+
     mode: "auto" (multicast if available, else peer stores), "peer", "multicast".  Raises if symmetric
     memory cannot be set up (the caller then falls back to ``all_gather_frames`` = NCCL)."""
 
-    def __init__(self, B, H, W, device, group=None, mode="auto"):
+    def __init__(self, B, H, W, device, group=None, mode="auto", slots=1):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.B, self.H, self.W = B, H, W
+        self.B, self.H, self.W, self.slots = B, H, W, slots
         assert (H * W * 3) % 4 == 0
-        self.buf = symm_mem.empty(self.world * B * H * W * 3, dtype=torch.uint8, device=device)
+        per_slot = self.world * B * H * W * 3
+        self.buf = symm_mem.empty(slots * per_slot, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.peers_dev = int(self.hdl.buffer_ptrs_dev)
@@ -629,10 +634,23 @@ class FrameGather:
             raise _lib.MsiError("FrameGather: no multicast address on this fabric")
         self.multicast_ptr = mc if mode in ("auto", "multicast") else 0
         self.mode = "multimem.st (NVSwitch multicast)" if self.multicast_ptr else "peer stores"
-        self.frames = self.buf.view(self.world * B, H, W, 3)
+        self.all_frames = self.buf.view(slots, self.world * B, H, W, 3)
+        self.frames = self.all_frames[0]
         self.first_frame = self.rank * B
         torch.cuda.synchronize(device)
         self.barrier()
+
+    def slot(self, k):
+        """The k-th gathered buffer of this allocation, with the attributes a pipeline's render launch reads."""
+        if self.slots == 1 and k == 0:
+            return self
+        assert 0 <= k < self.slots
+        v = object.__new__(FrameGather)
+        v.__dict__.update(self.__dict__)
+        v.frames = self.all_frames[k]
+        v.first_frame = k * self.world * self.B + self.rank * self.B   # frame index inside the whole allocation
+        v.slots = 1
+        return v
 
     def barrier(self):
         """All ranks' stores issued before the barrier (on the current stream) are visible after it."""

@@ -61,6 +61,32 @@ def main():
         g.barrier()
         if rank == 0:
             print(f"FUSED_OK world={world} mode={g.mode}")
+    # one symmetric allocation carved into two gathered buffers (one per frame lane, runtime.FrameGather.slot)
+    try:
+        g2 = FrameGather(hi - lo, H, W, dev, slots=2)
+    except Exception as e:
+        g2 = None
+        if rank == 0:
+            print(f"FUSED_SKIP slots: {type(e).__name__}: {e}")
+    if g2 is not None:
+        pipes = []
+        for k in range(2):
+            pk = MSIPipeline(wts, H, W, P, ngf, batch=hi - lo, device=dev)
+            pk.attach_gather(g2.slot(k))
+            # lane 1 renders the frames in reversed order, so the two slots must differ
+            sel = slice(lo, hi) if k == 0 else slice(hi - 1, lo - 1 if lo > 0 else None, -1)
+            pk.set_inputs(ref[sel].copy(), src[sel].copy(), tgt_pos=tp[sel].copy())
+            pk.step()
+            pipes.append(pk)
+        torch.cuda.synchronize()
+        g2.barrier()
+        assert torch.equal(g2.slot(0).frames, rgb8), f"rank {rank}: slot 0 differs from the NCCL all-gather"
+        want1 = all_gather_frames(pipes[1].out["rgb_u8"], world)
+        assert torch.equal(g2.slot(1).frames, want1), f"rank {rank}: slot 1 differs"
+        assert not torch.equal(g2.slot(1).frames, g2.slot(0).frames)
+        g2.barrier()
+        if rank == 0:
+            print(f"FUSED_OK world={world} slots=2 mode={g2.mode}")
     dist.barrier()
     dist.destroy_process_group()
 
