@@ -174,6 +174,37 @@ class ClockSampler:
                 "power_w_max": max(power), "samples": len(sm)}
 
 
+def sustained_energy(gpu_index, lanes, one_step, frames_per_step, ms_per_step_hint, seconds=1.5):
+    """~`seconds` of back-to-back steps on this rank: frames/s, watts (NVML total-energy counter), mJ per frame and the
+    SM clock they settle at.  None when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1e3
+        chunk = max(1, int(50.0 / max(ms_per_step_hint, 1e-3)))   # ~50 ms of steps between host synchronisations
+        torch.cuda.synchronize()
+        e0, t0 = pynvml.nvmlDeviceGetTotalEnergyConsumption(h), time.perf_counter()
+        steps, clocks = 0, []
+        while time.perf_counter() - t0 < seconds:
+            lanes.fork()
+            for _ in range(chunk):
+                one_step()
+            lanes.join()
+            clocks.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))   # sampled while the chunk runs
+            torch.cuda.synchronize()
+            steps += chunk
+        e1, t1 = pynvml.nvmlDeviceGetTotalEnergyConsumption(h), time.perf_counter()
+        frames = steps * frames_per_step
+        return {"seconds": t1 - t0, "frames_per_s_per_gpu": frames / (t1 - t0), "watts": (e1 - e0) / 1e3 / (t1 - t0),
+                "power_limit_w": limit_w, "mJ_per_frame": (e1 - e0) / frames, "sm_mhz_median": statistics.median(clocks),
+                "note": "continuous steps on this GPU (no host synchronisation for ~50 ms at a time): at the power limit the "
+                        "SM clock drops and frames/s = power limit / joules per frame; the headline regions are K-step bursts"}
+    except Exception as e:  # pragma: no cover
+        log("energy block unavailable:", e)
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (the reference itself needs Python 2.7 + TF 1.14)
 # ------------------------------------------------------------------------------------------------
@@ -540,6 +571,17 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     phase("per-kernel profile done")
 
+    # ---- sustained region + energy (rank 0's GPU): the frame rate sits on the board's power cap ----------------------
+    # The K-step regions above are short bursts (tens of ms between host synchronisations); run continuously, the
+    # step draws the board's power limit and the SM clock settles below its maximum, so frames/s is bounded by JOULES
+    # PER FRAME.  This block reports that regime beside the headline: ~1.5 s of back-to-back steps, the NVML
+    # total-energy counter around them, SM clock sampled through NVML (scripts/exp_energy.py attributes the joules).
+    energy = None
+    if rank == 0 and not args.no_layer_profile and gather is None:   # (the NCCL all-gather form needs every rank in step)
+        energy = sustained_energy(local_rank, lanes, one_step, Bp, float(statistics.median(dev_all)) / K)
+        phase("sustained / energy region done")
+    barrier()
+
     # max over ranks of every repeat (a region ends when the slowest rank ends), then the median repeat
     per_rank = None
     if world > 1:
@@ -661,6 +703,7 @@ def run_ours(args):
                              f"{n_lanes} lane(s) x 2 batches in flight (H2D / compute / D2H on three streams per lane)"},
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,
+            "energy": energy,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "parity": parity,

@@ -106,7 +106,16 @@ struct TcParams {
     int a_stages;
     int T;               // taps per W ring slot
     int w_stages;
-    int halo_x0[4], halo_y0[4];  // per class: halo origin relative to the tile origin (min dx, min dy)
+    int halo_x0[4], halo_y0[4];  // per class (or parity plane): halo origin in INPUT pixels relative to (ox0, oy0) * in_stride
+    // Stride-2 convs: the input splits into 4 parity planes (y & 1, x & 1); input pixel 2 o + d = plane (d mod 2), plane
+    // pixel o + floor(d / 2), so every tap is again a row-shifted view of a dense halo tile -- of ITS parity plane.  A
+    // 64-channel chunk is therefore `vpar` = 4 halo tiles (TMA element stride 2), each serving the taps of one plane
+    // (4 + 2 + 2 + 1 for a 3x3 kernel); the taps are ordered plane by plane (taps[0], and so the packed weights).
+    // vpar = 1: one tile per chunk (stride 1, deconv classes).  `sel` below = parity plane (vpar = 4) or class.
+    int vpar;
+    int v_n[4];                  // taps served by the halo tile of `sel`
+    int v_off[4][9];             // smem row offset of every such tap inside the tile
+    int w_ntaps;                 // taps per (class, chunk) in the packed weights
     int stage_out;       // 1: the epilogue transposes its tiles through shared memory (coalesced stores)
     int x_off;           // added to every TMA x coordinate: the wrap padding of the source rows (MSI_NET_WRAP)
     // MSI_NET_WRAP deconvs: slim.layer_norm sees the FULL output of the VALID transposed conv over the
@@ -1043,8 +1052,8 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         s_launch = (blockIdx.x == 0) ? (int)atomicAdd((unsigned long long*)&p.trace[9 * kTraceRegion], 1ull) : -1;
         trace_g(p.trace, s_launch, 0);
     }
-    __shared__ __align__(8) uint64_t a_full_bar[2];
-    __shared__ __align__(8) uint64_t a_empty_bar[2];
+    __shared__ __align__(8) uint64_t a_full_bar[4];
+    __shared__ __align__(8) uint64_t a_empty_bar[4];
     __shared__ __align__(8) uint64_t w_full_bar[8];
     __shared__ __align__(8) uint64_t w_empty_bar[8];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -1066,10 +1075,10 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
 
     if (threadIdx.x < 36) {
         const int c = threadIdx.x / 9, t = threadIdx.x % 9;
-        const int ddx = p.taps[c].dx[t] - p.halo_x0[c], ddy = p.taps[c].dy[t] - p.halo_y0[c];
-        s_off[c][t] = (p.orient == 0) ? ddy * p.PF + ddx : ddx * p.PF + ddy;
-        if (t == 0) s_ntaps[c] = p.taps[c].n;
+        s_off[c][t] = p.v_off[c][t];
+        if (t == 0) s_ntaps[c] = p.v_n[c];
     }
+    const int vpar = p.vpar;
     const uint32_t afull0 = smem_u32(&a_full_bar[0]);
     const uint32_t aempty0 = smem_u32(&a_empty_bar[0]);
     const uint32_t wfull0 = smem_u32(&w_full_bar[0]);
@@ -1077,9 +1086,11 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]);
     const uint32_t tempty0 = smem_u32(&tmem_empty_bar[0]);
     if (threadIdx.x == 96) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(afull0 + 8u * s, 1);
             mbar_init(aempty0 + 8u * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8u * s, 1);
             mbar_init(tempty0 + 8u * s, PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues arrive on the leader
         }
@@ -1125,25 +1136,29 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             uint32_t phase = 0;
             for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
                 const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
-                const int hx = tc.ox0 + p.halo_x0[tc.cls] + p.x_off, hy = tc.oy0 + p.halo_y0[tc.cls];
-                const int cf = (p.orient == 0) ? hx : hy, cs = (p.orient == 0) ? hy : hx;
+                const int bx = tc.ox0 * p.in_stride + p.x_off, by = tc.oy0 * p.in_stride;
                 for (int ch = 0; ch < chunks_total; ++ch) {
-                    mbar_wait(aempty0 + 8u * stage, phase ^ 1u);
-                    trace_ev(p.trace, 4, tr_i++);
                     const bool second = ch >= chunks0;
-                    if (!PAIR) {
-                        mbar_expect_tx(afull0 + 8u * stage, a_tx);
-                        tma_load_5d(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
-                                    (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
-                    } else {
-                        // both CTAs' halos count on the leader's barrier, which the leader arms for both
-                        if (is_leader) mbar_expect_tx(afull0 + 8u * stage, 2u * a_tx);
-                        tma_load_5d_pair(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
-                                         (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
-                    }
-                    if (++stage == a_stages) {
-                        stage = 0;
-                        phase ^= 1u;
+                    for (int v = 0; v < vpar; ++v) {  // (stride 2: the halo tiles of the four parity planes)
+                        const int sel = (vpar > 1) ? v : tc.cls;
+                        const int hx = bx + p.halo_x0[sel], hy = by + p.halo_y0[sel];
+                        const int cf = (p.orient == 0) ? hx : hy, cs = (p.orient == 0) ? hy : hx;
+                        mbar_wait(aempty0 + 8u * stage, phase ^ 1u);
+                        trace_ev(p.trace, 4, tr_i++);
+                        if (!PAIR) {
+                            mbar_expect_tx(afull0 + 8u * stage, a_tx);
+                            tma_load_5d(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
+                                        (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                        } else {
+                            // both CTAs' halos count on the leader's barrier, which the leader arms for both
+                            if (is_leader) mbar_expect_tx(afull0 + 8u * stage, 2u * a_tx);
+                            tma_load_5d_pair(smem_base + (uint32_t)stage * a_slot_bytes, second ? &a1 : &a0, afull0 + 8u * stage,
+                                             (second ? ch - chunks0 : ch) * kBlockK, cf, cs, 0, tc.b);
+                        }
+                        if (++stage == a_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
                 }
             }
@@ -1156,7 +1171,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             uint32_t phase = 0;
             for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
                 const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
-                const int ntaps = s_ntaps[tc.cls];
+                const int ntaps = p.w_ntaps;
                 int kb = tc.cls * chunks_total * ntaps;
                 const int n_slots = chunks_total * (ntaps / T);
                 for (int sl = 0; sl < n_slots; ++sl, kb += T) {
@@ -1200,7 +1215,6 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         const int units_per_cls = p.units_per_col * p.n_tiles;
         for (int unit = cluster_id; unit < p.total_units; unit += n_ctas, ++local) {
             const int cls = (p.ncls > 1) ? unit / units_per_cls : 0;  // (a division only for the deconv classes)
-            const int slots_per_chunk = s_ntaps[cls] / T;
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
             // the epilogue has drained this accumulator (tested ahead, during the previous unit's last slot)
@@ -1211,7 +1225,11 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             const uint32_t next_tempty = tempty0 + 8u * (uint32_t)(acc ^ 1);
             const uint32_t next_tparity = ((uint32_t)((local + 1) >> 1) & 1u) ^ 1u;
             uint32_t accumulate = 0u;
-            for (int ch = 0; ch < chunks_total; ++ch) {
+            const int vchunks = chunks_total * vpar;  // halo tiles per unit (stride 2: four parity planes per chunk)
+            for (int vc = 0, v = 0; vc < vchunks; ++vc, v = (v + 1 == vpar) ? 0 : v + 1) {
+                const int sel = (vpar > 1) ? v : cls;
+                const int slots_per_chunk = s_ntaps[sel] / T;
+                const bool last_tile = vc == vchunks - 1;
                 if (!a_ready) mbar_wait(afull0 + 8u * a_stage, a_phase);
                 if (tr_chunk == 0 && leader) trace_g(p.trace, tr_launch, 3);
                 trace_ev(leader ? p.trace : nullptr, 5, tr_chunk++);
@@ -1225,7 +1243,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                 for (int sl = 0; sl < slots_per_chunk; ++sl) {
                     int off[T];
 #pragma unroll
-                    for (int t = 0; t < T; ++t) off[t] = s_off[cls][sl * T + t] * 8;
+                    for (int t = 0; t < T; ++t) off[t] = s_off[sel][sl * T + t] * 8;
                     const uint32_t cur = (uint32_t)w_stage;
                     if (!w_ready) mbar_wait(wfull0 + 8u * cur, w_phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1241,7 +1259,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                     w_ready = mbar_test_wait(wfull0 + 8u * w_stage, w_phase);
                     if (sl == slots_per_chunk - 1) {
                         a_ready = mbar_test_wait(afull0 + 8u * a_stage, a_phase);
-                        t_ready = (ch == chunks_total - 1) ? mbar_test_wait(next_tempty, next_tparity) : false;
+                        t_ready = last_tile ? mbar_test_wait(next_tempty, next_tparity) : false;
                     }
                     if (leader) {
                         trace_ev(p.trace, 0, tr_slot);
@@ -1283,13 +1301,13 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                             umma_commit(wempty0 + 8u * cur);
                             if (sl == slots_per_chunk - 1) {
                                 umma_commit(a_done_bar);
-                                if (ch == chunks_total - 1) umma_commit(tfull0 + 8u * acc);
+                                if (last_tile) umma_commit(tfull0 + 8u * acc);
                             }
                         } else {  // the slots and the accumulators of BOTH CTAs
                             umma_commit_pair(wempty0 + 8u * cur);
                             if (sl == slots_per_chunk - 1) {
                                 umma_commit_pair(a_done_bar);
-                                if (ch == chunks_total - 1) umma_commit_pair(tfull0 + 8u * acc);
+                                if (last_tile) umma_commit_pair(tfull0 + 8u * acc);
                             }
                         }
                         trace_ev(p.trace, 1, tr_slot);
@@ -1513,7 +1531,7 @@ int encode_w_map(CUtensorMap* m, const __half* base, int K, int cout, int ncls, 
 // 5-D activation map of the halo kernel: {C, fast, slow, hi|lo, B}, box {64, PF, PS, 2, 1}.  The hi
 // and lo tensors are two carve-outs of one workspace, so "lo" is "hi" at a constant byte offset.
 int encode_act_map5(CUtensorMap* m, const __half* hi, const __half* lo, int C, int W, int H, int B, int orient, int PF,
-                    int PS) {
+                    int PS, int estride) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -1529,8 +1547,9 @@ int encode_act_map5(CUtensorMap* m, const __half* hi, const __half* lo, int C, i
                           (cuuint64_t)B};
     cuuint64_t strides[4] = {orient == 0 ? row : img_row, orient == 0 ? img_row : row, (cuuint64_t)hl,
                              (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)PF, (cuuint32_t)PS, 2, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    // estride = 2 (stride-2 convs): every second pixel of the traversed 2 PF x 2 PS window = one parity plane's halo tile
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)(PF * estride), (cuuint32_t)(PS * estride), 2, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)hi, dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1693,6 +1712,19 @@ int launch_halo(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t st
     return MSI_OK;
 }
 
+// MSI_CONV_HALO_S2=1: the stride-2 convs (conv1_2, conv2_2, conv3_3) run on the halo kernel with four parity-plane halo
+// tiles per chunk (TcParams::vpar).  Built, parity-tested (tests/test_gpu_net.py::test_stride2_halo_matches_per_tap_kernel)
+// and measured on B200: 27.1 / 28.0 / 28.5 us against 25.9 / 27.3 / 25.1 us on the per-tap kernel -- no gain, so the
+// default stays off.  The pipeline trace (profiles/r2_trace_conv{1_2,3_3}_s2.log) shows why: the strided halo loads
+// complete ~4-5 K clocks after issue and the MMA loop runs at ~760 clocks per tap against 592 at the pipe's rate (per-SM
+// TMA ingest, ~50 B/clk, is the limit in both forms: these layers have one or two N tiles per pixel tile, so there is
+// little operand reuse to win), and 14 of the 26 us of a launch are fixed costs outside the MMA loop (first loads 4 us,
+// last epilogue 3.7 us, store drain + statistics 2.5 us, CTA skew + finalisation 3.5 us).
+bool stride2_halo_enabled() {
+    const char* env = getenv("MSI_CONV_HALO_S2");
+    return env && atoi(env) == 1;
+}
+
 // Halo-kernel plan: tile orientation, halo extents, ring sizes, 5-D / 4-D tensor maps.  Returns
 // MSI_ERR_UNSUPPORTED when the layer does not fit (the caller then uses the per-tap kernel).
 int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batch) {
@@ -1703,33 +1735,87 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     p.BW = p.orient == 0 ? 8 : 16;
     p.BH = p.orient == 0 ? 16 : 8;
     int ext_x = -1, ext_y = -1;
-    for (int c = 0; c < p.ncls; ++c) {
-        int minx = 1 << 20, maxx = -(1 << 20), miny = 1 << 20, maxy = -(1 << 20);
-        for (int t = 0; t < p.taps[c].n; ++t) {
-            minx = std::min(minx, p.taps[c].dx[t]);
-            maxx = std::max(maxx, p.taps[c].dx[t]);
-            miny = std::min(miny, p.taps[c].dy[t]);
-            maxy = std::max(maxy, p.taps[c].dy[t]);
+    const bool s2 = (L.kind == kConv && p.in_stride == 2);
+    p.vpar = s2 ? 4 : 1;
+    p.w_ntaps = p.taps[0].n;
+    int rel_x[4][9], rel_y[4][9];  // tap position inside the halo tile of its `sel` (class or parity plane), in tile pixels
+    if (s2) {
+        // input pixel 2 o + d = parity plane (d mod 2), plane pixel o + floor(d / 2)
+        if (plan->n_tile != 128 || p.ncls != 1 || p.taps[0].n > 9) return MSI_ERR_UNSUPPORTED;
+        const TapList src = p.taps[0];
+        int par[9], qx[9], qy[9];
+        int qminx = 1 << 20, qmaxx = -(1 << 20), qminy = 1 << 20, qmaxy = -(1 << 20);
+        for (int t = 0; t < src.n; ++t) {
+            const int px = ((src.dx[t] % 2) + 2) % 2, py = ((src.dy[t] % 2) + 2) % 2;
+            qx[t] = (src.dx[t] - px) / 2;
+            qy[t] = (src.dy[t] - py) / 2;
+            par[t] = py * 2 + px;
+            qminx = std::min(qminx, qx[t]);
+            qmaxx = std::max(qmaxx, qx[t]);
+            qminy = std::min(qminy, qy[t]);
+            qmaxy = std::max(qmaxy, qy[t]);
         }
-        p.halo_x0[c] = minx;
-        p.halo_y0[c] = miny;
-        const int ex = p.BW + maxx - minx, ey = p.BH + maxy - miny;
-        if (c > 0 && (ex != ext_x || ey != ext_y || p.taps[c].n != p.taps[0].n)) return MSI_ERR_UNSUPPORTED;
-        ext_x = ex;
-        ext_y = ey;
+        TapList dst = src;
+        int n = 0;
+        for (int v = 0; v < 4; ++v) {  // taps plane by plane: the order of the packed weights and of the W ring
+            p.v_n[v] = 0;
+            for (int t = 0; t < src.n; ++t) {
+                if (par[t] != v) continue;
+                dst.dx[n] = src.dx[t];
+                dst.dy[n] = src.dy[t];
+                dst.wtap[n] = src.wtap[t];
+                rel_x[v][p.v_n[v]] = qx[t] - qminx;
+                rel_y[v][p.v_n[v]] = qy[t] - qminy;
+                ++p.v_n[v];
+                ++n;
+            }
+            if (p.v_n[v] == 0) return MSI_ERR_UNSUPPORTED;
+            p.halo_x0[v] = 2 * qminx + (v & 1);
+            p.halo_y0[v] = 2 * qminy + (v >> 1);
+        }
+        p.taps[0] = dst;
+        ext_x = p.BW + qmaxx - qminx;
+        ext_y = p.BH + qmaxy - qminy;
+    } else {
+        for (int c = 0; c < p.ncls; ++c) {
+            int minx = 1 << 20, maxx = -(1 << 20), miny = 1 << 20, maxy = -(1 << 20);
+            for (int t = 0; t < p.taps[c].n; ++t) {
+                minx = std::min(minx, p.taps[c].dx[t]);
+                maxx = std::max(maxx, p.taps[c].dx[t]);
+                miny = std::min(miny, p.taps[c].dy[t]);
+                maxy = std::max(maxy, p.taps[c].dy[t]);
+            }
+            p.halo_x0[c] = minx;
+            p.halo_y0[c] = miny;
+            const int ex = p.BW + maxx - minx, ey = p.BH + maxy - miny;
+            if (c > 0 && (ex != ext_x || ey != ext_y || p.taps[c].n != p.taps[0].n)) return MSI_ERR_UNSUPPORTED;
+            ext_x = ex;
+            ext_y = ey;
+            p.v_n[c] = p.taps[c].n;
+            for (int t = 0; t < p.taps[c].n; ++t) {
+                rel_x[c][t] = p.taps[c].dx[t] - minx;
+                rel_y[c][t] = p.taps[c].dy[t] - miny;
+            }
+        }
+        for (int c = p.ncls; c < 4; ++c) p.v_n[c] = 0;
     }
     p.PF = p.orient == 0 ? ext_x : ext_y;
     p.PS = p.orient == 0 ? ext_y : ext_x;
+    for (int c = 0; c < 4; ++c)
+        for (int t = 0; t < 9; ++t)
+            p.v_off[c][t] = (t < p.v_n[c]) ? ((p.orient == 0) ? rel_y[c][t] * p.PF + rel_x[c][t] : rel_x[c][t] * p.PF + rel_y[c][t]) : 0;
     p.a_rows = p.PF * p.PS;
     p.a_slot_bytes = (2 * p.a_rows * 128 + 1023) / 1024 * 1024;
-    p.a_stages = 2;
+    // stride 2: four smaller tiles per chunk, the shortest serving ONE tap -- a third slot keeps the loads two tiles ahead
+    p.a_stages = s2 ? 3 : 2;
     const int ntaps = p.taps[0].n;
     p.T = (plan->n_tile == 64) ? ((ntaps % 3 == 0) ? 3 : 2) : 1;
     {
         const char* env = getenv("MSI_HALO_T");  // experiment: taps per W slot for the Cout = 64 layers
         if (env && plan->n_tile == 64 && atoi(env) == 1) p.T = 1;  // measured: 667 clk per tap (issue-thread bound) vs 572 for T = 3
     }
-    if (ntaps % p.T != 0 || p.PS > 256 || p.PF > 256) return MSI_ERR_UNSUPPORTED;
+    if (ntaps % p.T != 0 || p.PS > 256 || p.PF > 256 || p.PF * p.in_stride > 256 || p.PS * p.in_stride > 256) return MSI_ERR_UNSUPPORTED;
+    if (s2 && p.T != 1) return MSI_ERR_UNSUPPORTED;  // (the planes serve 4 + 2 + 2 + 1 taps)
     if (plan->pair && plan->n_tile == 64 && p.T == 1) return MSI_ERR_UNSUPPORTED;  // (no such instantiation)
     // A pair synchronises its two CTAs at every unit boundary (accumulator hand-over across the cluster): with only
     // a few W slots per unit that costs more than the halved weight traffic wins (measured: conv8_2, 3 slots per
@@ -1757,7 +1843,7 @@ int plan_halo(TcPlan* plan, const LayerPlan& L, const ActBuf* srcs, int max_batc
     int rc = MSI_OK;
     for (int s = 0; s < L.nsrc && rc == MSI_OK; ++s)
         rc = encode_act_map5(&plan->a_map[s][0], srcs[s].hi, plan->fp8x ? reinterpret_cast<const __half*>(srcs[s].q8) : srcs[s].lo,
-                             srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.orient, p.PF, p.PS);
+                             srcs[s].c_stride, srcs[s].Wp, srcs[s].H, max_batch, p.orient, p.PF, p.PS, p.in_stride);
     if (rc == MSI_OK && L.nsrc == 1) plan->a_map[1][0] = plan->a_map[0][0];
     const int nkb = L.ncls * (p.chunks[0] + p.chunks[1]) * ntaps;
     if (rc == MSI_OK) rc = encode_w_map4(&plan->w_map[0], L.w_hi, L.cout, nkb, plan->n_tile, p.T, plan->pair ? 1 : 2);
@@ -1881,7 +1967,7 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
     {
         const char* env = getenv("MSI_CONV_HALO");
         const bool want = !(env && atoi(env) == 0) && plan->split && plan->cl == 1 &&
-                          ((L.kind == kConv && L.stride == 1) || L.kind == kDeconv);
+                          ((L.kind == kConv && (L.stride == 1 || (L.stride == 2 && stride2_halo_enabled()))) || L.kind == kDeconv);
         if (want) {
             TcPlan saved = *plan;
             // CTA pairs (tcgen05 cta_group::2): the two CTAs of a cluster take two consecutive pixel tiles of a
@@ -1972,6 +2058,8 @@ int conv_tc_pack_weights(LayerPlan& L, const ActBuf* srcs, cudaStream_t st) {
         q.taps[0] = conv_taps(L);
     const long long total = (long long)L.ncls * L.cout * L.K;
     const TcPlan* plan = reinterpret_cast<const TcPlan*>(L.tc_plan);
+    if (plan && plan->halo)  // the halo plan's own tap order (stride 2: plane by plane)
+        for (int c = 0; c < plan->p.ncls; ++c) q.taps[c] = plan->p.taps[c];
     if (plan && plan->halo)
         pack_weights_halo_kernel<<<ceil_div(total, 256), 256, 0, st>>>(q, plan->p.chunks[0] + plan->p.chunks[1],
                                                                         plan->p.taps[0].n, plan->pair ? plan->n_tile : 0);
