@@ -740,9 +740,18 @@ def main():
     # a stalled run dumps every thread's stack to stderr (and again every 120 s) instead of dying silently at the
     # driver's timeout
     import faulthandler
-    faulthandler.dump_traceback_later(180, repeat=True, file=sys.stderr)
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "180")), repeat=True, file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
+    if os.environ.get("MSI_BEACON") == "1":
+        # debugging: a run that is still going after BENCH_BEACON_S seconds prints which conv launches have CTAs that
+        # never exited and the phase each of their roles reached (msi_debug_beacon_dump reads host-mapped memory)
+        def beacon_dump():
+            time.sleep(float(os.environ.get("BENCH_BEACON_S", "30")))
+            from matryodshka_b200 import _lib
+            _lib.load().msi_debug_beacon_dump()
+            sys.stderr.flush()
+        threading.Thread(target=beacon_dump, daemon=True).start()
     return run_ours(args)
 
 

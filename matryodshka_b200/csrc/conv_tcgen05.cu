@@ -126,6 +126,10 @@ struct TcParams {
     int grid_off;
     int stat_all;
     long long* trace;    // debugging: CTA 0 records clock64() of its pipeline events here (null = off)
+    // debugging (MSI_BEACON=1): every CTA posts the phase each of its roles has reached into host-mapped memory, slot
+    // (beacon_seq, blockIdx.x), so that a stalled launch can be read from the host while the GPU is stuck
+    long long* beacon;
+    int beacon_seq;
     // Head fused with the RGBA assembly (MSI.infer_msi `blend_psv`, msi.py:130-147): the epilogue turns a pixel's
     // L blend weights and L alphas into its L RGBA layers, reading the two PSV eyes of that pixel from the net's
     // own input operand (fp16 hi + lo).  rgba == null: the plain head (tanh -> pred).
@@ -392,10 +396,18 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's barrier
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kLeaderMask) : "memory");
 }
+// CTA pair: warp 1 of BOTH CTAs executes the allocation.  The allocation permit of a cta_group::2 allocation belongs to the
+// PAIR: it must not be relinquished until both CTAs' tcgen05.alloc have returned.  (Relinquishing right after the own
+// alloc, as the single-CTA kernels do, is a race: when the leader's relinquish overtakes the peer's alloc -- seen once
+// in ~8 runs of bench.py, never in isolation -- the peer's alloc blocks forever and the pair spins in its prologue, the
+// leader in barrier.cluster.wait; profiles/r2_hang_beacon.log.)  tmem_relinquish_pair() is therefore called after the
+// cluster barrier that follows the allocation.
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 template <int COLS>
@@ -405,6 +417,17 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t base) {
 __host__ __device__ constexpr uint32_t make_idesc_pair(int n) {  // M = 256 across the CTA pair
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
+
+// ---- debugging beacon (MSI_BEACON) ----
+constexpr int kBeaconSeqs = 1024, kBeaconCtas = 160, kBeaconSlots = 8;
+// slot 0: thread 0 (1 entered, 2 set-up + cluster sync done, 3 past griddepcontrol.wait, 9 at the final sync, 0 exited);
+// 1: MMA warp (1 in its loop, 2 done); 2: epilogue warp 0 (1 in its loop, 2 loop done, 3 statistics done);
+// 3: A producer (1 in its loop, 2 done); 4: W producer (1 in its loop, 2 done); 5: units finished by the MMA warp
+#define MSI_BEACON(p, k, v)                                                                                              \
+    do {                                                                                                                  \
+        if ((p).beacon != nullptr)                                                                                        \
+            ((volatile long long*)(p).beacon)[((size_t)(p).beacon_seq * kBeaconCtas + blockIdx.x) * kBeaconSlots + (k)] = (v); \
+    } while (0)
 
 // ---- debugging trace (MSI_TC_TRACE) ----
 constexpr int kTraceRegion = 1024, kTraceRegions = 10;
@@ -443,8 +466,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
     float s_sum = 0.f, s_sq = 0.f;
     int cur_b = -1;
     int local = 0;
+    if (ew == 0 && lane == 0) MSI_BEACON(p, 2, 1);
     for (int unit = cluster_id; unit < p.total_units; unit += n_clusters, ++local) {
         const TileCoord tc = decode_unit(p, unit, cta_rank, CL, N_TILE);
+        if (ew == 0 && lane == 0) MSI_BEACON(p, 6, (long long)local);
         if (p.do_stats && tc.b != cur_b) {
             if (cur_b >= 0) {
                 // this (frame, CTA, warp) slot belongs to this warp alone: plain read-modify-write
@@ -585,6 +610,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
         if (p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && local < 512) p.trace[6 * 1024 + 2 * local + 1] = clock64();
     }
     if (ew == 0 && lane == 0) trace_g(p.trace, tr_launch, 5);
+    if (ew == 0 && lane == 0) MSI_BEACON(p, 2, 2);
     if (p.do_stats) {
         if (cur_b >= 0) {
             const double ds = warp_sum_d((double)s_sum), dq = warp_sum_d((double)s_sq);
@@ -642,6 +668,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const int ew, c
         }
         if (ew == 0 && lane == 0) trace_g(p.trace, tr_launch, 6);
     }
+    if (ew == 0 && lane == 0) MSI_BEACON(p, 2, 3);
 }
 
 // Epilogue of the head fused with the RGBA assembly (replaces the `pred` round trip through HBM and the separate
@@ -812,6 +839,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     constexpr int kOffWLo = kOffWHi + kWTileBytes;
 
     extern __shared__ uint8_t smem_raw[];
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 1);
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -870,8 +898,10 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
     if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast targets them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 2);
     pdl_trigger();
     pdl_wait();  // everything above overlapped the previous kernel's tail; its output is read below
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 3);
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -1002,6 +1032,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
                                                   tmem_base, tfull0, tempty0, &s_is_last, s_red);
     }
 
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 9);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its smem / barriers
@@ -1009,6 +1040,7 @@ conv_igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap a0_hi, const __gri
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 0);
 }
 
 // ---- the halo kernel ---------------------------------------------------------------------------
@@ -1048,6 +1080,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ int s_launch;  // trace only
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 1);
     if (p.trace != nullptr && threadIdx.x == 0) {
         s_launch = (blockIdx.x == 0) ? (int)atomicAdd((unsigned long long*)&p.trace[9 * kTraceRegion], 1ull) : -1;
         trace_g(p.trace, s_launch, 0);
@@ -1106,25 +1139,31 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     }
     if (warp == 2 && lane == 0) prefetch_tmap(&wmap);
     if (warp == 1) {
+        if (lane == 0) MSI_BEACON(p, 1, 10);
         if (PAIR)
             tmem_alloc_pair<kTmemCols>(&tmem_base_smem);
         else
             tmem_alloc<kTmemCols>(&tmem_base_smem);
+        if (lane == 0) MSI_BEACON(p, 1, 11);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 12);
     if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
+    if (PAIR && warp == 1) tmem_relinquish_pair();  // both CTAs' allocations have returned (see tmem_alloc_pair)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
     const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // stride of the unit loops (clusters)
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 0);
     const int tr_launch = (p.trace != nullptr) ? s_launch : -1;
     if (threadIdx.x == 0) trace_g(p.trace, tr_launch, 1);
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 2);
     // Programmatic dependent launch: the set-up above and the first weight loads below overlap the
     // tail of the previous kernel (the weights do not depend on it); every other role waits here.
     pdl_trigger();
     if (warp != 2) pdl_wait();
     if (threadIdx.x == 0) trace_g(p.trace, tr_launch, 2);
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 3);
 
     if (warp == 0) {
         // =============================== A (halo) producer ===============================
@@ -1134,6 +1173,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             int tr_i = 0;
             int stage = 0;
             uint32_t phase = 0;
+            MSI_BEACON(p, 3, 1);
             for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
                 const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
                 const int bx = tc.ox0 * p.in_stride + p.x_off, by = tc.oy0 * p.in_stride;
@@ -1162,6 +1202,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                     }
                 }
             }
+            MSI_BEACON(p, 3, 2);
         }
     } else if (warp == 2) {
         // =============================== W producer ===============================
@@ -1169,6 +1210,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             int stage = 0;
             int tr_i = 0;
             uint32_t phase = 0;
+            MSI_BEACON(p, 4, 1);
             for (int unit = cluster_id; unit < p.total_units; unit += n_ctas) {
                 const TileCoord tc = decode_unit(p, unit, cta_rank, PAIR ? 2 : 1, N_TILE);
                 const int ntaps = p.w_ntaps;
@@ -1192,6 +1234,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                     }
                 }
             }
+            MSI_BEACON(p, 4, 2);
         }
     } else if (warp == 1 && (!PAIR || is_leader)) {
         // =============================== MMA issuer (PAIR: the leader CTA issues for both) ===============================
@@ -1212,9 +1255,11 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         int local = 0;
         int tr_slot = 0, tr_chunk = 0;
         trace_ev(leader ? p.trace : nullptr, 7, 1);
+        if (leader) MSI_BEACON(p, 1, 1);
         const int units_per_cls = p.units_per_col * p.n_tiles;
         for (int unit = cluster_id; unit < p.total_units; unit += n_ctas, ++local) {
             const int cls = (p.ncls > 1) ? unit / units_per_cls : 0;  // (a division only for the deconv classes)
+            if (leader) MSI_BEACON(p, 5, (long long)local);
             const int acc = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
             // the epilogue has drained this accumulator (tested ahead, during the previous unit's last slot)
@@ -1318,6 +1363,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
             }
         }
         if (leader) trace_g(p.trace, tr_launch, 4);
+        if (leader) MSI_BEACON(p, 1, 2);
     } else if (warp >= 3) {
         // =============================== epilogue (warps 3..10) ===============================
         const int row = (warp & 3) * 32 + lane;  // M index inside the tile: 8-pixel group = row / 8
@@ -1333,10 +1379,12 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
                                                                            tr_launch);
     }
 
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 9);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) trace_ev(p.trace, 7, 2);
     if (threadIdx.x == 0 && *(volatile int*)&s_is_last >= 0) trace_g(p.trace, tr_launch, 7);
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 10);
     if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch its memory / barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1345,6 +1393,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         else
             tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (threadIdx.x == 0) MSI_BEACON(p, 0, 0);
 }
 
 // e4m3 weight copies of MSI_PREC_FP16_FP8X (scales: net_internal.cuh)
@@ -1651,6 +1700,38 @@ int launch_tc_nt(const TcPlan* plan, const TcParams& p, bool pdl, cudaStream_t s
     if (plan->cl == 2)
         return plan->split ? launch_tc<N_TILE, 1, 2>(plan, p, pdl, st) : launch_tc<N_TILE, 0, 2>(plan, p, pdl, st);
     return plan->split ? launch_tc<N_TILE, 1, 1>(plan, p, pdl, st) : launch_tc<N_TILE, 0, 1>(plan, p, pdl, st);
+}
+
+// MSI_BEACON=1: host-mapped progress beacons of every conv launch (see MSI_BEACON in the kernels)
+long long* g_beacon_host = nullptr;
+long long* g_beacon_dev = nullptr;
+int g_beacon_next = 0;
+struct BeaconInfo {
+    char scope[16];
+    int grid, halo, pair, fp8x, n_tile;
+};
+BeaconInfo g_beacon_info[kBeaconSeqs];
+bool beacon_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* env = getenv("MSI_BEACON");
+        on = (env && atoi(env) == 1) ? 1 : 0;
+    }
+    return on == 1;
+}
+long long* beacon_buffer() {
+    if (!beacon_enabled()) return nullptr;
+    if (!g_beacon_host) {
+        const size_t bytes = sizeof(long long) * kBeaconSeqs * kBeaconCtas * kBeaconSlots;
+        if (cudaHostAlloc(&g_beacon_host, bytes, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&g_beacon_dev, g_beacon_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            g_beacon_host = g_beacon_dev = nullptr;
+            return nullptr;
+        }
+        memset(g_beacon_host, 0, bytes);
+    }
+    return g_beacon_dev;
 }
 
 long long* g_trace_dev = nullptr;
@@ -2015,6 +2096,38 @@ int conv_tc_plan_create(LayerPlan& L, const ActBuf* srcs, int max_batch, int pre
 
 }  // namespace msi
 
+// Debugging hook (not part of include/msi_b200.h): prints, for every conv launch slot whose CTAs have not all exited, the
+// phase each role of each such CTA has reached (MSI_BEACON=1; readable while the GPU is stuck).  Returns the number of
+// unfinished CTAs.
+extern "C" int msi_debug_beacon_dump(void) {
+    using namespace msi;
+    if (!g_beacon_host) {
+        fprintf(stderr, "[beacon] not enabled (MSI_BEACON=1)\n");
+        return -1;
+    }
+    int open_ctas = 0;
+    for (int seq = 0; seq < kBeaconSeqs; ++seq) {
+        const BeaconInfo& bi = g_beacon_info[seq];
+        int n_open = 0;
+        for (int c = 0; c < kBeaconCtas; ++c)
+            if (((volatile long long*)g_beacon_host)[((size_t)seq * kBeaconCtas + c) * kBeaconSlots] != 0) ++n_open;
+        if (n_open == 0) continue;
+        open_ctas += n_open;
+        fprintf(stderr, "[beacon] seq %d layer %s grid %d halo %d pair %d fp8x %d n_tile %d: %d CTAs not exited\n", seq, bi.scope,
+                bi.grid, bi.halo, bi.pair, bi.fp8x, bi.n_tile, n_open);
+        int shown = 0;
+        for (int c = 0; c < kBeaconCtas && shown < 24; ++c) {
+            volatile long long* b = (volatile long long*)g_beacon_host + ((size_t)seq * kBeaconCtas + c) * kBeaconSlots;
+            if (b[0] == 0) continue;
+            fprintf(stderr, "[beacon]    cta %3d: main %lld mma %lld (unit %lld) epi %lld (unit %lld) A-prod %lld W-prod %lld\n", c,
+                    b[0], b[1], b[5], b[2], b[6], b[3], b[4]);
+            ++shown;
+        }
+    }
+    fprintf(stderr, "[beacon] %d CTAs not exited in total\n", open_ctas);
+    return open_ctas;
+}
+
 // Debugging hook (not part of include/msi_b200.h): copies the pipeline-event clocks that CTA 0 of the
 // layer named by MSI_TC_TRACE recorded during its last launch.  Returns the number of entries.
 extern "C" int msi_debug_conv_trace(long long* host_out, int max_entries) {
@@ -2099,12 +2212,25 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
         p.psv_Wp = fuse->Wp;
         p.psv_xpad = fuse->x_pad;
     }
+    p.beacon = beacon_buffer();
+    p.beacon_seq = 0;
     const int cl = plan->cl;
     p.m_tiles = B * p.tiles_x * p.tiles_y;
     p.units_per_col = (p.m_tiles + cl - 1) / cl;
     p.total_units = p.ncls * p.n_tiles * p.units_per_col;
     int clusters = num_sms();
     if (clusters > kMaxPersistentCtas) clusters = kMaxPersistentCtas;
+    {
+        // experiment (MSI_CONV_MAX_CTAS): a conv launch takes at most this many SMs, so that two frames' conv kernels run side
+        // by side and one's start-up / last epilogue overlaps the other's MMA loop (runtime.MSIFrameLanes)
+        static int cap = -1;
+        if (cap < 0) {
+            const char* env = getenv("MSI_CONV_MAX_CTAS");
+            cap = env ? atoi(env) : 0;
+            if (cap < 2) cap = 0;
+        }
+        if (cap > 0 && clusters > cap) clusters = cap;
+    }
     clusters /= cl;
     if (clusters > p.total_units) clusters = p.total_units;
     const int grid = clusters * cl;
@@ -2112,6 +2238,18 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
     if (p.do_stats && grid * kEpiWarps > p.n_partials) {
         set_error("conv_tc_forward: %d partial slots < %d", p.n_partials, grid * kEpiWarps);
         return MSI_ERR_STATE;
+    }
+    if (p.beacon != nullptr) {
+        p.beacon_seq = g_beacon_next;
+        g_beacon_next = (g_beacon_next + 1) % kBeaconSeqs;
+        BeaconInfo& bi = g_beacon_info[p.beacon_seq];
+        strncpy(bi.scope, L.scope, sizeof(bi.scope) - 1);
+        bi.scope[sizeof(bi.scope) - 1] = 0;
+        bi.grid = grid;
+        bi.halo = plan->halo;
+        bi.pair = plan->pair;
+        bi.fp8x = plan->fp8x;
+        bi.n_tile = plan->n_tile;
     }
     int rc;
     const bool pdl = after_kernel && pdl_enabled();

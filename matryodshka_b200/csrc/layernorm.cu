@@ -83,8 +83,8 @@ ln_finalize_kernel(const double2* __restrict__ partials, int n_partials, long lo
     }
 }
 
-// thread = kLnUnroll x 8 consecutive channels; the raw tensor is read once (streaming load)
-static constexpr int kLnUnroll = 2;
+// thread = UNROLL x 8 consecutive channels; the raw tensor is read once (streaming load).  UNROLL = 4 for the large
+// tensors (more bytes in flight per thread), 2 for the small ones (more blocks: they are latency-bound)
 // Offset (in elements) of element `lin` of a dense [rows, W, C] tensor inside the wrap-padded
 // [rows, W + 2 x_pad, C] layout, and the offsets of its wrap copies (or -1): column x < x_pad is
 // repeated right of the image, column x >= W - x_pad left of it (nets.py:288-295 wrap_pad).
@@ -113,23 +113,48 @@ __device__ __forceinline__ size_t q8_offset(size_t e, int C) {
     return pix * (size_t)C * 2 + (size_t)(c >> 6) * 128 + (c & 63);
 }
 
-template <bool WRAP>
+template <bool WRAP, int UNROLL>
 __global__ void __launch_bounds__(256)
-ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, const float2* __restrict__ stats,
+ln_apply_kernel(const float* raw, long long n_per_sample, int C, const float2* stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out_hi,
                 __half* __restrict__ out_lo, uint8_t* __restrict__ out_q8, int W, int x_pad) {
+    // `raw` and `stats` are written by the PREVIOUS kernel, which may still be running when this one starts
+    // (programmatic dependent launch): they are deliberately not `const __restrict__` -- that would license the compiler
+    // to treat them as read-only for the kernel's lifetime and hoist their loads above griddepcontrol.wait (it did, with
+    // `stats`: LayerNorm then ran on the zeroed statistics of a conv kernel that had not finished) -- and the statistics
+    // are read with a volatile asm load, which cannot move across the wait.
     // programmatic dependent launch: let the next conv kernel set itself up, then wait for the conv
     // kernel that produced `raw` and `stats` (no-ops when launched without the attribute)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.y;
-    const float2 st = stats[b];
-    // kLnUnroll groups of 8 elements per thread, all loads issued before the first use
-    long long idx[kLnUnroll];
-    float4 v0[kLnUnroll], v1[kLnUnroll];
+    float2 st;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(st.x), "=f"(st.y) : "l"(stats + b) : "memory");
+    // A thread's 8 channels are the same for all of its groups when a block's 2048 elements are whole pixels
+    // (C divides 2048: every ngf that is a power of two): scale and shift are then formed once per thread
+    const bool fixed_c = (2048 % C) == 0;
+    float inv[8], sh[8];
+    auto load_affine = [&](int c0) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int g = 0; g < kLnUnroll; ++g) {
-        idx[g] = (((long long)blockIdx.x * kLnUnroll + g) * 256 + threadIdx.x) * 8;
+        for (int q = 0; q < 8; ++q) {
+            inv[q] = st.y * gm[q];
+            sh[q] = bt[q] - st.x * inv[q];
+        }
+    };
+    const int c_fixed = (int)((threadIdx.x * 8u) % (unsigned)C);
+    if (fixed_c) load_affine(c_fixed);
+    // UNROLL groups of 8 elements per thread, all loads issued before the first use
+    long long idx[UNROLL];
+    float4 v0[UNROLL], v1[UNROLL];
+#pragma unroll
+    for (int g = 0; g < UNROLL; ++g) {
+        idx[g] = (((long long)blockIdx.x * UNROLL + g) * 256 + threadIdx.x) * 8;
         if (idx[g] < n_per_sample) {
             const size_t off = (size_t)b * n_per_sample + idx[g];
             v0[g] = __ldcs(reinterpret_cast<const float4*>(raw + off));
@@ -137,30 +162,29 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
         }
     }
 #pragma unroll
-    for (int g = 0; g < kLnUnroll; ++g) {
+    for (int g = 0; g < UNROLL; ++g) {
         if (idx[g] >= n_per_sample) continue;
-        const int c0 = (int)(idx[g] % C);
         const size_t off = (size_t)b * n_per_sample + idx[g];
+        const int c0 = fixed_c ? c_fixed : (int)(idx[g] % C);
+        if (!fixed_c) load_affine(c0);
+        // (the q8 tensor: chunk c0 / 64 of the pixel holds [hi8 x 64 | lo8 x 64]; no division: the pixel base is off - c0)
+        const size_t q8_in_pix = (size_t)(c0 >> 6) * 128 + (size_t)(c0 & 63);
         const float x[8] = {v0[g].x, v0[g].y, v0[g].z, v0[g].w, v1[g].x, v1[g].y, v1[g].z, v1[g].w};
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        __align__(16) __half hi[8];
-        __align__(16) __half lo[8];
+        __align__(16) __half2 hi[4];
+        __align__(16) __half2 lo[4];
         float hf[8], lf[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float inv = st.y * gm[q];
-            const float sh = bt[q] - st.x * inv;
-            float y = x[q] * inv + sh;
-            y = fmaxf(y, 0.f) * MSI_ACT_SCALE;
-            hi[q] = __float2half_rn(y);
-            hf[q] = __half2float(hi[q]);
-            lf[q] = y - hf[q];
-            lo[q] = __float2half_rn(lf[q]);
+        for (int q = 0; q < 8; q += 2) {
+            // (same roundings as the scalar form: y -> fp16 hi, residual y - hi -> fp16 lo; packed converts)
+            const float y0 = fmaxf(x[q] * inv[q] + sh[q], 0.f) * MSI_ACT_SCALE;
+            const float y1 = fmaxf(x[q + 1] * inv[q + 1] + sh[q + 1], 0.f) * MSI_ACT_SCALE;
+            hi[q >> 1] = __floats2half2_rn(y0, y1);
+            const float2 h2 = __half22float2(hi[q >> 1]);
+            hf[q] = h2.x;
+            hf[q + 1] = h2.y;
+            lf[q] = y0 - h2.x;
+            lf[q + 1] = y1 - h2.y;
+            lo[q >> 1] = __floats2half2_rn(lf[q], lf[q + 1]);
         }
         uint2 h8 = make_uint2(0u, 0u), l8 = make_uint2(0u, 0u);
         if (out_q8 != nullptr) {
@@ -174,7 +198,7 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
             *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(hi);
             if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
             if (out_q8 != nullptr) {
-                uint8_t* q = out_q8 + q8_offset(off, C);
+                uint8_t* q = out_q8 + (off - (size_t)c0) * 2 + q8_in_pix;
                 *reinterpret_cast<uint2*>(q) = h8;
                 *reinterpret_cast<uint2*>(q + 64) = l8;
             }
@@ -184,7 +208,7 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
             *reinterpret_cast<uint4*>(out_hi + m) = *reinterpret_cast<const uint4*>(hi);
             if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + m) = *reinterpret_cast<const uint4*>(lo);
             if (out_q8 != nullptr) {
-                uint8_t* q = out_q8 + q8_offset((size_t)m, C);
+                uint8_t* q = out_q8 + ((size_t)m - (size_t)c0) * 2 + q8_in_pix;
                 *reinterpret_cast<uint2*>(q) = h8;
                 *reinterpret_cast<uint2*>(q + 64) = l8;
             }
@@ -192,7 +216,7 @@ ln_apply_kernel(const float* __restrict__ raw, long long n_per_sample, int C, co
                 *reinterpret_cast<uint4*>(out_hi + cp) = *reinterpret_cast<const uint4*>(hi);
                 if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + cp) = *reinterpret_cast<const uint4*>(lo);
                 if (out_q8 != nullptr) {
-                    uint8_t* q = out_q8 + q8_offset((size_t)cp, C);
+                    uint8_t* q = out_q8 + ((size_t)cp - (size_t)c0) * 2 + q8_in_pix;
                     *reinterpret_cast<uint2*>(q) = h8;
                     *reinterpret_cast<uint2*>(q + 64) = l8;
                 }
@@ -215,8 +239,10 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
         ln_finalize_kernel<<<B, 256, 0, st>>>(partials, np, n_per_sample, stats);
         MSI_LAUNCH_CHECK();
     }
+    // 4 groups per thread where there are enough blocks to fill the GPU several times over, else 2
+    const int unroll = (n_per_sample * B >= (4ll << 20)) ? 4 : 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ceil_div(n_per_sample, 256 * 8 * kLnUnroll), B);
+    cfg.gridDim = dim3(ceil_div(n_per_sample, 256 * 8 * unroll), B);
     cfg.blockDim = dim3(256);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -224,12 +250,10 @@ int ln_forward(const float* raw, int B, long long n_per_sample, int C, const flo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && stats_ready && pdl_enabled()) ? 1 : 0;
-    if (x_pad > 0)
-        MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<true>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
-                                    out_hi, out_lo, out_q8, W, x_pad));
-    else
-        MSI_CUDA(cudaLaunchKernelEx(&cfg, ln_apply_kernel<false>, raw, n_per_sample, C, (const float2*)stats, gamma, beta,
-                                    out_hi, out_lo, out_q8, W, x_pad));
+    auto kern = (x_pad > 0) ? (unroll == 4 ? ln_apply_kernel<true, 4> : ln_apply_kernel<true, 2>)
+                            : (unroll == 4 ? ln_apply_kernel<false, 4> : ln_apply_kernel<false, 2>);
+    MSI_CUDA(cudaLaunchKernelEx(&cfg, kern, raw, n_per_sample, C, (const float2*)stats, gamma, beta, out_hi, out_lo, out_q8, W,
+                                x_pad));
     MSI_LAUNCH_CHECK();
     return MSI_OK;
 }

@@ -11,7 +11,12 @@ eng = NetEngine(wts, H, W, 6 * P, 2 * P, ngf, "cuda", max_batch=B, precision=os.
 hi, lo = eng.input_buffers(B)
 hi.normal_(); lo.zero_()
 out = torch.empty((B, H, W, 2 * P), device="cuda")
+rgba = torch.empty((B, H, W, P, 4), device="cuda")
+fused = eng.can_fuse_rgba and os.environ.get("FUSED", "1") != "0"   # the head as the pipeline runs it: fused RGBA assembly
 for _ in range(int(os.environ.get("N", "2"))):
-    eng.forward(hi_lo=(hi, lo), out=out)
+    if fused:
+        eng.forward_rgba(hi_lo=(hi, lo), out=rgba)
+    else:
+        eng.forward(hi_lo=(hi, lo), out=out)
 torch.cuda.synchronize()
-print("ok", bool(torch.isnan(out).any()))
+print("ok", "fused head" if fused else "plain head", bool(torch.isnan(rgba if fused else out).any()))

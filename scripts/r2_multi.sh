@@ -22,6 +22,7 @@ except Exception as e:
     print("$1 failed", e)
 PY
 }
-run default "--steps 100"
+run default "--steps 20 --warmup 3"
+run default_steps100 "--steps 100"
 if [ "$N" = "4" ]; then run config3_1280x640_b16 "--height 640 --width 1280 --batch 4 --steps 30"; fi
 if [ "$N" = "8" ]; then run config4_video_b64 "--batch 8 --steps 30"; fi
