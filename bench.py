@@ -63,9 +63,47 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Stall guard.  A measurement that stops making progress (a stuck GPU kernel, a rank that never reaches a collective) must
+# not cost the whole run: phase() stamps the time of the last progress; a watchdog thread (start_stall_guard) that sees no
+# progress for BENCH_STALL_S seconds has rank 0 print the line assembled from what WAS measured (marked "partial", with the
+# phase it stalled in) and ends the process (exit code 0 if the headline value is in that line, else 3).
+_STALL = {"t": time.time(), "phase": "start", "fallback": None, "armed": False}
+
+
 def phase(msg):
     """Progress line on stderr (rank-tagged, seconds since start): a run that stalls is attributable from its log."""
+    _STALL["t"], _STALL["phase"] = time.time(), msg
     log(f"[bench +{time.perf_counter() - _T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}")
+
+
+def stall_guard_tick(now=None, limit=None, exit_fn=os._exit):
+    """One check of the stall guard (separate from the thread so that it can be tested without a GPU).  Returns True when
+    it fired."""
+    now = time.time() if now is None else now
+    limit = float(os.environ.get("BENCH_STALL_S", "150")) if limit is None else limit
+    if not _STALL["armed"] or now - _STALL["t"] <= limit:
+        return False
+    why = f"no progress for {now - _STALL['t']:.0f} s after: {_STALL['phase']}"
+    log(f"[bench] STALLED ({why}); ending the run")
+    have = _STALL["fallback"] is not None and _STALL["fallback"].get("value") is not None
+    if int(os.environ.get("RANK", "0")) == 0:
+        line = dict(_STALL["fallback"] or {"metric": METRIC, "value": None, "unit": UNIT, "higher_is_better": True})
+        line["partial"] = f"stalled: {why}; only what was measured before the stall is reported"
+        emit(line)
+    _STALL["armed"] = False
+    # exit code 0 when the headline was measured (the line says `partial`), 3 when there is nothing to report
+    exit_fn(0 if have else 3)
+    return True
+
+
+def start_stall_guard():
+    _STALL["t"], _STALL["armed"] = time.time(), True
+
+    def loop():
+        while True:
+            time.sleep(2.0)
+            stall_guard_tick()
+    threading.Thread(target=loop, daemon=True).start()
 
 
 # Libraries (NCCL's version banner, for one) write to fd 1.  main() keeps the real stdout for the ONE JSON
@@ -405,6 +443,27 @@ def run_ours(args):
 
     H, W, P, ngf, Bp = args.height, args.width, args.planes, args.ngf, args.batch
     K, Wm = args.steps, max(args.warmup, MIN_WARMUP)
+    start_stall_guard()
+
+    def reduce_max(xs):
+        """Max over ranks of every repeat (a region ends when the slowest rank ends)."""
+        if world == 1:
+            return list(xs)
+        t = torch.tensor(xs, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def fallback_line(dev_red, e2e_red=None):
+        """The line as far as it is known (stall guard): the headline from the device-resident regions, e2e when measured."""
+        frames = world * Bp * K
+        d = statistics.median(dev_red)
+        return {"metric": METRIC, "value": frames / (d * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": d / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": workload_string(W, H, P, Bp, ngf, world), "frames_per_step": world * Bp,
+                           "precision": args.precision, "frames_in_flight": max(1, args.lanes)},
+                "e2e": None if e2e_red is None else {"value": frames / (statistics.median(e2e_red) * 1e-3), "unit": UNIT,
+                                                      "ms_per_step": statistics.median(e2e_red) / K}}
     seed = 8964 + rank
     ref, src = synth.ods_pair(Bp, H, W, seed)
     wts = synth.net_weights(6 * P, 2 * P, ngf, 8964)
@@ -513,6 +572,9 @@ def run_ours(args):
     # the line reports the median region, with min / max beside it
     dev_all = [timed(K, one_step) for _ in range(REPEATS)]
     phase(f"device-resident regions done: median {statistics.median(dev_all) / K:.4f} ms/step")
+    dev_own = list(dev_all)
+    dev_red = reduce_max(dev_all)
+    _STALL["fallback"] = fallback_line(dev_red)
     if gathers:
         check_gathered()
         phase("gathered buffers checked")
@@ -554,6 +616,9 @@ def run_ours(args):
         e2e_all.append((time.perf_counter() - t0) * 1e3)
     assert torch.equal(last[0], pipe.out["rgb_u8"].cpu()), "e2e result differs from the device-resident result"
     phase(f"end-to-end regions done: median {statistics.median(e2e_all) / K:.4f} ms/step")
+    e2e_own = list(e2e_all)
+    e2e_red = reduce_max(e2e_all)
+    _STALL["fallback"] = fallback_line(dev_red, e2e_red)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) ---------------
     if args.no_layer_profile:  # e.g. under `ncu` for the launch list: only the real steps' kernels
@@ -571,30 +636,15 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     phase("per-kernel profile done")
 
-    # ---- sustained region + energy (rank 0's GPU): the frame rate sits on the board's power cap ----------------------
-    # The K-step regions above are short bursts (tens of ms between host synchronisations); run continuously, the
-    # step draws the board's power limit and the SM clock settles below its maximum, so frames/s is bounded by JOULES
-    # PER FRAME.  This block reports that regime beside the headline: ~1.5 s of back-to-back steps, the NVML
-    # total-energy counter around them, SM clock sampled through NVML (scripts/exp_energy.py attributes the joules).
-    energy = None
-    if rank == 0 and not args.no_layer_profile and gather is None:   # (the NCCL all-gather form needs every rank in step)
-        energy = sustained_energy(local_rank, lanes, one_step, Bp, float(statistics.median(dev_all)) / K)
-        phase("sustained / energy region done")
-    barrier()
-
     # max over ranks of every repeat (a region ends when the slowest rank ends), then the median repeat
     per_rank = None
     if world > 1:
-        def max_over_ranks(xs):
-            t = torch.tensor(xs, device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return [float(v) for v in t]
-        mine = torch.tensor([statistics.median(dev_all), statistics.median(e2e_all)], device=dev, dtype=torch.float64)
+        mine = torch.tensor([statistics.median(dev_own), statistics.median(e2e_own)], device=dev, dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = {"device_ms_per_step": [round(float(a[0]) / K, 5) for a in allr],
                     "e2e_ms_per_step": [round(float(a[1]) / K, 5) for a in allr]}
-        dev_all, e2e_all, single_all = max_over_ranks(dev_all), max_over_ranks(e2e_all), max_over_ranks(single_all)
+    dev_all, e2e_all, single_all = dev_red, e2e_red, reduce_max(single_all)
     dev_ms, e2e_ms, single_ms = statistics.median(dev_all), statistics.median(e2e_all), statistics.median(single_all)
 
     if rank == 0:
@@ -703,11 +753,23 @@ def run_ours(args):
                              f"{n_lanes} lane(s) x 2 batches in flight (H2D / compute / D2H on three streams per lane)"},
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,
-            "energy": energy,
+            "energy": None,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "parity": parity,
         }
+        # ---- sustained region + energy: the frame rate sits on the board's power limit ------------------------------------
+        # The K-step regions above are short bursts (tens of ms between host synchronisations); run continuously, the step
+        # draws the board's power limit and the SM clock settles below its maximum, so frames/s is bounded by JOULES PER
+        # FRAME.  This block reports that regime beside the headline: ~1 s of back-to-back steps, the NVML total-energy
+        # counter around them, SM clock sampled through NVML (scripts/exp_energy.py attributes the joules).  It runs last
+        # and on one GPU only: the complete line is already the stall guard's fallback, so a stall here costs only this key.
+        _STALL["fallback"] = line
+        phase("line assembled")
+        if world == 1 and not args.no_layer_profile:
+            line["energy"] = sustained_energy(local_rank, lanes, one_step, Bp, dev_ms / K, seconds=1.0)
+            phase("sustained / energy region done")
+        _STALL["armed"] = False
         emit(line)
     if world > 1:
         dist.barrier()

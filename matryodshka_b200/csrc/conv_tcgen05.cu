@@ -396,19 +396,17 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's barrier
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kLeaderMask) : "memory");
 }
-// CTA pair: warp 1 of BOTH CTAs executes the allocation.  The allocation permit of a cta_group::2 allocation belongs to the
-// PAIR: it must not be relinquished until both CTAs' tcgen05.alloc have returned.  (Relinquishing right after the own
-// alloc, as the single-CTA kernels do, is a race: when the leader's relinquish overtakes the peer's alloc -- seen once
-// in ~8 runs of bench.py, never in isolation -- the peer's alloc blocks forever and the pair spins in its prologue, the
-// leader in barrier.cluster.wait; profiles/r2_hang_beacon.log.)  tmem_relinquish_pair() is therefore called after the
-// cluster barrier that follows the allocation.
+// CTA pair: warp 1 of BOTH CTAs executes the allocation (same warp id, same shared-memory offset for the result: one
+// allocation at the same columns of both CTAs' TMEM).  The allocation permit of a cta_group::2 allocation belongs to the
+// PAIR: relinquishing it right after the own alloc, as the single-CTA kernels do, is a race -- when the leader's
+// relinquish overtakes the peer's alloc (seen once in ~8 runs of bench.py, never in isolation), the peer's alloc blocks
+// forever and the pair spins in its prologue, the leader in barrier.cluster.wait (profiles/r2_hang_beacon.log).  The
+// pair kernel therefore never relinquishes: a persistent conv CTA owns its SM (no other CTA that allocates TMEM fits
+// beside it), so there is nobody to hand the permit to before the CTA exits.
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
                  : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_pair() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t base) {
@@ -1150,7 +1148,6 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     __syncthreads();
     if (threadIdx.x == 0) MSI_BEACON(p, 0, 12);
     if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
-    if (PAIR && warp == 1) tmem_relinquish_pair();  // both CTAs' allocations have returned (see tmem_alloc_pair)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
     const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // stride of the unit loops (clusters)

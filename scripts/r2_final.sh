@@ -22,12 +22,14 @@ except Exception as e:
     print("$f failed", e)
 PY
 done
+if [ -z "$SKIP_NCU_FULL" ]; then
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:conv_ -s 18 -c 18 -f -o gpurun_out/r2_final_conv \
     python scripts/one_forward.py > gpurun_out/r2_final_ncu_conv.log 2>&1
 tail -2 gpurun_out/r2_final_ncu_conv.log
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"psv_gather_pair|render_composite_v2|prep_images|ln_apply" -s 4 -c 8 -f \
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"psv_gather_pair|render_composite_v2|prep_images" -s 3 -c 3 -f \
     -o gpurun_out/r2_final_geom python scripts/one_frame.py > gpurun_out/r2_final_ncu_geom.log 2>&1
 tail -2 gpurun_out/r2_final_ncu_geom.log
+fi
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_final_launches.csv \
     python bench.py --steps 2 --warmup 1 --lanes 1 --no-graph --no-layer-profile --no-cpu-baseline > gpurun_out/r2_final_ncu_list.log 2>&1
 wc -l gpurun_out/r2_final_launches.csv; ls -la gpurun_out/r2_final_conv.ncu-rep gpurun_out/r2_final_geom.ncu-rep

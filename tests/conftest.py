@@ -19,6 +19,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_gpu = False
     if has_gpu:
+        # a stuck GPU kernel must end the tier in bounded time with a stack dump, not hold the box until the caller's limit
+        # (pytest-timeout, method "thread": a thread blocked inside a CUDA call cannot be interrupted by a signal)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(420, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -268,3 +268,39 @@ def test_reference_module_names_resolve():
                        (nets, ["msi_coord_train_net", "msi_train_net"])):
         for n in names:
             assert callable(getattr(mod, n)), (mod.__name__, n)
+
+
+def test_bench_stall_guard_reports_what_was_measured(capfd, monkeypatch):
+    """bench.py's stall guard: no progress for BENCH_STALL_S seconds -> rank 0 prints the line assembled so far, marked
+    partial with the phase it stalled in, and the process ends (exit code 0 when the headline was measured, else 3);
+    progress (phase()) re-arms the clock."""
+    import json
+    import time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    monkeypatch.delenv("RANK", raising=False)
+    exits = []
+    bench._STALL.update({"armed": True, "t": time.time(), "phase": "start", "fallback": None})
+    bench.phase("device-resident regions done")
+    assert bench.stall_guard_tick(limit=150, exit_fn=exits.append) is False and exits == []
+    bench._STALL["fallback"] = {"metric": bench.METRIC, "value": 1000.0, "unit": bench.UNIT, "e2e": None}
+    assert bench.stall_guard_tick(now=time.time() + 200, limit=150, exit_fn=exits.append) is True
+    assert exits == [0]   # the headline was measured: the line is marked partial, the process ends cleanly
+    out = capfd.readouterr().out.strip().splitlines()[-1]
+    line = json.loads(out)
+    assert line["value"] == 1000.0 and line["e2e"] is None
+    assert "stalled" in line["partial"] and "device-resident regions done" in line["partial"]
+    # disarmed after firing: a second tick does nothing
+    assert bench.stall_guard_tick(now=time.time() + 400, limit=150, exit_fn=exits.append) is False
+    # nothing measured yet: still one well-formed line
+    bench._STALL.update({"armed": True, "t": time.time() - 500, "phase": "pipelines built", "fallback": None})
+    assert bench.stall_guard_tick(limit=150, exit_fn=exits.append) is True
+    assert exits[-1] == 3
+    line = json.loads(capfd.readouterr().out.strip().splitlines()[-1])
+    assert line["value"] is None and line["metric"] == bench.METRIC
+    # other ranks end silently
+    monkeypatch.setenv("RANK", "3")
+    bench._STALL.update({"armed": True, "t": time.time() - 500, "phase": "x", "fallback": None})
+    assert bench.stall_guard_tick(limit=150, exit_fn=exits.append) is True
+    assert capfd.readouterr().out.strip() == ""
+    bench._STALL["armed"] = False
