@@ -304,3 +304,109 @@ def test_bench_stall_guard_reports_what_was_measured(capfd, monkeypatch):
     assert bench.stall_guard_tick(limit=150, exit_fn=exits.append) is True
     assert capfd.readouterr().out.strip() == ""
     bench._STALL["armed"] = False
+
+
+def test_bench_run_ours_dry_run_with_the_gpu_layer_stubbed(monkeypatch, capfd):
+    """bench.run_ours end to end with the GPU layer replaced by stand-ins (no CUDA here): every statement of the
+    measurement flow executes -- regions, reductions, stall-guard fallbacks, roofline assembly, the energy block -- and
+    ONE JSON line with the contract's keys comes out.  Guards the bench against a typo that only a GPU box would find."""
+    import contextlib
+    import json
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from matryodshka_b200 import runtime as rt
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 20.0
+
+    class FakeNet:
+        ws_bytes = 900 << 20
+
+    class FakePipe:
+        def __init__(self):
+            self.use_graph, self.fused_rgba, self.static_rig = True, True, True
+            self.net, self.hi, self.lo, self.pred_buf = FakeNet(), None, None, None
+            self.rgba = torch.zeros(4)
+            self.out = {"rgb_u8": torch.arange(12, dtype=torch.uint8)}
+            self.h2d_bytes_per_step, self.d2h_bytes_per_step = 4915200, 1228800
+
+        def step(self):
+            pass
+
+        def stage_times(self, reps=5):
+            return {"psv_build": 0.074, "net": 0.9, "render_composite": 0.066}
+
+    class FakeLanes:
+        def __init__(self, *a, lanes=2, **k):
+            self.lanes = [FakePipe() for _ in range(lanes)]
+            self.streams = [None] * lanes
+            self._n = 0
+
+        def __len__(self):
+            return len(self.lanes)
+
+        def set_inputs(self, *a, **k):
+            pass
+
+        def fork(self):
+            pass
+
+        def join(self):
+            pass
+
+        def step(self, after_compute=None):
+            return self.lanes[0]
+
+        def submit(self, *a, **k):
+            self._n += 1
+
+        def collect(self):
+            self._n -= 1
+            return (self.lanes[0].out["rgb_u8"].clone(), None)
+
+    n_layers = 18
+    scopes = [f"l{i}" for i in range(n_layers - 1)] + ["color_pred"]
+
+    def fake_profile(net, hi_lo, out, reps=3, rgba=None, cold_l2=False):
+        return scopes, np.full(n_layers, 0.045), np.full(n_layers, 0.009), np.ones(n_layers)
+
+    monkeypatch.setattr(rt, "MSIFrameLanes", FakeLanes)
+    monkeypatch.setattr(rt, "profile_net_layers", fake_profile)
+    monkeypatch.setattr(_lib, "launch_count", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(bench, "sustained_energy", lambda *a, **k: {"mJ_per_frame": 987.0, "watts": 950.0})
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    args = types.SimpleNamespace(gpus=1, steps=4, warmup=3, impl="ours", height=32, width=64, planes=32, ngf=64, batch=1,
+                                 conv_impl="tcgen05", precision="fp16_fp8x", lanes=2, gather="auto", no_graph=False,
+                                 no_cpu_baseline=True, no_layer_profile=False)
+    assert bench.run_ours(args) == 0
+    assert bench._STALL["armed"] is False   # disarmed before the line is printed
+    out = [ln for ln in capfd.readouterr().out.strip().splitlines() if ln.startswith("{")]
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "energy"):
+        assert key in line, key
+    assert line["metric"] == bench.METRIC and line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] == 3
+    assert abs(line["value"] - 4 / 20.0e-3) < 1e-6          # 4 frames in the fake 20 ms region
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 4915200
+    assert line["energy"]["mJ_per_frame"] == 987.0
+    assert line["roofline"]["hbm_kernels"]["psv_build"]["frac"] > 0 and "partial" not in line
+    assert line["config"]["frames_in_flight"] == 2 and line["config"]["timed_regions"]["repeats"] == bench.REPEATS
