@@ -396,6 +396,41 @@ def test_bench_run_ours_dry_run_with_the_gpu_layer_stubbed(monkeypatch, capfd):
     args = types.SimpleNamespace(gpus=1, steps=4, warmup=3, impl="ours", height=32, width=64, planes=32, ngf=64, batch=1,
                                  conv_impl="tcgen05", precision="fp16_fp8x", lanes=2, gather="auto", no_graph=False,
                                  no_cpu_baseline=True, no_layer_profile=False)
+    # ---- first the N = 2 flow (rank 0 of a stubbed process group, NCCL form of the gather): reductions, per-rank
+    # medians, no energy block
+    import torch.distributed as dist
+    real_tensor = torch.tensor
+
+    def cpu_tensor(data, *a, **k):
+        k.pop("device", None)
+        return real_tensor(data, *a, **k)
+
+    def fake_all_gather(out_list, t, *a, **k):
+        for o in out_list:
+            o.copy_(t)
+
+    monkeypatch.setattr(torch, "tensor", cpu_tensor)
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_gather", fake_all_gather)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(rt, "all_gather_frames", lambda t, world, group=None: t)
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    args2 = types.SimpleNamespace(**{**vars(args), "gpus": 2, "gather": "nccl"})
+    assert bench.run_ours(args2) == 0
+    out = [ln for ln in capfd.readouterr().out.strip().splitlines() if ln.startswith("{")]
+    assert len(out) == 1
+    line2 = json.loads(out[0])
+    assert line2["n_gpus"] == 2 and abs(line2["value"] - 2 * 4 / 20.0e-3) < 1e-6 and line2["energy"] is None
+    assert len(line2["config"]["timed_regions"]["per_rank_median"]["device_ms_per_step"]) == 2
+    assert "NCCL all_gather" in line2["config"]["collective"] and line2["scaling"] == "weak"
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    # ---- then N = 1
     assert bench.run_ours(args) == 0
     assert bench._STALL["armed"] is False   # disarmed before the line is printed
     out = [ln for ln in capfd.readouterr().out.strip().splitlines() if ln.startswith("{")]
