@@ -80,7 +80,7 @@ def stall_guard_tick(now=None, limit=None, exit_fn=os._exit):
     """One check of the stall guard (separate from the thread so that it can be tested without a GPU).  Returns True when
     it fired."""
     now = time.time() if now is None else now
-    limit = float(os.environ.get("BENCH_STALL_S", "150")) if limit is None else limit
+    limit = float(os.environ.get("BENCH_STALL_S", "120")) if limit is None else limit
     if not _STALL["armed"] or now - _STALL["t"] <= limit:
         return False
     why = f"no progress for {now - _STALL['t']:.0f} s after: {_STALL['phase']}"
@@ -501,7 +501,7 @@ def run_ours(args):
     if world > 1:
         if args.gather != "nccl":
             # ONE symmetric allocation for all lanes (one rendezvous, one multicast object), set up under a time limit:
-            # if it cannot be had within 90 s on EVERY rank, all ranks use the NCCL all-gather instead
+            # if it cannot be had within 75 s on EVERY rank, all ranks use the NCCL all-gather instead (the stall guard allows 120 s)
             box = {}
 
             def setup():
@@ -513,7 +513,7 @@ def run_ours(args):
             phase("setting up the symmetric gathered buffer")
             th = threading.Thread(target=setup, daemon=True)
             th.start()
-            th.join(90.0)
+            th.join(75.0)
             ok = torch.tensor([1 if "g" in box else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 1:
