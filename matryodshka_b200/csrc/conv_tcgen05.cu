@@ -130,6 +130,7 @@ struct TcParams {
     // (beacon_seq, blockIdx.x), so that a stalled launch can be read from the host while the GPU is stuck
     long long* beacon;
     int beacon_seq;
+    int pair_relinquish;  // MSI_PAIR_RELINQUISH=1 (A/B switch): the pair relinquishes its TMEM permit after the prologue's cluster barrier
     // Head fused with the RGBA assembly (MSI.infer_msi `blend_psv`, msi.py:130-147): the epilogue turns a pixel's
     // L blend weights and L alphas into its L RGBA layers, reading the two PSV eyes of that pixel from the net's
     // own input operand (fp16 hi + lo).  rgba == null: the plain head (tanh -> pred).
@@ -407,6 +408,11 @@ template <int COLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
                  : "memory");
+}
+// MSI_PAIR_RELINQUISH=1 only (the form that ran 24 clean bench runs; kept as an A/B switch for scripts/stress_bench.sh):
+// relinquish AFTER the cluster barrier that follows the allocation, when both CTAs' allocs have returned
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t base) {
@@ -1148,6 +1154,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
     __syncthreads();
     if (threadIdx.x == 0) MSI_BEACON(p, 0, 12);
     if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
+    if (PAIR && p.pair_relinquish != 0 && warp == 1) tmem_relinquish_pair();  // (A/B switch; default: never, see tmem_alloc_pair)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
     const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // stride of the unit loops (clusters)
@@ -2211,6 +2218,14 @@ int conv_tc_forward(const LayerPlan& L, int B, float* out, bool after_kernel, cu
     }
     p.beacon = beacon_buffer();
     p.beacon_seq = 0;
+    {
+        static int relq = -1;
+        if (relq < 0) {
+            const char* env = getenv("MSI_PAIR_RELINQUISH");
+            relq = (env && atoi(env) == 1) ? 1 : 0;
+        }
+        p.pair_relinquish = relq;
+    }
     const int cl = plan->cl;
     p.m_tiles = B * p.tiles_x * p.tiles_y;
     p.units_per_col = (p.m_tiles + cl - 1) / cl;
