@@ -570,7 +570,10 @@ def run_ours(args):
     # EXACTLY K steps between the two events, barrier + synchronize on both sides; the region is repeated REPEATS
     # times (a 20-step region is ~20 ms: one scheduling hiccup on one rank moves a single sample by percents) and
     # the line reports the median region, with min / max beside it
-    dev_all = [timed(K, one_step) for _ in range(REPEATS)]
+    dev_all = [timed(K, one_step)]
+    _STALL["fallback"] = fallback_line(reduce_max(dev_all))   # (the first region alone: what a stall in the others would leave)
+    phase("first device-resident region done")
+    dev_all += [timed(K, one_step) for _ in range(REPEATS - 1)]
     phase(f"device-resident regions done: median {statistics.median(dev_all) / K:.4f} ms/step")
     dev_own = list(dev_all)
     dev_red = reduce_max(dev_all)
