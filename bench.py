@@ -68,6 +68,7 @@ def log(*a):
 # progress for BENCH_STALL_S seconds has rank 0 print the line assembled from what WAS measured (marked "partial", with the
 # phase it stalled in) and ends the process (exit code 0 if the headline value is in that line, else 3).
 _STALL = {"t": time.time(), "phase": "start", "fallback": None, "armed": False}
+_CHILDREN = []   # subprocesses to kill when the stall guard ends the process
 
 
 def phase(msg):
@@ -91,6 +92,11 @@ def stall_guard_tick(now=None, limit=None, exit_fn=os._exit):
         line["partial"] = f"stalled: {why}; only what was measured before the stall is reported"
         emit(line)
     _STALL["armed"] = False
+    for proc in list(_CHILDREN):   # (os._exit skips clean-up: do not leave the nvidia-smi sampler running on the box)
+        try:
+            proc.kill()
+        except Exception:
+            pass
     # exit code 0 when the headline was measured (the line says `partial`), 3 when there is nothing to report
     exit_fn(0 if have else 3)
     return True
@@ -171,6 +177,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            _CHILDREN.append(self.proc)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception as e:  # pragma: no cover
