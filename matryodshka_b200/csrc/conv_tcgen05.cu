@@ -1142,6 +1142,12 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap a0, const __grid_co
         if (p.nsrc == 2) prefetch_tmap(&a1);
     }
     if (warp == 2 && lane == 0) prefetch_tmap(&wmap);
+    if (PAIR) {
+        // both CTAs of the pair are running and in step before either issues the pair's TMEM allocation (a cta_group::2
+        // allocation is executed by one warp of EACH CTA; the Blackwell guide: "sync both CTAs before TMEM alloc")
+        __syncthreads();
+        cluster_sync_all();
+    }
     if (warp == 1) {
         if (lane == 0) MSI_BEACON(p, 1, 10);
         if (PAIR)
